@@ -1,0 +1,200 @@
+/* jess_b200.h -- C ABI of the B200-native template-query engine.
+ *
+ * This header is the drop-in boundary for the PyJess hot path
+ *   Jess(templates).query(molecule, rmsd_threshold, distance_cutoff,
+ *                         max_dynamic_distance, ...) -> Hit ...
+ * It replaces the subset of the reference C library that PyJess's Cython
+ * module binds through include/jess/{jess,super,molecule,template,
+ * tess_template,tess_atom,res_index}.pxd.  Every entry point below cites the
+ * reference interface it stands in for (paths relative to the reference
+ * checkout; "eff:" = file after applying patches/<file>.patch).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch/Python types.
+ *   - every function returns JB_OK (0) or a negative jb_status; the text of
+ *     the last error on the calling thread is available via jb_last_error().
+ *   - all *_desc structs are HOST memory, borrowed for the duration of the
+ *     call; handles own their device (HBM) memory.
+ *   - one jb_context per GPU per process (one process per GPU under
+ *     torchrun); all work of a context is issued on one CUDA stream which
+ *     the caller may supply (e.g. torch.cuda.current_stream().cuda_stream).
+ *   - there is NO CPU fallback: if no CUDA device is usable, every entry
+ *     point fails with JB_ERR_CUDA.
+ *
+ * Tokens.  Atom names are the reference's 4-char tokens (blanks -> '_',
+ * eff:Atom.c:17-30), residue names its 3-char tokens followed by NUL
+ * (compared over 4 bytes, eff:TessAtom.h:81-91).  Both travel as uint32,
+ * byte i of the token in bits [8i, 8i+8) (little endian memcpy of char[4]).
+ */
+#ifndef JESS_B200_H
+#define JESS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JB_ABI_VERSION 1
+/* hard limit of the GPU path; larger templates are rejected loudly */
+#define JB_MAX_TEMPLATE_ATOMS 32
+
+typedef enum jb_status {
+    JB_OK = 0,
+    JB_ERR_INVALID = -1,   /* bad argument / unsupported template            */
+    JB_ERR_CUDA = -2,      /* CUDA runtime error or no device                */
+    JB_ERR_NOMEM = -3,     /* host or device allocation failure              */
+    JB_ERR_CAPACITY = -4   /* a single structure overflowed the frontier cap */
+} jb_status;
+
+/* IgnoreType of the reference (eff:Template.h:24-29) */
+typedef enum jb_ignore_chain {
+    JB_IGNORE_NONE = 0,
+    JB_IGNORE_RESIDUES = 1,
+    JB_IGNORE_ATOMS = 2
+} jb_ignore_chain;
+
+/* ---- flat template table --------------------------------------------------
+ * What Template.__init__ builds per template (src/pyjess/_jess.pyx:1825-1912):
+ * n TessAtom records (eff:TessAtom.h:36-49) + the n x n FP64 distance matrix.
+ * Templates are listed in INSERTION order; the engine reports template
+ * indices in that numbering.  TA = atom_offset[n_templates].                 */
+typedef struct jb_template_table {
+    int32_t n_templates;
+    const int32_t *atom_offset;      /* [T+1]  first atom of template t       */
+    const int32_t *match_mode;       /* [TA]   TessAtom.code                  */
+    const int32_t *residue_number;   /* [TA]   TessAtom.resSeq                */
+    const uint8_t *chain_id2;        /* [TA]   TessAtom.chainID2              */
+    const double *position;          /* [TA*3] TessAtom.pos                   */
+    const double *distance_weight;   /* [TA]   TessAtom.distWeight            */
+    const int32_t *name_offset;      /* [TA+1] into atom_names                */
+    const uint32_t *atom_names;      /* 4-char tokens                         */
+    const int32_t *resname_offset;   /* [TA+1] into residue_names             */
+    const uint32_t *residue_names;   /* 3-char tokens + NUL                   */
+    const int64_t *distance_offset;  /* [T+1]  into distances, n*n per tpl    */
+    const double *distances;         /* TessTemplate.distance, row major      */
+} jb_template_table;
+
+/* ---- flat molecule batch ---------------------------------------------------
+ * Structure-of-arrays image of M reference Molecules (eff:Molecule.h:24-30,
+ * struct _Atom eff:Atom.h:29-47).  Only the fields the query path reads.
+ * NA = atom_offset[n_molecules].                                             */
+typedef struct jb_molecule_batch {
+    int32_t n_molecules;
+    const int64_t *atom_offset;      /* [M+1]                                 */
+    const double *x;                 /* [NA] Atom.x[0]                        */
+    const double *y;                 /* [NA] Atom.x[1]                        */
+    const double *z;                 /* [NA] Atom.x[2]                        */
+    const uint32_t *name;            /* [NA] Atom.name[0..3]                  */
+    const uint32_t *residue_name;    /* [NA] Atom.resName[0..3]               */
+    const int32_t *residue_number;   /* [NA] Atom.resSeq                      */
+    const uint8_t *chain_id2;        /* [NA] Atom.chainID2                    */
+} jb_molecule_batch;
+
+/* arguments of Jess.query (src/pyjess/_jess.pyx:2758-2769) that reach the
+ * search; max_candidates is order dependent and not part of this ABI.        */
+typedef struct jb_query_params {
+    double rmsd_threshold;
+    double distance_cutoff;          /* Jess_query t  (eff:Jess.c:119)        */
+    double max_dynamic_distance;     /* Jess_query s                          */
+    int32_t ignore_chain;            /* jb_ignore_chain                       */
+    int32_t reorder;                 /* Scanner_reuse reorder flag            */
+    int32_t best_match;              /* keep min-RMSD hit per (mol, template) */
+    int32_t reserved;
+} jb_query_params;
+
+/* compacted hits, host memory owned by the jb_result they were fetched from.
+ * Canonical order: (molecule, template, atom tuple) ascending.
+ * Record i: atoms[i*stride + k] = index (within its molecule) of the atom
+ * matched to template atom k (JessQuery_atoms, eff:Jess.c:169-174); -1 pad.
+ * rotation/centre0/centre1 as Superposition_rotation / _centroid(0|1)
+ * (vendor/jess/src/Super.c:222-233): x' = R (x - centre0) + centre1.         */
+typedef struct jb_hits {
+    int64_t count;
+    int32_t stride;                  /* max template size of the set          */
+    int32_t reserved;
+    const int32_t *molecule;         /* [count]                               */
+    const int32_t *template_index;   /* [count]                               */
+    const int32_t *atoms;            /* [count*stride]                        */
+    const double *rmsd;              /* [count]                               */
+    const double *rotation;          /* [count*9] row major                   */
+    const double *centre0;           /* [count*3] centroid of matched atoms   */
+    const double *centre1;           /* [count*3] centroid of template atoms  */
+} jb_hits;
+
+/* device-side counters of one query run (define the algorithmic bytes of the
+ * roofline): everything is summed over the pairs of the batch.    */
+typedef struct jb_stats {
+    int64_t pairs;                   /* M*T                                   */
+    int64_t live_pairs;              /* pairs with no empty candidate set     */
+    int64_t candidate_atoms;         /* sum_k |C_k| over live pairs           */
+    int64_t candidate_records;       /* entries in the per-(mol,spec) lists   */
+    int64_t frontier_items;          /* sum_l F_l  (accepted partial matches) */
+    int64_t frontier_ints;           /* sum_l l*F_l                           */
+    int64_t candidate_tests;         /* annulus-join evaluations              */
+    int64_t tuples;                  /* full tuples superposed                */
+    int64_t hits;                    /* tuples passing the RMSD threshold     */
+    int64_t nan_dropped;             /* hits dropped for a NaN rotation       */
+    int64_t chunks;                  /* pair chunks processed                 */
+    int64_t retries;                 /* chunks re-run after a capacity split  */
+    double kernel_ms;                /* device time of the last run (events)  */
+} jb_stats;
+
+typedef struct jb_context jb_context;
+typedef struct jb_templates jb_templates;
+typedef struct jb_molecules jb_molecules;
+typedef struct jb_result jb_result;
+
+/* ---- library -------------------------------------------------------------- */
+int jb_abi_version(void);
+const char *jb_last_error(void);
+int jb_device_count(void);
+
+/* One context per GPU.  `stream` is a cudaStream_t (0/NULL = a private
+ * non-blocking stream).  `workspace_bytes` bounds the frontier workspace in
+ * HBM (0 = default, 1/16 of the device memory).                              */
+int jb_context_create(int device, void *stream, int64_t workspace_bytes,
+                      jb_context **out);
+void jb_context_destroy(jb_context *ctx);
+int jb_context_synchronize(jb_context *ctx);
+
+/* ---- templates: replaces Jess_create + Jess_addTemplate (jess.pxd:18-21,
+ * eff:Jess.c:79-117) and TessTemplate_copy (eff:TessTemplate.c:388-460).
+ * De-duplicates atom specs and uploads the replicated tables to the GPU.     */
+int jb_templates_create(jb_context *ctx, const jb_template_table *table,
+                        jb_templates **out);
+void jb_templates_free(jb_templates *tpl);
+int jb_templates_spec_count(const jb_templates *tpl);
+
+/* ---- molecules: replaces Molecule_* (molecule.pxd:17-21) and
+ * ResIndex_create (res_index.pxd:13, eff:ResIndex.c:28-113).  Copies the SoA
+ * host image (pinned or pageable) to HBM on the context stream.              */
+int jb_molecules_upload(jb_context *ctx, const jb_molecule_batch *batch,
+                        jb_molecules **out);
+void jb_molecules_free(jb_molecules *mol);
+
+/* ---- query: replaces Jess_query + the JessQuery_next loop +
+ * JessQuery_superposition + Superposition_rmsd/rotation/centroid +
+ * the RMSD/NaN filter of Query.__next__ (jess.pxd:21-29, super.pxd:8-14,
+ * src/pyjess/_jess.pyx:2197-2283) for EVERY (molecule, template) pair of the
+ * batch.  Launches the kernels on the context stream and returns without
+ * waiting for them; hits stay in HBM until jb_result_fetch.                  */
+int jb_query_run(jb_context *ctx, const jb_templates *tpl,
+                 const jb_molecules *mol, const jb_query_params *params,
+                 jb_result **out);
+/* Waits for the run, copies the compacted hits to host memory (device->host)
+ * and sorts them canonically.                                                */
+int jb_result_fetch(jb_result *res, jb_hits *out);
+int jb_result_stats(jb_result *res, jb_stats *out);
+void jb_result_free(jb_result *res);
+
+/* End-to-end convenience: upload + run + fetch for host buffers.             */
+int jb_query_host(jb_context *ctx, const jb_templates *tpl,
+                  const jb_molecule_batch *batch,
+                  const jb_query_params *params, jb_result **out,
+                  jb_hits *hits);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JESS_B200_H */

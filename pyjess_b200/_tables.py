@@ -1,0 +1,273 @@
+"""Flat host tables of the C ABI (``include/jess_b200.h``) as ctypes structs.
+
+`TemplateTable` is what `Jess.__init__` hands to ``jb_templates_create``
+(the stand-in for Jess_create/Jess_addTemplate, reference include/jess/jess.pxd:18-21);
+`MoleculeBatch` is the structure-of-arrays image of a list of molecules handed to
+``jb_molecules_upload`` (stand-in for Molecule_* / ResIndex_create).  Both are cut
+out of the numpy storage of `_model` without per-atom Python work.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+
+from ._model import Molecule, Template
+
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_u32p = C.POINTER(C.c_uint32)
+c_u8p = C.POINTER(C.c_uint8)
+c_f64p = C.POINTER(C.c_double)
+
+JB_MAX_TEMPLATE_ATOMS = 32
+IGNORE_CHAIN = {None: 0, "residues": 1, "atoms": 2}
+
+
+class jb_template_table(C.Structure):
+    _fields_ = [
+        ("n_templates", C.c_int32),
+        ("atom_offset", c_i32p),
+        ("match_mode", c_i32p),
+        ("residue_number", c_i32p),
+        ("chain_id2", c_u8p),
+        ("position", c_f64p),
+        ("distance_weight", c_f64p),
+        ("name_offset", c_i32p),
+        ("atom_names", c_u32p),
+        ("resname_offset", c_i32p),
+        ("residue_names", c_u32p),
+        ("distance_offset", c_i64p),
+        ("distances", c_f64p),
+    ]
+
+
+class jb_molecule_batch(C.Structure):
+    _fields_ = [
+        ("n_molecules", C.c_int32),
+        ("atom_offset", c_i64p),
+        ("x", c_f64p),
+        ("y", c_f64p),
+        ("z", c_f64p),
+        ("name", c_u32p),
+        ("residue_name", c_u32p),
+        ("residue_number", c_i32p),
+        ("chain_id2", c_u8p),
+    ]
+
+
+class jb_query_params(C.Structure):
+    _fields_ = [
+        ("rmsd_threshold", C.c_double),
+        ("distance_cutoff", C.c_double),
+        ("max_dynamic_distance", C.c_double),
+        ("ignore_chain", C.c_int32),
+        ("reorder", C.c_int32),
+        ("best_match", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+class jb_hits(C.Structure):
+    _fields_ = [
+        ("count", C.c_int64),
+        ("stride", C.c_int32),
+        ("reserved", C.c_int32),
+        ("molecule", c_i32p),
+        ("template_index", c_i32p),
+        ("atoms", c_i32p),
+        ("rmsd", c_f64p),
+        ("rotation", c_f64p),
+        ("centre0", c_f64p),
+        ("centre1", c_f64p),
+    ]
+
+
+class jb_stats(C.Structure):
+    _fields_ = [
+        ("pairs", C.c_int64),
+        ("live_pairs", C.c_int64),
+        ("candidate_atoms", C.c_int64),
+        ("candidate_records", C.c_int64),
+        ("frontier_items", C.c_int64),
+        ("frontier_ints", C.c_int64),
+        ("candidate_tests", C.c_int64),
+        ("tuples", C.c_int64),
+        ("hits", C.c_int64),
+        ("nan_dropped", C.c_int64),
+        ("chunks", C.c_int64),
+        ("retries", C.c_int64),
+        ("kernel_ms", C.c_double),
+    ]
+
+    def as_dict(self) -> dict:
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+def _ptr(arr: np.ndarray, typ):
+    return arr.ctypes.data_as(typ)
+
+
+class TemplateTable:
+    """Concatenated tables of a template list (insertion order)."""
+
+    def __init__(self, templates: Sequence[Template]):
+        templates = list(templates)
+        self.n_templates = len(templates)
+        sizes = [len(t) for t in templates]
+        self.sizes = np.asarray(sizes, dtype=np.int32)
+        self.max_atoms = max(sizes, default=0)
+        self.atom_offset = np.zeros(self.n_templates + 1, dtype=np.int32)
+        np.cumsum(sizes, out=self.atom_offset[1:])
+        ta = int(self.atom_offset[-1])
+        self.match_mode = np.zeros(ta, dtype=np.int32)
+        self.residue_number = np.zeros(ta, dtype=np.int32)
+        self.chain_id2 = np.zeros(ta, dtype=np.uint8)
+        self.position = np.zeros((ta, 3), dtype=np.float64)
+        self.distance_weight = np.zeros(ta, dtype=np.float64)
+        self.name_offset = np.zeros(ta + 1, dtype=np.int32)
+        self.resname_offset = np.zeros(ta + 1, dtype=np.int32)
+        names, resnames = [], []
+        k = 0
+        for t in templates:
+            for a in t:
+                self.match_mode[k] = a._code
+                self.residue_number[k] = a._resseq
+                self.chain_id2[k] = a._chain2
+                self.position[k] = a._pos
+                self.distance_weight[k] = a._weight
+                nt, rt = a._name_tokens(), a._resname_tokens()
+                names.append(nt)
+                resnames.append(rt)
+                self.name_offset[k + 1] = self.name_offset[k] + len(nt)
+                self.resname_offset[k + 1] = self.resname_offset[k] + len(rt)
+                k += 1
+        self.atom_names = np.concatenate(names).astype("<u4") if names else np.zeros(0, "<u4")
+        self.residue_names = np.concatenate(resnames).astype("<u4") if resnames else np.zeros(0, "<u4")
+        if len(self.atom_names) == 0:
+            self.atom_names = np.zeros(1, "<u4")
+        if len(self.residue_names) == 0:
+            self.residue_names = np.zeros(1, "<u4")
+        self.distance_offset = np.zeros(self.n_templates + 1, dtype=np.int64)
+        np.cumsum([n * n for n in sizes], out=self.distance_offset[1:])
+        dist = [t._dist.reshape(-1) for t in templates]
+        self.distances = np.concatenate(dist) if dist else np.zeros(0, np.float64)
+        if len(self.distances) == 0:
+            self.distances = np.zeros(1, np.float64)
+        self._struct = None
+
+    def as_struct(self) -> jb_template_table:
+        if self._struct is None:
+            s = jb_template_table()
+            s.n_templates = self.n_templates
+            s.atom_offset = _ptr(self.atom_offset, c_i32p)
+            s.match_mode = _ptr(self.match_mode, c_i32p)
+            s.residue_number = _ptr(self.residue_number, c_i32p)
+            s.chain_id2 = _ptr(self.chain_id2, c_u8p)
+            s.position = _ptr(self.position, c_f64p)
+            s.distance_weight = _ptr(self.distance_weight, c_f64p)
+            s.name_offset = _ptr(self.name_offset, c_i32p)
+            s.atom_names = _ptr(self.atom_names, c_u32p)
+            s.resname_offset = _ptr(self.resname_offset, c_i32p)
+            s.residue_names = _ptr(self.residue_names, c_u32p)
+            s.distance_offset = _ptr(self.distance_offset, c_i64p)
+            s.distances = _ptr(self.distances, c_f64p)
+            self._struct = s
+        return self._struct
+
+
+class MoleculeBatch:
+    """Structure-of-arrays image of a list of molecules.
+
+    With ``pinned=True`` the arrays live in page-locked host memory (allocated
+    through torch, which is plumbing only) so that the upload is a true async
+    DMA; this is the staging buffer of SURVEY 7.2 "Host".
+    """
+
+    FIELDS = (("x", np.float64), ("y", np.float64), ("z", np.float64), ("name", np.uint32),
+              ("resname", np.uint32), ("resseq", np.int32), ("chain", np.uint8))
+
+    def __init__(self, molecules: Sequence[Molecule], pinned: bool = False):
+        molecules = list(molecules)
+        self.molecules = molecules
+        self.n_molecules = len(molecules)
+        packs = [m._packed() for m in molecules]
+        counts = [p["n"] for p in packs]
+        self.atom_offset = np.zeros(self.n_molecules + 1, dtype=np.int64)
+        np.cumsum(counts, out=self.atom_offset[1:])
+        total = int(self.atom_offset[-1])
+        self.n_atoms = total
+        self._keep = []
+        for field, dtype in self.FIELDS:
+            buf = self._alloc(max(total, 1), dtype, pinned)
+            if packs:
+                np.concatenate([p[field] for p in packs], out=buf[:total])
+            setattr(self, field, buf)
+        self._struct = None
+
+    def _alloc(self, n, dtype, pinned):
+        if pinned:
+            import torch
+            t = torch.empty(n * np.dtype(dtype).itemsize, dtype=torch.uint8, pin_memory=True)
+            self._keep.append(t)
+            return t.numpy().view(dtype)
+        return np.zeros(n, dtype=dtype)
+
+    @property
+    def nbytes(self) -> int:
+        return int(self.atom_offset.nbytes + sum(getattr(self, f).nbytes for f, _ in self.FIELDS))
+
+    def as_struct(self) -> jb_molecule_batch:
+        if self._struct is None:
+            s = jb_molecule_batch()
+            s.n_molecules = self.n_molecules
+            s.atom_offset = _ptr(self.atom_offset, c_i64p)
+            s.x = _ptr(self.x, c_f64p)
+            s.y = _ptr(self.y, c_f64p)
+            s.z = _ptr(self.z, c_f64p)
+            s.name = _ptr(self.name, c_u32p)
+            s.residue_name = _ptr(self.resname, c_u32p)
+            s.residue_number = _ptr(self.resseq, c_i32p)
+            s.chain_id2 = _ptr(self.chain, c_u8p)
+            self._struct = s
+        return self._struct
+
+
+def query_params(rmsd_threshold, distance_cutoff, max_dynamic_distance, ignore_chain=None,
+                 reorder=True, best_match=False) -> jb_query_params:
+    if ignore_chain not in IGNORE_CHAIN:
+        raise ValueError(f"invalid value for `ignore_chain`: {ignore_chain!r}")
+    return jb_query_params(float(rmsd_threshold), float(distance_cutoff), float(max_dynamic_distance),
+                           IGNORE_CHAIN[ignore_chain], int(bool(reorder)), int(bool(best_match)), 0)
+
+
+class HitTable:
+    """Host copy of a `jb_hits` record set as numpy arrays (canonical order)."""
+
+    __slots__ = ("count", "stride", "molecule", "template", "atoms", "rmsd", "rotation", "centre0", "centre1")
+
+    def __init__(self, hits: jb_hits):
+        n, stride = int(hits.count), int(hits.stride)
+        self.count, self.stride = n, stride
+
+        def grab(ptr, shape, dtype):
+            size = int(np.prod(shape))
+            if n == 0 or size == 0:
+                return np.zeros(shape, dtype=dtype)
+            return np.ctypeslib.as_array(ptr, shape=(size,)).reshape(shape).copy()
+
+        self.molecule = grab(hits.molecule, (n,), np.int32)
+        self.template = grab(hits.template_index, (n,), np.int32)
+        self.atoms = grab(hits.atoms, (n, stride), np.int32)
+        self.rmsd = grab(hits.rmsd, (n,), np.float64)
+        self.rotation = grab(hits.rotation, (n, 3, 3), np.float64)
+        self.centre0 = grab(hits.centre0, (n, 3), np.float64)
+        self.centre1 = grab(hits.centre1, (n, 3), np.float64)
+
+    def keys(self):
+        """Canonical hit identities: (molecule, template, atom-index tuple)."""
+        return [
+            (int(self.molecule[i]), int(self.template[i]), tuple(int(a) for a in self.atoms[i] if a >= 0))
+            for i in range(self.count)
+        ]
