@@ -1,0 +1,202 @@
+"""ctypes binding of the C ABI (include/jess_b200.h) -- the ONLY compute path.
+
+If ``libjess_b200.so`` is missing or no CUDA device is usable this module raises;
+there is deliberately no CPU fallback (BASELINE.json north_star).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Optional
+
+from ._tables import (HitTable, MoleculeBatch, TemplateTable, jb_hits, jb_molecule_batch, jb_query_params,
+                      jb_stats, jb_template_table)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libjess_b200.so")
+
+EXPORTS = [
+    "jb_abi_version", "jb_last_error", "jb_device_count",
+    "jb_context_create", "jb_context_destroy", "jb_context_synchronize",
+    "jb_templates_create", "jb_templates_free", "jb_templates_spec_count",
+    "jb_molecules_upload", "jb_molecules_free",
+    "jb_query_run", "jb_result_fetch", "jb_result_stats", "jb_result_free", "jb_query_host",
+]
+
+_lib = None
+_lock = threading.Lock()
+
+
+class EngineError(RuntimeError):
+    """A C-ABI call failed (status code + jb_last_error text)."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__(f"jess_b200 status {status}: {message}")
+        self.status = status
+
+
+def load_library():
+    """dlopen the engine; raises if it was not built (never falls back)."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise ImportError(
+                    f"{LIB_PATH} not found: build it with `python -m pyjess_b200._build` "
+                    "(there is no CPU fallback)")
+            lib = C.CDLL(LIB_PATH)
+            vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+            P = C.POINTER
+            sig = {
+                "jb_abi_version": (i32, []),
+                "jb_last_error": (C.c_char_p, []),
+                "jb_device_count": (i32, []),
+                "jb_context_create": (i32, [i32, vp, i64, P(vp)]),
+                "jb_context_destroy": (None, [vp]),
+                "jb_context_synchronize": (i32, [vp]),
+                "jb_templates_create": (i32, [vp, P(jb_template_table), P(vp)]),
+                "jb_templates_free": (None, [vp]),
+                "jb_templates_spec_count": (i32, [vp]),
+                "jb_molecules_upload": (i32, [vp, P(jb_molecule_batch), P(vp)]),
+                "jb_molecules_free": (None, [vp]),
+                "jb_query_run": (i32, [vp, vp, vp, P(jb_query_params), P(vp)]),
+                "jb_result_fetch": (i32, [vp, P(jb_hits)]),
+                "jb_result_stats": (i32, [vp, P(jb_stats)]),
+                "jb_result_free": (None, [vp]),
+                "jb_query_host": (i32, [vp, vp, P(jb_molecule_batch), P(jb_query_params), P(vp), P(jb_hits)]),
+            }
+            for name, (res, args) in sig.items():
+                fn = getattr(lib, name)
+                fn.restype, fn.argtypes = res, args
+            _lib = lib
+    return _lib
+
+
+def _check(status: int):
+    if status != 0:
+        raise EngineError(status, load_library().jb_last_error().decode("utf-8", "replace"))
+
+
+class Context:
+    """One engine context = one GPU + one stream (include/jess_b200.h: jb_context)."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None, workspace_bytes: int = 0):
+        self.lib = load_library()
+        self._h = C.c_void_p()
+        _check(self.lib.jb_context_create(int(device), C.c_void_p(stream or 0), int(workspace_bytes), C.byref(self._h)))
+        self.device = int(device)
+
+    def close(self):
+        if self._h:
+            self.lib.jb_context_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        _check(self.lib.jb_context_synchronize(self._h))
+
+
+class DeviceTemplates:
+    def __init__(self, ctx: Context, table: TemplateTable):
+        self.ctx, self.table = ctx, table
+        self._h = C.c_void_p()
+        _check(ctx.lib.jb_templates_create(ctx._h, C.byref(table.as_struct()), C.byref(self._h)))
+
+    @property
+    def spec_count(self) -> int:
+        return int(self.ctx.lib.jb_templates_spec_count(self._h))
+
+    def close(self):
+        if self._h and self.ctx._h:
+            self.ctx.lib.jb_templates_free(self._h)
+        self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceMolecules:
+    def __init__(self, ctx: Context, batch: MoleculeBatch):
+        self.ctx, self.batch = ctx, batch
+        self._h = C.c_void_p()
+        _check(ctx.lib.jb_molecules_upload(ctx._h, C.byref(batch.as_struct()), C.byref(self._h)))
+
+    def close(self):
+        if self._h and self.ctx._h:
+            self.ctx.lib.jb_molecules_free(self._h)
+        self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Result:
+    def __init__(self, ctx: Context, handle):
+        self.ctx, self._h = ctx, handle
+
+    def fetch(self) -> HitTable:
+        hits = jb_hits()
+        _check(self.ctx.lib.jb_result_fetch(self._h, C.byref(hits)))
+        return HitTable(hits)
+
+    def stats(self) -> dict:
+        st = jb_stats()
+        _check(self.ctx.lib.jb_result_stats(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def close(self):
+        if self._h:
+            self.ctx.lib.jb_result_free(self._h)
+        self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def query_run(ctx: Context, templates: DeviceTemplates, molecules: DeviceMolecules, params: jb_query_params) -> Result:
+    """Kernels only: inputs already resident in HBM, hits stay in HBM."""
+    h = C.c_void_p()
+    _check(ctx.lib.jb_query_run(ctx._h, templates._h, molecules._h, C.byref(params), C.byref(h)))
+    return Result(ctx, h)
+
+
+def query_host(ctx: Context, templates: DeviceTemplates, batch: MoleculeBatch, params: jb_query_params):
+    """End to end from host buffers: upload + kernels + hit download.
+    Returns (HitTable, stats)."""
+    h = C.c_void_p()
+    hits = jb_hits()
+    _check(ctx.lib.jb_query_host(ctx._h, templates._h, C.byref(batch.as_struct()), C.byref(params), C.byref(h),
+                                 C.byref(hits)))
+    res = Result(ctx, h)
+    try:
+        return HitTable(hits), res.stats()
+    finally:
+        res.close()
+
+
+_default = {}
+
+
+def default_context(device: Optional[int] = None) -> Context:
+    """Process-wide context per device (LOCAL_RANK picks the GPU under torchrun)."""
+    if device is None:
+        device = int(os.environ.get("JB_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    ctx = _default.get(device)
+    if ctx is None:
+        ctx = _default[device] = Context(device)
+    return ctx

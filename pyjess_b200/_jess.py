@@ -1,0 +1,367 @@
+"""`Jess`, `Query`, `Hit`: the drop-in query API over the CUDA engine.
+
+Mirrors ``src/pyjess/_jess.pyx`` (Jess :2624-2869, Query :2090-2283, Hit :2286-2621).
+Where the reference pulls one tuple at a time out of a depth-first scanner
+(`Query.__next__` -> ``JessQuery_next``), this module runs the whole
+(templates x structures) batch on the GPU in ONE engine call and then iterates the
+compacted hit records lazily:
+
+* `Jess.query(molecule, ...)` is the single-structure special case;
+* `Jess.query_many(molecules, ...)` is the batch entry point: one
+  launch sequence for all structures, one `Query` per structure.
+
+Iteration order: templates in REVERSE insertion order like the reference
+(eff:Jess.c:109-117), hits of one template in canonical atom-tuple order (the
+reference's order is its k-d tree walk; `reorder=True` already changes it there).
+Order-dependent ``max_candidates`` is not reproducible by a breadth-first engine
+and raises `NotImplementedError`.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import io
+import math
+import warnings
+from typing import Iterable, List, Optional, Sequence
+
+import numpy as np
+
+from ._model import Atom, Mat4, Molecule, Template, _format_atom, _transform_points
+from ._tables import HitTable, MoleculeBatch, TemplateTable, query_params
+
+__all__ = ["Jess", "Query", "Hit"]
+
+
+class Hit:
+    """One (template, atom tuple) match with its superposition (_jess.pyx:2286-2621)."""
+
+    __slots__ = ("rmsd", "_rotation", "_centre", "_atoms", "_template", "_molecule")
+
+    def __getstate__(self):
+        return {
+            "rotation": [float(v) for v in self._rotation.reshape(-1)],
+            "centre": [[float(v) for v in row] for row in self._centre],
+            "atoms": self.atoms(transform=False),
+            "rmsd": self.rmsd,
+            "template": self.template(transform=False),
+            "molecule": self.molecule(transform=False),
+        }
+
+    def __setstate__(self, state):
+        self.rmsd = state["rmsd"]
+        self._template = state["template"]
+        self._molecule = state["molecule"]
+        self._rotation = np.asarray(state["rotation"], dtype=np.float64).reshape(3, 3)
+        self._centre = np.asarray(state["centre"], dtype=np.float64).reshape(2, 3)
+        atoms = state["atoms"]
+        if len(atoms) != len(self._template):
+            raise ValueError(f"unexpected number of atoms: {len(atoms)!r} (expected {len(self._template)!r})")
+        self._atoms = np.concatenate([a._rec for a in atoms]) if atoms else np.zeros(0, dtype=self._molecule._atoms.dtype)
+
+    def __reduce__(self):
+        return _rebuild_hit, (self.__getstate__(),)
+
+    # T(c1) . R . T(-c0)  (_jess.pyx:2343-2377)
+    @property
+    def transformation(self) -> Mat4:
+        mc, mr, mv = np.eye(4), np.eye(4), np.eye(4)
+        mc[:3, 3] = -self._centre[0]
+        mr[:3, :3] = self._rotation
+        mv[:3, 3] = self._centre[1]
+        return Mat4(mv) @ Mat4(mr) @ Mat4(mc)
+
+    @property
+    def inverse_transformation(self) -> Mat4:
+        mc, mr, mv = np.eye(4), np.eye(4), np.eye(4)
+        mv[:3, 3] = -self._centre[1]
+        mr[:3, :3] = self._rotation.T
+        mc[:3, 3] = self._centre[0]
+        return Mat4(mc) @ Mat4(mr) @ Mat4(mv)
+
+    @property
+    def determinant(self) -> float:
+        p = self._rotation.reshape(-1)
+        det = 0.0
+        det += p[0] * (p[4] * p[8] - p[5] * p[7])
+        det -= p[1] * (p[3] * p[8] - p[5] * p[6])
+        det += p[2] * (p[3] * p[7] - p[4] * p[6])
+        return float(det)
+
+    @property
+    def log_evalue(self) -> float:
+        return self._template._log_evalue(self.rmsd, len(self._molecule))
+
+    @property
+    def evalue(self) -> float:
+        return math.exp(self.log_evalue)
+
+    def atoms(self, transform: bool = True) -> List[Atom]:
+        recs = self._atoms
+        if transform:
+            recs = recs.copy()
+            recs["x"] = _transform_points(self._atoms["x"].copy(), np.asarray(self.transformation))
+        return [Atom._view(recs[k:k + 1], owner=self) for k in range(len(recs))]
+
+    def molecule(self, transform: bool = False) -> Molecule:
+        if not transform:
+            return self._molecule
+        return self._molecule.transform(self.transformation)
+
+    def template(self, transform: bool = False) -> Template:
+        if not transform:
+            return self._template
+        return self._template.transform(self.inverse_transformation)
+
+    def dumps(self, format: str = "pdb", transform: bool = True) -> str:
+        buf = io.StringIO()
+        self.dump(buf, format=format, transform=transform)
+        return buf.getvalue()
+
+    def dump(self, file, format: str = "pdb", transform: bool = True) -> None:
+        """Same text as the reference / original Jess (_jess.pyx:2541-2621)."""
+        if self._template.id is None:
+            raise RuntimeError("cannot dump `Hit` where `self.template.id` is `None`")
+        if self._molecule.id is None:
+            raise RuntimeError("cannot dump `Hit` where `self.molecule.id` is `None`")
+        file.write("REMARK ")
+        file.write(self._molecule.id)
+        file.write(f" {self.rmsd:5.3f} ")
+        file.write(self._template.id)
+        file.write(f" Det={self.determinant:4,.1f} log(E)~ {self.log_evalue:4.2f}\n")
+        xyz = self._atoms["x"]
+        if transform:
+            xyz = _transform_points(xyz.copy(), np.asarray(self.transformation))
+        for k in range(len(self._atoms)):
+            file.write(_format_atom(self._atoms[k], xyz[k]))
+        file.write("ENDMDL\n")
+
+
+def _rebuild_hit(state):
+    hit = Hit.__new__(Hit)
+    hit.__setstate__(state)
+    return hit
+
+
+class _BatchRun:
+    """Shared, lazily executed engine call of one `query` / `query_many`."""
+
+    __slots__ = ("jess", "molecules", "params_args", "table", "stats", "_slices", "done")
+
+    def __init__(self, jess, molecules, params_args):
+        self.jess = jess
+        self.molecules = molecules
+        self.params_args = params_args
+        self.table: Optional[HitTable] = None
+        self.stats = None
+        self._slices = None
+        self.done = False
+
+    def run(self):
+        if self.done:
+            return
+        self.done = True
+        jess, mols = self.jess, self.molecules
+        if len(jess) == 0 or not mols or all(len(m) == 0 for m in mols) or jess._table.max_atoms == 0:
+            self._slices = [np.zeros(0, dtype=np.int64) for _ in mols]
+            return
+        from . import _capi  # raises if the CUDA engine is missing: no fallback
+        ctx = _capi.default_context()
+        dev_tpl = jess._device_templates(ctx)
+        batch = MoleculeBatch(mols)
+        params = query_params(*self.params_args)
+        self.table, self.stats = _capi.query_host(ctx, dev_tpl, batch, params)
+        if self.stats["nan_dropped"]:
+            warnings.warn("Jess returned a superposition matrix with NaN values", UserWarning, stacklevel=4)
+        t = self.table
+        # iteration order per structure: template DESCENDING (reverse insertion), canonical tuple order within
+        slices = []
+        bounds = np.searchsorted(t.molecule, np.arange(len(mols) + 1))
+        for m in range(len(mols)):
+            idx = np.arange(bounds[m], bounds[m + 1])
+            if len(idx):
+                idx = idx[np.argsort(-t.template[idx], kind="stable")]
+            slices.append(idx)
+        self._slices = slices
+
+    def indices(self, m: int) -> np.ndarray:
+        self.run()
+        return self._slices[m]
+
+
+class Query:
+    """Iterator over the hits of one structure (_jess.pyx:2090-2283)."""
+
+    def __init__(self, jess, molecule, rmsd_threshold, best_match, ignore_chain, max_candidates, run: _BatchRun,
+                 index: int):
+        self.ignore_chain = ignore_chain
+        self.max_candidates = max_candidates
+        self._jess = jess
+        self._molecule = molecule
+        self._rmsd_threshold = float(rmsd_threshold)
+        self._best_match = bool(best_match)
+        self._run = run
+        self._index = index
+        self._pos = 0
+
+    jess = property(lambda self: self._jess)
+    molecule = property(lambda self: self._molecule)
+    rmsd_threshold = property(lambda self: self._rmsd_threshold)
+    best_match = property(lambda self: self._best_match)
+
+    @property
+    def ignore_chain(self):
+        return self._ignore_chain
+
+    @ignore_chain.setter
+    def ignore_chain(self, value):
+        if value not in (None, "residues", "atoms"):
+            raise ValueError(f"invalid value for `ignore_chain`: {value!r}")
+        self._ignore_chain = value
+
+    @property
+    def max_candidates(self):
+        return self._max_candidates
+
+    @max_candidates.setter
+    def max_candidates(self, value):
+        if value is not None and value < 0:
+            raise ValueError(f"invalid value for `max_candidates` argument: {value!r}")
+        self._max_candidates = value
+
+    def __iter__(self):
+        return self
+
+    def __next__(self) -> Hit:
+        if self._max_candidates is not None:
+            raise NotImplementedError(
+                "max_candidates depends on the reference's depth-first k-d tree order and is not "
+                "available on the breadth-first GPU engine; use max_candidates=None")
+        idx = self._run.indices(self._index)
+        if self._pos >= len(idx):
+            raise StopIteration
+        i = int(idx[self._pos])
+        self._pos += 1
+        return self._make_hit(i)
+
+    def _make_hit(self, i: int) -> Hit:
+        t = self._run.table
+        tpl_index = int(t.template[i])
+        template = self._jess._templates[tpl_index]
+        n = len(template)
+        hit = Hit.__new__(Hit)
+        hit.rmsd = float(t.rmsd[i])
+        hit._rotation = t.rotation[i].copy()
+        hit._centre = np.stack([t.centre0[i], t.centre1[i]])
+        hit._atoms = self._molecule._atoms[t.atoms[i, :n]].copy()
+        hit._template = template
+        hit._molecule = self._molecule
+        return hit
+
+    # vectorised access for heavy consumers (no Hit objects)
+    def hit_table(self):
+        """(HitTable, row indices of this structure) of the underlying batch."""
+        return self._run.table, self._run.indices(self._index)
+
+    @property
+    def stats(self):
+        self._run.run()
+        return self._run.stats
+
+
+class Jess:
+    """A set of templates to query structures with (_jess.pyx:2624-2869)."""
+
+    def __init__(self, templates: Iterable[Template] = ()):
+        tpls = []
+        for t in templates:
+            if not isinstance(t, Template):
+                raise TypeError(f"expected Template, found {type(t).__name__}")
+            tpls.append(t)
+        self._templates = tuple(tpls)
+        # the engine works on its own packed copy: later edits of the Template
+        # objects cannot affect it (the reference deep-copies, _jess.pyx:2703-2707)
+        self._table = TemplateTable(self._templates)
+        self._device = {}
+
+    def _device_templates(self, ctx):
+        from . import _capi
+        dev = self._device.get(id(ctx))
+        if dev is None:
+            dev = self._device[id(ctx)] = _capi.DeviceTemplates(ctx, self._table)
+        return dev
+
+    def __copy__(self):
+        return self.copy()
+
+    def __reduce__(self):
+        return type(self), (self._templates,)
+
+    def __eq__(self, other):
+        if not isinstance(other, Jess):
+            return NotImplemented
+        return self._templates == other._templates
+
+    def __hash__(self):
+        return hash((Jess, self._templates))
+
+    def __len__(self):
+        return len(self._templates)
+
+    def __bool__(self):
+        return len(self._templates) > 0
+
+    def __getitem__(self, index):
+        if isinstance(index, slice):
+            return type(self)(self._templates[index])
+        n = len(self._templates)
+        i = int(index)
+        if i < 0:
+            i += n
+        if i < 0 or i >= n:
+            raise IndexError(index)
+        return self._templates[i]
+
+    def __iter__(self):
+        return iter(self._templates)
+
+    def copy(self):
+        return type(self)(self._templates)
+
+    @staticmethod
+    def _normalise_ignore_chain(ignore_chain):
+        if ignore_chain is True:
+            warnings.warn(
+                "`ignore_chain` parameter expects string parameters to specificy the mode since PyJess v0.7.0. "
+                "Use `ignore_chain='atoms'` instead of `ignore_chain=True`", DeprecationWarning, stacklevel=3)
+            return "atoms"
+        if ignore_chain is False:
+            warnings.warn(
+                "`ignore_chain` parameter expects string parameters to specificy the mode since PyJess v0.7.0. "
+                "Use `ignore_chain=None` instead of `ignore_chain=False`", DeprecationWarning, stacklevel=3)
+            return None
+        return ignore_chain
+
+    def query(self, molecule: Molecule, rmsd_threshold: float, distance_cutoff: float, max_dynamic_distance: float, *,
+              max_candidates: Optional[int] = None, ignore_chain=None, best_match: bool = False,
+              reorder: bool = True) -> Query:
+        """Scan one structure (_jess.pyx:2758-2869).  Lazy: the engine runs on the
+        first ``next()``."""
+        return self.query_many([molecule], rmsd_threshold, distance_cutoff, max_dynamic_distance,
+                               max_candidates=max_candidates, ignore_chain=ignore_chain, best_match=best_match,
+                               reorder=reorder)[0]
+
+    def query_many(self, molecules: Sequence[Molecule], rmsd_threshold: float, distance_cutoff: float,
+                   max_dynamic_distance: float, *, max_candidates: Optional[int] = None, ignore_chain=None,
+                   best_match: bool = False, reorder: bool = True) -> List[Query]:
+        """Scan a batch of structures with ONE engine call; returns one `Query`
+        per structure, in input order."""
+        molecules = list(molecules)
+        for m in molecules:
+            if not isinstance(m, Molecule):
+                raise TypeError(f"expected Molecule, found {type(m).__name__}")
+        ignore_chain = self._normalise_ignore_chain(ignore_chain)
+        if ignore_chain not in (None, "residues", "atoms"):
+            raise ValueError(f"invalid value for `ignore_chain`: {ignore_chain!r}")
+        run = _BatchRun(self, molecules,
+                        (rmsd_threshold, distance_cutoff, max_dynamic_distance, ignore_chain, reorder, best_match))
+        return [Query(self, m, rmsd_threshold, best_match, ignore_chain, max_candidates, run, i)
+                for i, m in enumerate(molecules)]

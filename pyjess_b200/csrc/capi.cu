@@ -1,0 +1,698 @@
+// capi.cu -- host side of the C ABI declared in include/jess_b200.h.
+//
+// Owns the HBM layout (DESIGN.md "Data layout"), de-duplicates template-atom
+// specs, drives the kernels of kernels.cuh chunk by chunk on ONE stream with a
+// grow-and-retry protocol for the frontier/candidate/hit buffers, and returns
+// canonically ordered hits.  No CPU fallback: without a CUDA device every entry
+// point fails with JB_ERR_CUDA.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/jess_b200.h"
+#include "kernels.cuh"
+
+using namespace jb;
+
+// ---- errors -------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(e_ == cudaErrorMemoryAllocation ? JB_ERR_NOMEM : JB_ERR_CUDA, "%s: %s (%s:%d)", \
+                        #call, cudaGetErrorString(e_), __FILE__, __LINE__);                             \
+    } while (0)
+
+// ---- device buffers ---------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    // grow-only; contents are NOT preserved unless keep > 0 (bytes to copy over)
+    cudaError_t ensure(size_t need, cudaStream_t st, size_t keep = 0)
+    {
+        if (need <= bytes) return cudaSuccess;
+        size_t nb = std::max(need, bytes + bytes / 2);
+        nb = (nb + 255) & ~(size_t)255;
+        void *q = nullptr;
+        cudaError_t e = cudaMalloc(&q, nb);
+        if (e != cudaSuccess) return e;
+        if (keep && p) {
+            e = cudaMemcpyAsync(q, p, std::min(keep, bytes), cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) { cudaFree(q); return e; }
+            cudaStreamSynchronize(st);
+        }
+        if (p) cudaFree(p);
+        p = q;
+        bytes = nb;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+template <class T> static cudaError_t upload(DevBuf &b, const T *src, size_t n, cudaStream_t st)
+{
+    cudaError_t e = b.ensure(std::max<size_t>(n, 1) * sizeof(T), st);
+    if (e != cudaSuccess) return e;
+    if (n == 0) return cudaSuccess;
+    return cudaMemcpyAsync(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice, st);
+}
+
+// ---- handles ---------------------------------------------------------------------
+struct jb_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    size_t ws_limit = 0;          // bytes the frontier buffers may use in total
+    int group = 8;                // lanes per partial match (JB_GROUP)
+    // workspace (grow only)
+    DevBuf cx, cy, cz, cidx, ccnt, coff, recs, fr[2], tuples, ctr;
+    DevBuf h_mol, h_tpl, h_atoms, h_rmsd, h_rot, h_c0, h_c1;
+    long long hit_cap = 0;
+    int hit_stride = 0;
+    Counters *host_ctr = nullptr; // pinned
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+struct jb_templates {
+    jb_context *ctx = nullptr;
+    int T = 0, TA = 0, S = 0, nmax = 0;
+    std::vector<int> atom_off;
+    DevBuf d_atom_off, d_spec, d_resseq, d_chain, d_pos, d_weight, d_dist_off, d_dist, d_lo2, d_hi2;
+    DevBuf s_code, s_noff, s_nraw, s_nup, s_roff, s_rup;
+    long long n_dist = 0;
+};
+
+struct jb_molecules {
+    jb_context *ctx = nullptr;
+    int M = 0;
+    long long NA = 0;
+    std::vector<long long> atom_off;
+    DevBuf d_off, x, y, z, name, res, resseq, chain;
+};
+
+struct jb_result {
+    jb_context *ctx = nullptr;
+    long long count = 0;      // hits in the device buffers of ctx (valid until the next run)
+    int stride = 0;
+    int best_match = 0;
+    jb_stats stats{};
+    bool fetched = false;
+    std::vector<int32_t> mol, tpl, atoms;
+    std::vector<double> rmsd, rot, c0, c1;
+};
+
+// ---- library -----------------------------------------------------------------------
+extern "C" int jb_abi_version(void) { return JB_ABI_VERSION; }
+extern "C" const char *jb_last_error(void) { return g_err; }
+extern "C" int jb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int jb_context_create(int device, void *stream, int64_t workspace_bytes, jb_context **out)
+{
+    if (!out) return fail(JB_ERR_INVALID, "jb_context_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(JB_ERR_CUDA, "no CUDA device available (%s); the engine has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(JB_ERR_INVALID, "device %d out of range (0..%d)", device, n - 1);
+    CU(cudaSetDevice(device));
+    jb_context *c = new jb_context();
+    c->device = device;
+    if (stream) c->stream = (cudaStream_t)stream;
+    else { CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    c->ws_limit = workspace_bytes > 0 ? (size_t)workspace_bytes : total_b / 8;
+    if (const char *g = getenv("JB_GROUP")) {
+        int v = atoi(g);
+        if (v == 4 || v == 8 || v == 16 || v == 32) c->group = v;
+    }
+    CU(cudaMallocHost(&c->host_ctr, sizeof(Counters)));
+    CU(c->ctr.ensure(sizeof(Counters), c->stream));
+    CU(cudaEventCreate(&c->ev0));
+    CU(cudaEventCreate(&c->ev1));
+    *out = c;
+    return JB_OK;
+}
+
+extern "C" void jb_context_destroy(jb_context *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf *bufs[] = { &c->cx, &c->cy, &c->cz, &c->cidx, &c->ccnt, &c->coff, &c->recs, &c->fr[0], &c->fr[1],
+                       &c->tuples, &c->ctr, &c->h_mol, &c->h_tpl, &c->h_atoms, &c->h_rmsd, &c->h_rot, &c->h_c0,
+                       &c->h_c1 };
+    for (DevBuf *b : bufs) b->release();
+    if (c->host_ctr) cudaFreeHost(c->host_ctr);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int jb_context_synchronize(jb_context *c)
+{
+    if (!c) return fail(JB_ERR_INVALID, "NULL context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return JB_OK;
+}
+
+// ---- templates ------------------------------------------------------------------------
+static uint32_t upper4_host(uint32_t t)
+{
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) {
+        uint32_t c = (t >> (8 * i)) & 0xffu;
+        if (c >= 'a' && c <= 'z') c &= ~0x20u;
+        r |= c << (8 * i);
+    }
+    return r;
+}
+
+static bool mode_valid(int code) { return (code >= -1 && code <= 8) || (code >= 100 && code <= 107); }
+static bool mode_uses_names(int code) { return code == -1 || code == 0 || code == 3 || code == 8 || code == 100 || code == 103; }
+static bool mode_uses_resnames(int code) { return code < 100; }
+
+extern "C" int jb_templates_create(jb_context *c, const jb_template_table *tb, jb_templates **out)
+{
+    if (!c || !tb || !out) return fail(JB_ERR_INVALID, "jb_templates_create: NULL argument");
+    *out = nullptr;
+    CU(cudaSetDevice(c->device));
+    const int T = tb->n_templates;
+    if (T < 0) return fail(JB_ERR_INVALID, "negative template count");
+    jb_templates *t = new jb_templates();
+    t->ctx = c;
+    t->T = T;
+    t->atom_off.assign(tb->atom_offset, tb->atom_offset + T + 1);
+    t->TA = T ? t->atom_off[T] : 0;
+    for (int i = 0; i < T; i++) {
+        const int n = t->atom_off[i + 1] - t->atom_off[i];
+        if (n > JB_MAX_TEMPLATE_ATOMS) {
+            delete t;
+            return fail(JB_ERR_INVALID, "template %d has %d atoms; the GPU path supports at most %d", i, n,
+                        JB_MAX_TEMPLATE_ATOMS);
+        }
+        t->nmax = std::max(t->nmax, n);
+    }
+    // de-duplicate atom specs: (mode, set of names it reads, set of residue names it reads)
+    std::map<std::vector<uint32_t>, int> seen;
+    std::vector<int> spec(t->TA), s_code, s_noff{0}, s_roff{0};
+    std::vector<uint32_t> s_nraw, s_nup, s_rup;
+    for (int a = 0; a < t->TA; a++) {
+        const int code = tb->match_mode[a];
+        if (!mode_valid(code)) { delete t; return fail(JB_ERR_INVALID, "template atom %d: invalid match mode %d", a, code); }
+        std::vector<uint32_t> names, res;
+        if (mode_uses_names(code))
+            names.assign(tb->atom_names + tb->name_offset[a], tb->atom_names + tb->name_offset[a + 1]);
+        if (mode_uses_resnames(code))
+            for (int k = tb->resname_offset[a]; k < tb->resname_offset[a + 1]; k++) res.push_back(upper4_host(tb->residue_names[k]));
+        std::sort(names.begin(), names.end()); names.erase(std::unique(names.begin(), names.end()), names.end());
+        std::sort(res.begin(), res.end()); res.erase(std::unique(res.begin(), res.end()), res.end());
+        std::vector<uint32_t> key{ (uint32_t)code, (uint32_t)names.size() };
+        key.insert(key.end(), names.begin(), names.end());
+        key.insert(key.end(), res.begin(), res.end());
+        auto it = seen.find(key);
+        if (it == seen.end()) {
+            const int id = (int)s_code.size();
+            seen.emplace(key, id);
+            s_code.push_back(code);
+            for (uint32_t v : names) { s_nraw.push_back(v); s_nup.push_back(upper4_host(v)); }
+            for (uint32_t v : res) s_rup.push_back(v);
+            s_noff.push_back((int)s_nraw.size());
+            s_roff.push_back((int)s_rup.size());
+            spec[a] = id;
+        } else spec[a] = it->second;
+    }
+    t->S = (int)s_code.size();
+    t->n_dist = T ? tb->distance_offset[T] : 0;
+    cudaStream_t st = c->stream;
+    std::vector<long long> dist_off(tb->distance_offset, tb->distance_offset + T + 1);
+    cudaError_t e = cudaSuccess;
+#define UP(buf, ptr, n) if (e == cudaSuccess) e = upload(buf, ptr, (size_t)(n), st)
+    UP(t->d_atom_off, t->atom_off.data(), T + 1);
+    UP(t->d_spec, spec.data(), t->TA);
+    UP(t->d_resseq, tb->residue_number, t->TA);
+    UP(t->d_chain, tb->chain_id2, t->TA);
+    UP(t->d_pos, tb->position, 3 * (size_t)t->TA);
+    UP(t->d_weight, tb->distance_weight, t->TA);
+    UP(t->d_dist_off, dist_off.data(), T + 1);
+    UP(t->d_dist, tb->distances, t->n_dist);
+    UP(t->s_code, s_code.data(), s_code.size());
+    UP(t->s_noff, s_noff.data(), s_noff.size());
+    UP(t->s_nraw, s_nraw.data(), s_nraw.size());
+    UP(t->s_nup, s_nup.data(), s_nup.size());
+    UP(t->s_roff, s_roff.data(), s_roff.size());
+    UP(t->s_rup, s_rup.data(), s_rup.size());
+#undef UP
+    if (e == cudaSuccess) e = t->d_lo2.ensure(std::max<size_t>(t->n_dist, 1) * sizeof(double), st);
+    if (e == cudaSuccess) e = t->d_hi2.ensure(std::max<size_t>(t->n_dist, 1) * sizeof(double), st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // host vectors die at return
+    if (e != cudaSuccess) {
+        jb_templates_free(t);
+        return fail(e == cudaErrorMemoryAllocation ? JB_ERR_NOMEM : JB_ERR_CUDA, "template upload: %s", cudaGetErrorString(e));
+    }
+    *out = t;
+    return JB_OK;
+}
+
+extern "C" void jb_templates_free(jb_templates *t)
+{
+    if (!t) return;
+    cudaSetDevice(t->ctx->device);
+    cudaStreamSynchronize(t->ctx->stream);
+    DevBuf *bufs[] = { &t->d_atom_off, &t->d_spec, &t->d_resseq, &t->d_chain, &t->d_pos, &t->d_weight, &t->d_dist_off,
+                       &t->d_dist, &t->d_lo2, &t->d_hi2, &t->s_code, &t->s_noff, &t->s_nraw, &t->s_nup, &t->s_roff,
+                       &t->s_rup };
+    for (DevBuf *b : bufs) b->release();
+    delete t;
+}
+
+extern "C" int jb_templates_spec_count(const jb_templates *t) { return t ? t->S : 0; }
+
+// ---- molecules --------------------------------------------------------------------------
+extern "C" int jb_molecules_upload(jb_context *c, const jb_molecule_batch *b, jb_molecules **out)
+{
+    if (!c || !b || !out) return fail(JB_ERR_INVALID, "jb_molecules_upload: NULL argument");
+    *out = nullptr;
+    CU(cudaSetDevice(c->device));
+    const int M = b->n_molecules;
+    if (M < 0) return fail(JB_ERR_INVALID, "negative molecule count");
+    jb_molecules *m = new jb_molecules();
+    m->ctx = c;
+    m->M = M;
+    m->atom_off.assign(b->atom_offset, b->atom_offset + M + 1);
+    m->NA = M ? m->atom_off[M] : 0;
+    for (int i = 0; i < M; i++)
+        if (m->atom_off[i + 1] < m->atom_off[i] || m->atom_off[i + 1] - m->atom_off[i] > 0x7fffffffLL) {
+            delete m;
+            return fail(JB_ERR_INVALID, "molecule %d: bad atom offsets", i);
+        }
+    cudaStream_t st = c->stream;
+    cudaError_t e = cudaSuccess;
+#define UP(buf, ptr, n) if (e == cudaSuccess) e = upload(buf, ptr, (size_t)(n), st)
+    UP(m->d_off, m->atom_off.data(), M + 1);
+    UP(m->x, b->x, m->NA);
+    UP(m->y, b->y, m->NA);
+    UP(m->z, b->z, m->NA);
+    UP(m->name, b->name, m->NA);
+    UP(m->res, b->residue_name, m->NA);
+    UP(m->resseq, b->residue_number, m->NA);
+    UP(m->chain, b->chain_id2, m->NA);
+#undef UP
+    // the offsets come from a host vector owned by the handle, the rest from caller
+    // memory that must stay valid until the stream reaches the copies: synchronise so
+    // that the caller may reuse its staging buffers immediately.
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        jb_molecules_free(m);
+        return fail(e == cudaErrorMemoryAllocation ? JB_ERR_NOMEM : JB_ERR_CUDA, "molecule upload: %s", cudaGetErrorString(e));
+    }
+    *out = m;
+    return JB_OK;
+}
+
+extern "C" void jb_molecules_free(jb_molecules *m)
+{
+    if (!m) return;
+    cudaSetDevice(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    DevBuf *bufs[] = { &m->d_off, &m->x, &m->y, &m->z, &m->name, &m->res, &m->resseq, &m->chain };
+    for (DevBuf *b : bufs) b->release();
+    delete m;
+}
+
+// ---- query --------------------------------------------------------------------------------
+static size_t expand_smem(int group, int level)
+{
+    const size_t ipw = 32 / group, lpad = level > 0 ? level : 1;
+    const size_t dbl = ipw * lpad * 5, ints = ipw * lpad * 3 + (size_t)kStageItems * (level + 2);
+    return (size_t)kExpandWarps * (dbl * sizeof(double) + ints * sizeof(int));
+}
+
+template <int G> static cudaError_t launch_expand(int grid, size_t smem, cudaStream_t st, const ExpandArgs &a,
+                                                  const TemplateTable &T, const MolTable &M, const CandTable &C)
+{
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_expand<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    k_expand<G><<<grid, kExpandThreads, smem, st>>>(a, T, M, C);
+    return cudaGetLastError();
+}
+
+struct Range { int m0, m1; };
+
+static int grow_hits(jb_context *c, long long need, int stride)
+{
+    if (need <= c->hit_cap && stride == c->hit_stride) return JB_OK;
+    const long long cap = std::max<long long>(need + need / 4, 1 << 16);
+    const size_t keep = (size_t)std::min(c->hit_cap, need);
+    cudaStream_t st = c->stream;
+    const bool same = stride == c->hit_stride;
+    CU(c->h_mol.ensure(cap * sizeof(int), st, same ? keep * sizeof(int) : 0));
+    CU(c->h_tpl.ensure(cap * sizeof(int), st, same ? keep * sizeof(int) : 0));
+    CU(c->h_atoms.ensure(cap * sizeof(int) * stride, st, same ? keep * sizeof(int) * stride : 0));
+    CU(c->h_rmsd.ensure(cap * sizeof(double), st, same ? keep * sizeof(double) : 0));
+    CU(c->h_rot.ensure(cap * 9 * sizeof(double), st, same ? keep * 9 * sizeof(double) : 0));
+    CU(c->h_c0.ensure(cap * 3 * sizeof(double), st, same ? keep * 3 * sizeof(double) : 0));
+    CU(c->h_c1.ensure(cap * 3 * sizeof(double), st, same ? keep * 3 * sizeof(double) : 0));
+    c->hit_cap = cap;
+    c->hit_stride = stride;
+    return JB_OK;
+}
+
+static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecules *mol, const jb_query_params *q,
+                          jb_result *res)
+{
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    jb_stats &S = res->stats;
+    S.pairs = (int64_t)t->T * mol->M;
+    if (t->T == 0 || mol->M == 0 || t->TA == 0) return JB_OK;
+
+    TemplateTable TT;
+    TT.n_templates = t->T;
+    TT.atom_off = t->d_atom_off.as<int>(); TT.spec = t->d_spec.as<int>(); TT.resseq = t->d_resseq.as<int>();
+    TT.chain = t->d_chain.as<unsigned char>(); TT.pos = t->d_pos.as<double>(); TT.weight = t->d_weight.as<double>();
+    TT.dist_off = t->d_dist_off.as<long long>(); TT.dist = t->d_dist.as<double>();
+    TT.lo2 = t->d_lo2.as<double>(); TT.hi2 = t->d_hi2.as<double>();
+    SpecTable ST;
+    ST.n_specs = t->S; ST.code = t->s_code.as<int>(); ST.name_off = t->s_noff.as<int>();
+    ST.name_raw = t->s_nraw.as<uint32_t>(); ST.name_up = t->s_nup.as<uint32_t>();
+    ST.res_off = t->s_roff.as<int>(); ST.res_up = t->s_rup.as<uint32_t>();
+
+    const int tuple_stride = t->nmax + 1;
+    const size_t classify_smem = (size_t)8 * t->S * sizeof(int);
+    if (classify_smem > 200 * 1024)
+        return fail(JB_ERR_INVALID, "%d distinct atom specs exceed the classify kernel's shared memory", t->S);
+    if (classify_smem > 48 * 1024)
+        CU(cudaFuncSetAttribute(k_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)classify_smem));
+
+    CU(cudaEventRecord(c->ev0, st));
+    k_shells<<<t->T, 128, 0, st>>>(TT, q->distance_cutoff, q->max_dynamic_distance);
+    CU(cudaGetLastError());
+
+    // initial capacities (grow on demand, see the retry loop)
+    if (c->fr[0].bytes == 0) {
+        const size_t init = std::min<size_t>(c->ws_limit / 2, (size_t)256 << 20);
+        CU(c->fr[0].ensure(init, st));
+        CU(c->fr[1].ensure(init, st));
+    }
+    if (c->tuples.bytes == 0) CU(c->tuples.ensure((size_t)64 << 20, st));
+    {
+        int rc = grow_hits(c, std::max<long long>(c->hit_cap, 1 << 16), res->stride);
+        if (rc != JB_OK) return rc;
+    }
+
+    // chunk the structures so that pair records and count tables stay bounded
+    const long long max_pairs = 8ll << 20;
+    std::vector<Range> work;
+    {
+        const int per = (int)std::max<long long>(1, max_pairs / std::max(1, t->T));
+        for (int m0 = mol->M; m0 > 0; m0 -= per) work.push_back({ std::max(0, m0 - per), m0 });
+        // processed back to front (pop_back) => ascending structure order
+    }
+    u64 hits_done = 0;
+    int attempts = 0;
+    while (!work.empty()) {
+        const Range r = work.back();
+        const int Mc = r.m1 - r.m0;
+        const long long pairs = (long long)Mc * t->T;
+        MolTable MT;
+        MT.n_molecules = Mc;
+        MT.atom_off = mol->d_off.as<long long>() + r.m0;
+        MT.x = mol->x.as<double>(); MT.y = mol->y.as<double>(); MT.z = mol->z.as<double>();
+        MT.name = mol->name.as<uint32_t>(); MT.res = mol->res.as<uint32_t>();
+        MT.resseq = mol->resseq.as<int>(); MT.chain = mol->chain.as<unsigned char>();
+
+        CU(c->ccnt.ensure((size_t)Mc * t->S * sizeof(int), st));
+        CU(c->coff.ensure((size_t)Mc * t->S * sizeof(long long), st));
+        CU(c->recs.ensure((size_t)pairs * sizeof(PairRec), st));
+        if (c->cidx.bytes == 0) {
+            const long long chunk_atoms = mol->atom_off[r.m1] - mol->atom_off[r.m0];
+            const size_t guess = (size_t)std::max<long long>(chunk_atoms * 4, 1 << 20);
+            CU(c->cx.ensure(guess * sizeof(double), st)); CU(c->cy.ensure(guess * sizeof(double), st));
+            CU(c->cz.ensure(guess * sizeof(double), st)); CU(c->cidx.ensure(guess * sizeof(int), st));
+        }
+        CandTable CT;
+        CT.cnt = c->ccnt.as<int>(); CT.off = c->coff.as<long long>();
+        CT.x = c->cx.as<double>(); CT.y = c->cy.as<double>(); CT.z = c->cz.as<double>(); CT.idx = c->cidx.as<int>();
+        CT.cap = (long long)(c->cidx.bytes / sizeof(int));
+        Counters *dc = c->ctr.as<Counters>();
+
+        // reset counters; the hit cursor continues after the chunks already done
+        memset(c->host_ctr, 0, sizeof(Counters));
+        c->host_ctr->hits = hits_done;
+        CU(cudaMemcpyAsync(dc, c->host_ctr, sizeof(Counters), cudaMemcpyHostToDevice, st));
+
+        k_classify<<<Mc, 256, classify_smem, st>>>(MT, ST, CT, dc);
+        CU(cudaGetLastError());
+        k_pairs<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(Mc, TT, t->S, CT.cnt, q->reorder, c->recs.as<PairRec>(), dc);
+        CU(cudaGetLastError());
+
+        const long long fr_ints[2] = { (long long)(c->fr[0].bytes / sizeof(int)), (long long)(c->fr[1].bytes / sizeof(int)) };
+        const long long tuple_cap = (long long)(c->tuples.bytes / sizeof(int)) / tuple_stride;
+        for (int l = 0; l < t->nmax; l++) {
+            ExpandArgs A;
+            A.level = l; A.n_specs = t->S; A.tuple_stride = tuple_stride;
+            A.recs = c->recs.as<PairRec>();
+            A.in = l == 0 ? nullptr : c->fr[(l - 1) & 1].as<int>();
+            A.in_count = l == 0 ? &dc->live_pairs : &dc->level[l];
+            A.in_cap = l == 0 ? pairs : fr_ints[(l - 1) & 1] / (l + 1);
+            A.out = c->fr[l & 1].as<int>();
+            A.out_count = &dc->level[l + 1];
+            A.out_cap = fr_ints[l & 1] / (l + 2);
+            A.tuples = c->tuples.as<int>(); A.tuple_cap = tuple_cap;
+            A.ignore_chain = q->ignore_chain; A.ctr = dc;
+            const size_t smem = expand_smem(c->group, l);
+            const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(smem, 1)));
+            const int grid = c->sm_count * per_sm;
+            cudaError_t e;
+            switch (c->group) {
+            case 4: e = launch_expand<4>(grid, smem, st, A, TT, MT, CT); break;
+            case 16: e = launch_expand<16>(grid, smem, st, A, TT, MT, CT); break;
+            case 32: e = launch_expand<32>(grid, smem, st, A, TT, MT, CT); break;
+            default: e = launch_expand<8>(grid, smem, st, A, TT, MT, CT); break;
+            }
+            CU(e);
+        }
+        HitBuf HB;
+        HB.mol = c->h_mol.as<int>(); HB.tpl = c->h_tpl.as<int>(); HB.atoms = c->h_atoms.as<int>();
+        HB.rmsd = c->h_rmsd.as<double>(); HB.rot = c->h_rot.as<double>(); HB.c0 = c->h_c0.as<double>();
+        HB.c1 = c->h_c1.as<double>(); HB.cap = c->hit_cap; HB.stride = c->hit_stride;
+        k_superpose<<<c->sm_count * 8, 128, 0, st>>>(c->tuples.as<int>(), &dc->tuples, tuple_cap, tuple_stride,
+                                                    c->recs.as<PairRec>(), TT, MT, r.m0, q->rmsd_threshold, HB, dc);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(c->host_ctr, dc, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        const Counters &hc = *c->host_ctr;
+        attempts++;
+
+        // ---- capacity checks: grow and retry, or split the chunk --------------------
+        bool retry = false, split = false;
+        if ((long long)hc.cand_total > CT.cap) {
+            const size_t need = (size_t)hc.cand_total + (size_t)hc.cand_total / 8;
+            CU(c->cx.ensure(need * sizeof(double), st)); CU(c->cy.ensure(need * sizeof(double), st));
+            CU(c->cz.ensure(need * sizeof(double), st)); CU(c->cidx.ensure(need * sizeof(int), st));
+            retry = true;
+        }
+        if (!retry) {
+            long long need_ints[2] = { 0, 0 };
+            for (int l = 0; l < t->nmax; l++)
+                need_ints[l & 1] = std::max(need_ints[l & 1], (long long)hc.level[l + 1] * (l + 2));
+            for (int b = 0; b < 2; b++)
+                if (need_ints[b] > fr_ints[b]) {
+                    const size_t want = (size_t)(need_ints[b] + need_ints[b] / 2) * sizeof(int);
+                    if (want * 2 > c->ws_limit && Mc > 1) split = true;
+                    else if (want * 2 > c->ws_limit)
+                        return fail(JB_ERR_CAPACITY, "structure %d needs a %zu MiB frontier; raise workspace_bytes", r.m0, want >> 20);
+                    else { CU(c->fr[b].ensure(want, st)); retry = true; }
+                }
+            if ((long long)hc.tuples > tuple_cap) {
+                CU(c->tuples.ensure((size_t)(hc.tuples + hc.tuples / 2) * tuple_stride * sizeof(int), st));
+                retry = true;
+            }
+            if ((long long)hc.hits > c->hit_cap) {
+                int rc = grow_hits(c, (long long)hc.hits, res->stride);
+                if (rc != JB_OK) return rc;
+                retry = true;
+            }
+        }
+        if (split) {
+            work.pop_back();
+            const int mid = r.m0 + Mc / 2;
+            work.push_back({ mid, r.m1 });
+            work.push_back({ r.m0, mid });
+            S.retries++;
+            continue;
+        }
+        if (retry) { S.retries++; continue; }
+
+        // ---- chunk done ------------------------------------------------------------------
+        work.pop_back();
+        hits_done = hc.hits;
+        S.chunks++;
+        S.live_pairs += (int64_t)hc.live_pairs;
+        S.candidate_atoms += (int64_t)hc.cand_atoms;
+        S.candidate_records += (int64_t)hc.cand_total;
+        S.candidate_tests += (int64_t)hc.cand_tests;
+        S.tuples += (int64_t)hc.tuples;
+        S.nan_dropped += (int64_t)hc.nan_dropped;
+        S.frontier_items += (int64_t)hc.tuples;
+        S.frontier_ints += (int64_t)hc.tuple_ints;
+        for (int l = 1; l <= t->nmax; l++) {
+            S.frontier_items += (int64_t)hc.level[l];
+            S.frontier_ints += (int64_t)hc.level[l] * l;
+        }
+        if (hc.unsupported)
+            return fail(JB_ERR_INVALID, "single-atom templates are not supported on the GPU path (%llu pairs)", hc.unsupported);
+    }
+    CU(cudaEventRecord(c->ev1, st));
+    CU(cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    S.kernel_ms = ms;
+    S.hits = (int64_t)hits_done;
+    res->count = (long long)hits_done;
+    (void)attempts;
+    return JB_OK;
+}
+
+extern "C" int jb_query_run(jb_context *c, const jb_templates *t, const jb_molecules *mol, const jb_query_params *q,
+                            jb_result **out)
+{
+    if (!c || !t || !mol || !q || !out) return fail(JB_ERR_INVALID, "jb_query_run: NULL argument");
+    *out = nullptr;
+    if (t->ctx != c || mol->ctx != c) return fail(JB_ERR_INVALID, "templates/molecules belong to another context");
+    if (q->ignore_chain < 0 || q->ignore_chain > 2) return fail(JB_ERR_INVALID, "invalid ignore_chain %d", q->ignore_chain);
+    jb_result *res = new jb_result();
+    res->ctx = c;
+    res->stride = std::max(t->nmax, 1);
+    res->best_match = q->best_match;
+    const int rc = query_run_impl(c, t, mol, q, res);
+    if (rc != JB_OK) { delete res; return rc; }
+    *out = res;
+    return JB_OK;
+}
+
+extern "C" int jb_result_fetch(jb_result *r, jb_hits *out)
+{
+    if (!r || !out) return fail(JB_ERR_INVALID, "jb_result_fetch: NULL argument");
+    jb_context *c = r->ctx;
+    CU(cudaSetDevice(c->device));
+    if (!r->fetched) {
+        const size_t n = (size_t)r->count, stride = (size_t)r->stride;
+        std::vector<int32_t> mol(n), tpl(n), atoms(n * stride);
+        std::vector<double> rmsd(n), rot(n * 9), c0(n * 3), c1(n * 3);
+        if (n) {
+            cudaStream_t st = c->stream;
+            CU(cudaMemcpyAsync(mol.data(), c->h_mol.p, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(tpl.data(), c->h_tpl.p, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(atoms.data(), c->h_atoms.p, n * stride * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(rmsd.data(), c->h_rmsd.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(rot.data(), c->h_rot.p, n * 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(c0.data(), c->h_c0.p, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(c1.data(), c->h_c1.p, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        }
+        // canonical order: (molecule, template, atom tuple)
+        std::vector<size_t> perm(n);
+        std::iota(perm.begin(), perm.end(), (size_t)0);
+        std::sort(perm.begin(), perm.end(), [&](size_t a, size_t b) {
+            if (mol[a] != mol[b]) return mol[a] < mol[b];
+            if (tpl[a] != tpl[b]) return tpl[a] < tpl[b];
+            const int32_t *pa = &atoms[a * stride], *pb = &atoms[b * stride];
+            for (size_t k = 0; k < stride; k++)
+                if (pa[k] != pb[k]) return pa[k] < pb[k];
+            return false;
+        });
+        if (r->best_match) {
+            // keep the smallest RMSD per (molecule, template); ties -> first in canonical
+            // order (the reference keeps the first in ITS iteration order, _jess.pyx:2238)
+            std::vector<size_t> keep;
+            for (size_t i = 0; i < n;) {
+                size_t j = i, best = i;
+                while (j < n && mol[perm[j]] == mol[perm[i]] && tpl[perm[j]] == tpl[perm[i]]) {
+                    if (rmsd[perm[j]] < rmsd[perm[best]]) best = j;
+                    j++;
+                }
+                keep.push_back(perm[best]);
+                i = j;
+            }
+            perm.swap(keep);
+        }
+        const size_t k = perm.size();
+        r->mol.resize(k); r->tpl.resize(k); r->atoms.resize(k * stride);
+        r->rmsd.resize(k); r->rot.resize(k * 9); r->c0.resize(k * 3); r->c1.resize(k * 3);
+        for (size_t i = 0; i < k; i++) {
+            const size_t s = perm[i];
+            r->mol[i] = mol[s]; r->tpl[i] = tpl[s]; r->rmsd[i] = rmsd[s];
+            memcpy(&r->atoms[i * stride], &atoms[s * stride], stride * sizeof(int32_t));
+            memcpy(&r->rot[i * 9], &rot[s * 9], 9 * sizeof(double));
+            memcpy(&r->c0[i * 3], &c0[s * 3], 3 * sizeof(double));
+            memcpy(&r->c1[i * 3], &c1[s * 3], 3 * sizeof(double));
+        }
+        r->fetched = true;
+    }
+    out->count = (int64_t)r->mol.size();
+    out->stride = r->stride;
+    out->reserved = 0;
+    out->molecule = r->mol.data(); out->template_index = r->tpl.data(); out->atoms = r->atoms.data();
+    out->rmsd = r->rmsd.data(); out->rotation = r->rot.data(); out->centre0 = r->c0.data(); out->centre1 = r->c1.data();
+    return JB_OK;
+}
+
+extern "C" int jb_result_stats(jb_result *r, jb_stats *out)
+{
+    if (!r || !out) return fail(JB_ERR_INVALID, "jb_result_stats: NULL argument");
+    *out = r->stats;
+    return JB_OK;
+}
+
+extern "C" void jb_result_free(jb_result *r) { delete r; }
+
+extern "C" int jb_query_host(jb_context *c, const jb_templates *t, const jb_molecule_batch *b, const jb_query_params *q,
+                             jb_result **out, jb_hits *hits)
+{
+    if (!out || !hits) return fail(JB_ERR_INVALID, "jb_query_host: NULL argument");
+    jb_molecules *m = nullptr;
+    int rc = jb_molecules_upload(c, b, &m);
+    if (rc != JB_OK) return rc;
+    rc = jb_query_run(c, t, m, q, out);
+    if (rc == JB_OK) rc = jb_result_fetch(*out, hits);
+    jb_molecules_free(m);
+    if (rc != JB_OK && *out) { jb_result_free(*out); *out = nullptr; }
+    return rc;
+}
