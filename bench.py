@@ -1,0 +1,301 @@
+#!/usr/bin/env python3
+"""bench.py -- template x structure pairs/s of the query hot path on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3|cfg3dense|cfg4shard|cfg5]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference's own CPU path (oracle/_ref)
+
+One "step" = one pass of the hot path (candidate lists -> pair set-up -> frontier
+sweep -> superposition/filter/compaction) over one batch of synthetic structures.
+Workload at N=1: BASELINE config 3 (1,000 M-CSA-shaped templates x 1,000 synthetic
+300-residue proteins = 1e6 pairs/step), the largest single-GPU configuration;
+weak scaling: every rank processes its own 1,000 structures (structures are the
+shard unit, templates replicated, no data-path collective).
+
+Prints ONE JSON line (rank 0).  `value` = pairs/s with inputs resident in HBM,
+`e2e` = the same through the C-ABI call with pinned HOST buffers (upload + kernels
++ hit download inside the timed region), `roofline` = the frontier sweep against the
+measured HBM peak, `cpu_baseline` = the reference C library on this box's cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "template-structure pairs/sec"
+UNIT = "pairs/s"
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own C implementation (oracle/_ref, built from
+    the unmodified sources) on all host cores, on a bounded sample of the workload."""
+    if rank != 0:
+        return
+    import oracle
+    from pyjess_b200 import synth
+    from pyjess_b200._tables import MoleculeBatch, TemplateTable, query_params
+    tpl, mols, params, kw = synth.workload(args.workload)
+    sample = mols[:args.cpu_structures]
+    tt, mb = TemplateTable(tpl), MoleculeBatch(sample)
+    qp = query_params(*params, **kw)
+    cores = host_cores()
+    kind = "reference" if oracle.ref_available() else "port"
+    fn = oracle.ref_query if kind == "reference" else oracle.query
+    for _ in range(args.warmup):
+        fn(tt, mb, qp, threads=cores)
+    times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        hits, st = fn(tt, mb, qp, threads=cores)
+        wall = time.perf_counter() - t0
+        times.append(st["kernel_ms"] / 1e3 if kind == "reference" else wall)
+    pairs = len(tpl) * len(sample)
+    sec = float(np.mean(times))
+    value = pairs / sec
+    desc = f"{len(tpl)} templates x first {len(sample)} structures of {args.workload} per step, query loops only"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "templates": len(tpl), "structures": len(sample),
+                   "thresholds": list(params)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "hits_per_step": int(hits.count),
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg3")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; invalid as a result)")
+    ap.add_argument("--cpu-structures", type=int, default=100, help="structures in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pyjess_b200 import _capi, synth
+    from pyjess_b200._tables import MoleculeBatch, TemplateTable, query_params
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    # ---- inputs (synthetic, seeded; structures differ per rank, templates replicated)
+    tpl, mols, params, kw = synth.workload(args.workload, scale=args.scale, rank=rank)
+    qp = query_params(*params, **kw)
+    stream = torch.cuda.Stream()           # the engine's stream; torch events are recorded on it
+    torch.cuda.set_stream(stream)
+    ctx = _capi.Context(local, stream=stream.cuda_stream)
+    tt = TemplateTable(tpl)
+    dev_tpl = _capi.DeviceTemplates(ctx, tt)
+    batch = MoleculeBatch(mols, pinned=True)
+    dev_mol = _capi.DeviceMolecules(ctx, batch)
+    pairs_rank = len(tpl) * len(mols)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident-input arm (kernels only) -------------------------------------------
+    stats = None
+    for _ in range(args.warmup):
+        res = _capi.query_run(ctx, dev_tpl, dev_mol, qp)
+        stats = res.stats()
+        res.close()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    expand_ms, launches = [], 0
+    t_wall = time.perf_counter()
+    for e0, e1 in evs:
+        flush.zero_()                      # L2 flush between timed iterations
+        e0.record(stream)
+        res = _capi.query_run(ctx, dev_tpl, dev_mol, qp)
+        e1.record(stream)
+        st = res.stats()
+        res.close()
+        expand_ms.append(st["expand_ms"])
+        launches += st["launches"]
+        stats = st
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop()
+    step_ms = float(np.sum([a.elapsed_time(b) for a, b in evs]))
+
+    # ---- end-to-end arm: pinned host buffers -> hits on the host ----------------------
+    for _ in range(2):
+        table, _ = _capi.query_host(ctx, dev_tpl, batch, qp)
+    barrier()
+    ee = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    d2h = 0
+    for e0, e1 in ee:
+        flush.zero_()
+        e0.record(stream)
+        table, _ = _capi.query_host(ctx, dev_tpl, batch, qp)
+        e1.record(stream)
+        d2h = int(table.count) * (8 + 4 * table.stride + 8 * 16)
+    barrier()
+    e2e_ms = float(np.sum([a.elapsed_time(b) for a, b in ee]))
+
+    # ---- reduce over ranks: MAX time, SUM pairs -----------------------------------------
+    red = torch.tensor([step_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(pairs_rank), float(stats["hits"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    step_ms, e2e_ms = float(red[0]), float(red[1])
+    pairs_all, hits_all = float(tot[0]), int(tot[1])
+
+    if rank == 0:
+        value = pairs_all * args.steps / (step_ms / 1e3)
+        e2e = pairs_all * args.steps / (e2e_ms / 1e3)
+        # roofline of the dominant stage (frontier sweep): algorithmic bytes of SURVEY 8d
+        peak, peak_src = measured_peak()
+        alg_bytes = 32.0 * stats["candidate_atoms"] + 8.0 * stats["frontier_ints"]
+        exp_ms = float(np.mean(expand_ms))
+        achieved = alg_bytes / (exp_ms / 1e3) / 1e9
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "templates": len(tpl), "structures_per_gpu": len(mols),
+                       "atoms_per_gpu": int(batch.n_atoms), "pairs_per_step": int(pairs_all),
+                       "thresholds": list(params), "sharding": f"structures x{world}, templates replicated",
+                       "cache": "L2 flushed (512 MiB write) before every timed step", "scale": args.scale},
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": int(batch.nbytes), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_expand (frontier sweep, all levels of one step)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "traffic": None,
+                         "algorithmic_bytes_per_step": alg_bytes, "kernel_ms_per_step": exp_ms,
+                         "share_of_step": exp_ms / max(stats["kernel_ms"], 1e-9)},
+            "stage_ms": {k: stats[k] for k in ("kernel_ms", "classify_ms", "pairs_ms", "expand_ms", "superpose_ms")},
+            "work": {k: stats[k] for k in ("pairs", "live_pairs", "candidate_atoms", "candidate_records",
+                                            "frontier_items", "frontier_ints", "candidate_tests", "tuples", "hits",
+                                            "nan_dropped", "chunks", "retries")},
+            "hits_per_step": hits_all,
+            "wall_s_timed_region": t_wall,
+        }
+        if not args.no_cpu_baseline:
+            import oracle
+            cores = host_cores()
+            sample = mols[:max(1, int(args.cpu_structures * args.scale))]
+            mb = MoleculeBatch(sample)
+            kind = "reference" if oracle.ref_available() else "port"
+            fn = oracle.ref_query if kind == "reference" else oracle.query
+            t0 = time.perf_counter()
+            cpu_hits, cst = fn(tt, mb, qp, threads=cores)
+            wall = time.perf_counter() - t0
+            sec = cst["kernel_ms"] / 1e3 if kind == "reference" else wall
+            out["cpu_baseline"] = {
+                "value": len(tpl) * len(sample) / sec, "unit": UNIT, "cores": cores, "kind": kind,
+                "sample": f"{len(tpl)} templates x first {len(sample)} structures of rank 0 "
+                          f"({len(tpl) * len(sample)} pairs), query loops only, {sec:.2f} s"}
+            # parity of the timed GPU result on that same sample (not timed)
+            keep = table.molecule < len(sample)
+            gpu_keys = sorted(zip(table.molecule[keep].tolist(), table.template[keep].tolist(),
+                                  map(tuple, table.atoms[keep].tolist())))
+            cpu_keys = sorted(zip(cpu_hits.molecule.tolist(), cpu_hits.template.tolist(),
+                                  map(tuple, cpu_hits.atoms.tolist())))
+            out["parity_on_sample"] = "identical hit set" if gpu_keys == cpu_keys else "MISMATCH"
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

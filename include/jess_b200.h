@@ -137,7 +137,12 @@ typedef struct jb_stats {
     int64_t nan_dropped;             /* hits dropped for a NaN rotation       */
     int64_t chunks;                  /* pair chunks processed                 */
     int64_t retries;                 /* chunks re-run after a capacity split  */
-    double kernel_ms;                /* device time of the last run (events)  */
+    int64_t launches;                /* kernels launched by the run           */
+    double kernel_ms;                /* device time of the whole run (events) */
+    double classify_ms;              /* ... of the candidate-list kernel      */
+    double pairs_ms;                 /* ... of the pair set-up kernels        */
+    double expand_ms;                /* ... of the frontier sweep (all levels)*/
+    double superpose_ms;             /* ... of the superposition kernel       */
 } jb_stats;
 
 typedef struct jb_context jb_context;

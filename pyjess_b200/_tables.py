@@ -98,7 +98,12 @@ class jb_stats(C.Structure):
         ("nan_dropped", C.c_int64),
         ("chunks", C.c_int64),
         ("retries", C.c_int64),
+        ("launches", C.c_int64),
         ("kernel_ms", C.c_double),
+        ("classify_ms", C.c_double),
+        ("pairs_ms", C.c_double),
+        ("expand_ms", C.c_double),
+        ("superpose_ms", C.c_double),
     ]
 
     def as_dict(self) -> dict:

@@ -89,7 +89,8 @@ struct jb_context {
     long long hit_cap = 0;
     int hit_stride = 0;
     Counters *host_ctr = nullptr; // pinned
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    struct jb_molecules *scratch_mol = nullptr;   // reused by jb_query_host (no per-call cudaMalloc)
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
 };
 
 struct jb_templates {
@@ -159,6 +160,7 @@ extern "C" int jb_context_create(int device, void *stream, int64_t workspace_byt
     CU(c->ctr.ensure(sizeof(Counters), c->stream));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
+    for (int i = 0; i < 5; i++) CU(cudaEventCreate(&c->evs[i]));
     *out = c;
     return JB_OK;
 }
@@ -172,9 +174,16 @@ extern "C" void jb_context_destroy(jb_context *c)
                        &c->tuples, &c->ctr, &c->h_mol, &c->h_tpl, &c->h_atoms, &c->h_rmsd, &c->h_rot, &c->h_c0,
                        &c->h_c1 };
     for (DevBuf *b : bufs) b->release();
+    if (c->scratch_mol) {
+        jb_molecules *m = c->scratch_mol;
+        DevBuf *mb[] = { &m->d_off, &m->x, &m->y, &m->z, &m->name, &m->res, &m->resseq, &m->chain };
+        for (DevBuf *b : mb) b->release();
+        delete m;
+    }
     if (c->host_ctr) cudaFreeHost(c->host_ctr);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    for (int i = 0; i < 5; i++) if (c->evs[i]) cudaEventDestroy(c->evs[i]);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -300,23 +309,17 @@ extern "C" void jb_templates_free(jb_templates *t)
 extern "C" int jb_templates_spec_count(const jb_templates *t) { return t ? t->S : 0; }
 
 // ---- molecules --------------------------------------------------------------------------
-extern "C" int jb_molecules_upload(jb_context *c, const jb_molecule_batch *b, jb_molecules **out)
+static int fill_molecules(jb_context *c, jb_molecules *m, const jb_molecule_batch *b)
 {
-    if (!c || !b || !out) return fail(JB_ERR_INVALID, "jb_molecules_upload: NULL argument");
-    *out = nullptr;
-    CU(cudaSetDevice(c->device));
     const int M = b->n_molecules;
     if (M < 0) return fail(JB_ERR_INVALID, "negative molecule count");
-    jb_molecules *m = new jb_molecules();
     m->ctx = c;
     m->M = M;
     m->atom_off.assign(b->atom_offset, b->atom_offset + M + 1);
     m->NA = M ? m->atom_off[M] : 0;
     for (int i = 0; i < M; i++)
-        if (m->atom_off[i + 1] < m->atom_off[i] || m->atom_off[i + 1] - m->atom_off[i] > 0x7fffffffLL) {
-            delete m;
+        if (m->atom_off[i + 1] < m->atom_off[i] || m->atom_off[i + 1] - m->atom_off[i] > 0x7fffffffLL)
             return fail(JB_ERR_INVALID, "molecule %d: bad atom offsets", i);
-        }
     cudaStream_t st = c->stream;
     cudaError_t e = cudaSuccess;
 #define UP(buf, ptr, n) if (e == cudaSuccess) e = upload(buf, ptr, (size_t)(n), st)
@@ -329,14 +332,23 @@ extern "C" int jb_molecules_upload(jb_context *c, const jb_molecule_batch *b, jb
     UP(m->resseq, b->residue_number, m->NA);
     UP(m->chain, b->chain_id2, m->NA);
 #undef UP
-    // the offsets come from a host vector owned by the handle, the rest from caller
-    // memory that must stay valid until the stream reaches the copies: synchronise so
-    // that the caller may reuse its staging buffers immediately.
+    // the caller's staging buffers must stay valid until the stream reaches the copies:
+    // synchronise so that they may be reused immediately.
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) {
-        jb_molecules_free(m);
+    if (e != cudaSuccess)
         return fail(e == cudaErrorMemoryAllocation ? JB_ERR_NOMEM : JB_ERR_CUDA, "molecule upload: %s", cudaGetErrorString(e));
-    }
+    return JB_OK;
+}
+
+extern "C" int jb_molecules_upload(jb_context *c, const jb_molecule_batch *b, jb_molecules **out)
+{
+    if (!c || !b || !out) return fail(JB_ERR_INVALID, "jb_molecules_upload: NULL argument");
+    *out = nullptr;
+    CU(cudaSetDevice(c->device));
+    jb_molecules *m = new jb_molecules();
+    m->ctx = c;
+    const int rc = fill_molecules(c, m, b);
+    if (rc != JB_OK) { jb_molecules_free(m); return rc; }
     *out = m;
     return JB_OK;
 }
@@ -423,6 +435,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
     CU(cudaEventRecord(c->ev0, st));
     k_shells<<<t->T, 128, 0, st>>>(TT, q->distance_cutoff, q->max_dynamic_distance);
     CU(cudaGetLastError());
+    S.launches++;
 
     // initial capacities (grow on demand, see the retry loop)
     if (c->fr[0].bytes == 0) {
@@ -477,10 +490,13 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         c->host_ctr->hits = hits_done;
         CU(cudaMemcpyAsync(dc, c->host_ctr, sizeof(Counters), cudaMemcpyHostToDevice, st));
 
+        CU(cudaEventRecord(c->evs[0], st));
         k_classify<<<Mc, 256, classify_smem, st>>>(MT, ST, CT, dc);
         CU(cudaGetLastError());
+        CU(cudaEventRecord(c->evs[1], st));
         k_pairs<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(Mc, TT, t->S, CT.cnt, q->reorder, c->recs.as<PairRec>(), dc);
         CU(cudaGetLastError());
+        CU(cudaEventRecord(c->evs[2], st));
 
         const long long fr_ints[2] = { (long long)(c->fr[0].bytes / sizeof(int)), (long long)(c->fr[1].bytes / sizeof(int)) };
         const long long tuple_cap = (long long)(c->tuples.bytes / sizeof(int)) / tuple_stride;
@@ -508,6 +524,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
             }
             CU(e);
         }
+        CU(cudaEventRecord(c->evs[3], st));
         HitBuf HB;
         HB.mol = c->h_mol.as<int>(); HB.tpl = c->h_tpl.as<int>(); HB.atoms = c->h_atoms.as<int>();
         HB.rmsd = c->h_rmsd.as<double>(); HB.rot = c->h_rot.as<double>(); HB.c0 = c->h_c0.as<double>();
@@ -515,10 +532,17 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         k_superpose<<<c->sm_count * 8, 128, 0, st>>>(c->tuples.as<int>(), &dc->tuples, tuple_cap, tuple_stride,
                                                     c->recs.as<PairRec>(), TT, MT, r.m0, q->rmsd_threshold, HB, dc);
         CU(cudaGetLastError());
+        CU(cudaEventRecord(c->evs[4], st));
         CU(cudaMemcpyAsync(c->host_ctr, dc, sizeof(Counters), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         const Counters &hc = *c->host_ctr;
         attempts++;
+        S.launches += 3 + t->nmax;
+        {
+            float ms[4] = { 0, 0, 0, 0 };
+            for (int i = 0; i < 4; i++) CU(cudaEventElapsedTime(&ms[i], c->evs[i], c->evs[i + 1]));
+            S.classify_ms += ms[0]; S.pairs_ms += ms[1]; S.expand_ms += ms[2]; S.superpose_ms += ms[3];
+        }
 
         // ---- capacity checks: grow and retry, or split the chunk --------------------
         bool retry = false, split = false;
@@ -686,13 +710,14 @@ extern "C" void jb_result_free(jb_result *r) { delete r; }
 extern "C" int jb_query_host(jb_context *c, const jb_templates *t, const jb_molecule_batch *b, const jb_query_params *q,
                              jb_result **out, jb_hits *hits)
 {
-    if (!out || !hits) return fail(JB_ERR_INVALID, "jb_query_host: NULL argument");
-    jb_molecules *m = nullptr;
-    int rc = jb_molecules_upload(c, b, &m);
+    if (!c || !b || !out || !hits) return fail(JB_ERR_INVALID, "jb_query_host: NULL argument");
+    *out = nullptr;
+    CU(cudaSetDevice(c->device));
+    if (!c->scratch_mol) c->scratch_mol = new jb_molecules();
+    int rc = fill_molecules(c, c->scratch_mol, b);      // grow-only device staging owned by the context
     if (rc != JB_OK) return rc;
-    rc = jb_query_run(c, t, m, q, out);
+    rc = jb_query_run(c, t, c->scratch_mol, q, out);
     if (rc == JB_OK) rc = jb_result_fetch(*out, hits);
-    jb_molecules_free(m);
     if (rc != JB_OK && *out) { jb_result_free(*out); *out = nullptr; }
     return rc;
 }
