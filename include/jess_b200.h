@@ -131,7 +131,8 @@ typedef struct jb_stats {
     int64_t candidate_records;       /* entries in the per-(mol,spec) lists   */
     int64_t frontier_items;          /* sum_l F_l  (accepted partial matches) */
     int64_t frontier_ints;           /* sum_l l*F_l                           */
-    int64_t candidate_tests;         /* annulus-join evaluations              */
+    int64_t candidate_tests;         /* (partial match, candidate) evaluations*/
+    int64_t box_survivors;           /* ... passing the FP32 join-box filter  */
     int64_t tuples;                  /* full tuples superposed                */
     int64_t hits;                    /* tuples passing the RMSD threshold     */
     int64_t nan_dropped;             /* hits dropped for a NaN rotation       */

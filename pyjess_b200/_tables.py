@@ -93,6 +93,7 @@ class jb_stats(C.Structure):
         ("frontier_items", C.c_int64),
         ("frontier_ints", C.c_int64),
         ("candidate_tests", C.c_int64),
+        ("box_survivors", C.c_int64),
         ("tuples", C.c_int64),
         ("hits", C.c_int64),
         ("nan_dropped", C.c_int64),

@@ -83,8 +83,10 @@ struct jb_context {
     int sm_count = 148;
     size_t ws_limit = 0;          // bytes the frontier buffers may use in total
     int group = 8;                // lanes per partial match (JB_GROUP)
+    int debug = 0;                // JB_DEBUG: per-level counts and times on stderr
+    cudaEvent_t lev[kMaxN + 1] = {};
     // workspace (grow only)
-    DevBuf cx, cy, cz, cidx, ccnt, coff, recs, fr[2], tuples, ctr;
+    DevBuf crec, chead, mext, recs, fr[2], tuples, ctr;
     DevBuf h_mol, h_tpl, h_atoms, h_rmsd, h_rot, h_c0, h_c1;
     long long hit_cap = 0;
     int hit_stride = 0;
@@ -97,7 +99,7 @@ struct jb_templates {
     jb_context *ctx = nullptr;
     int T = 0, TA = 0, S = 0, nmax = 0;
     std::vector<int> atom_off;
-    DevBuf d_atom_off, d_spec, d_resseq, d_chain, d_pos, d_weight, d_dist_off, d_dist, d_lo2, d_hi2;
+    DevBuf d_atom_off, d_spec, d_resseq, d_chain, d_pos, d_weight, d_dist_off, d_dist, d_shell;
     DevBuf s_code, s_noff, s_nraw, s_nup, s_roff, s_rup;
     long long n_dist = 0;
 };
@@ -107,7 +109,7 @@ struct jb_molecules {
     int M = 0;
     long long NA = 0;
     std::vector<long long> atom_off;
-    DevBuf d_off, x, y, z, name, res, resseq, chain;
+    DevBuf d_off, x, y, z, name, res, resseq, chain, atoms;
 };
 
 struct jb_result {
@@ -156,6 +158,8 @@ extern "C" int jb_context_create(int device, void *stream, int64_t workspace_byt
         int v = atoi(g);
         if (v == 4 || v == 8 || v == 16 || v == 32) c->group = v;
     }
+    if (const char *g = getenv("JB_DEBUG")) c->debug = atoi(g);
+    if (c->debug) for (int i = 0; i <= kMaxN; i++) CU(cudaEventCreate(&c->lev[i]));
     CU(cudaMallocHost(&c->host_ctr, sizeof(Counters)));
     CU(c->ctr.ensure(sizeof(Counters), c->stream));
     CU(cudaEventCreate(&c->ev0));
@@ -170,13 +174,13 @@ extern "C" void jb_context_destroy(jb_context *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = { &c->cx, &c->cy, &c->cz, &c->cidx, &c->ccnt, &c->coff, &c->recs, &c->fr[0], &c->fr[1],
+    DevBuf *bufs[] = { &c->crec, &c->chead, &c->mext, &c->recs, &c->fr[0], &c->fr[1],
                        &c->tuples, &c->ctr, &c->h_mol, &c->h_tpl, &c->h_atoms, &c->h_rmsd, &c->h_rot, &c->h_c0,
                        &c->h_c1 };
     for (DevBuf *b : bufs) b->release();
     if (c->scratch_mol) {
         jb_molecules *m = c->scratch_mol;
-        DevBuf *mb[] = { &m->d_off, &m->x, &m->y, &m->z, &m->name, &m->res, &m->resseq, &m->chain };
+        DevBuf *mb[] = { &m->d_off, &m->x, &m->y, &m->z, &m->name, &m->res, &m->resseq, &m->chain, &m->atoms };
         for (DevBuf *b : mb) b->release();
         delete m;
     }
@@ -283,8 +287,7 @@ extern "C" int jb_templates_create(jb_context *c, const jb_template_table *tb, j
     UP(t->s_roff, s_roff.data(), s_roff.size());
     UP(t->s_rup, s_rup.data(), s_rup.size());
 #undef UP
-    if (e == cudaSuccess) e = t->d_lo2.ensure(std::max<size_t>(t->n_dist, 1) * sizeof(double), st);
-    if (e == cudaSuccess) e = t->d_hi2.ensure(std::max<size_t>(t->n_dist, 1) * sizeof(double), st);
+    if (e == cudaSuccess) e = t->d_shell.ensure(std::max<size_t>(t->n_dist, 1) * sizeof(ShellRec), st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // host vectors die at return
     if (e != cudaSuccess) {
         jb_templates_free(t);
@@ -300,7 +303,7 @@ extern "C" void jb_templates_free(jb_templates *t)
     cudaSetDevice(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
     DevBuf *bufs[] = { &t->d_atom_off, &t->d_spec, &t->d_resseq, &t->d_chain, &t->d_pos, &t->d_weight, &t->d_dist_off,
-                       &t->d_dist, &t->d_lo2, &t->d_hi2, &t->s_code, &t->s_noff, &t->s_nraw, &t->s_nup, &t->s_roff,
+                       &t->d_dist, &t->d_shell, &t->s_code, &t->s_noff, &t->s_nraw, &t->s_nup, &t->s_roff,
                        &t->s_rup };
     for (DevBuf *b : bufs) b->release();
     delete t;
@@ -332,6 +335,13 @@ static int fill_molecules(jb_context *c, jb_molecules *m, const jb_molecule_batc
     UP(m->resseq, b->residue_number, m->NA);
     UP(m->chain, b->chain_id2, m->NA);
 #undef UP
+    if (e == cudaSuccess) e = m->atoms.ensure(std::max<size_t>((size_t)m->NA, 1) * sizeof(AtomRec), st);
+    if (e == cudaSuccess && m->NA > 0) {
+        k_pack_atoms<<<(unsigned)((m->NA + 255) / 256), 256, 0, st>>>(m->NA, m->x.as<double>(), m->y.as<double>(),
+                                                                     m->z.as<double>(), m->resseq.as<int>(),
+                                                                     m->chain.as<unsigned char>(), m->atoms.as<AtomRec>());
+        e = cudaGetLastError();
+    }
     // the caller's staging buffers must stay valid until the stream reaches the copies:
     // synchronise so that they may be reused immediately.
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -358,7 +368,7 @@ extern "C" void jb_molecules_free(jb_molecules *m)
     if (!m) return;
     cudaSetDevice(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
-    DevBuf *bufs[] = { &m->d_off, &m->x, &m->y, &m->z, &m->name, &m->res, &m->resseq, &m->chain };
+    DevBuf *bufs[] = { &m->d_off, &m->x, &m->y, &m->z, &m->name, &m->res, &m->resseq, &m->chain, &m->atoms };
     for (DevBuf *b : bufs) b->release();
     delete m;
 }
@@ -371,8 +381,7 @@ static size_t expand_smem(int group, int level)
     return (size_t)kExpandWarps * (dbl * sizeof(double) + ints * sizeof(int));
 }
 
-template <int G> static cudaError_t launch_expand(int grid, size_t smem, cudaStream_t st, const ExpandArgs &a,
-                                                  const TemplateTable &T, const MolTable &M, const CandTable &C)
+template <int G> static cudaError_t launch_expand(int grid, size_t smem, cudaStream_t st, const ExpandArgs &a)
 {
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
@@ -380,7 +389,7 @@ template <int G> static cudaError_t launch_expand(int grid, size_t smem, cudaStr
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    k_expand<G><<<grid, kExpandThreads, smem, st>>>(a, T, M, C);
+    k_expand<G><<<grid, kExpandThreads, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -419,7 +428,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
     TT.atom_off = t->d_atom_off.as<int>(); TT.spec = t->d_spec.as<int>(); TT.resseq = t->d_resseq.as<int>();
     TT.chain = t->d_chain.as<unsigned char>(); TT.pos = t->d_pos.as<double>(); TT.weight = t->d_weight.as<double>();
     TT.dist_off = t->d_dist_off.as<long long>(); TT.dist = t->d_dist.as<double>();
-    TT.lo2 = t->d_lo2.as<double>(); TT.hi2 = t->d_hi2.as<double>();
+    TT.shell = t->d_shell.as<ShellRec>();
     SpecTable ST;
     ST.n_specs = t->S; ST.code = t->s_code.as<int>(); ST.name_off = t->s_noff.as<int>();
     ST.name_raw = t->s_nraw.as<uint32_t>(); ST.name_up = t->s_nup.as<uint32_t>();
@@ -427,7 +436,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
 
     const int tuple_stride = t->nmax + 1;
     const size_t classify_smem = (size_t)8 * t->S * sizeof(int);
-    if (classify_smem > 200 * 1024)
+    if (classify_smem > 200 * 1024 || t->S > 65535)
         return fail(JB_ERR_INVALID, "%d distinct atom specs exceed the classify kernel's shared memory", t->S);
     if (classify_smem > 48 * 1024)
         CU(cudaFuncSetAttribute(k_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)classify_smem));
@@ -463,26 +472,22 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         const Range r = work.back();
         const int Mc = r.m1 - r.m0;
         const long long pairs = (long long)Mc * t->T;
+        CU(c->chead.ensure((size_t)Mc * t->S * sizeof(CandHead), st));
+        CU(c->mext.ensure((size_t)Mc * sizeof(MolExt), st));
+        CU(c->recs.ensure((size_t)pairs * sizeof(PairRec), st));
+        if (c->crec.bytes == 0) {
+            const long long chunk_atoms = mol->atom_off[r.m1] - mol->atom_off[r.m0];
+            CU(c->crec.ensure((size_t)std::max<long long>(chunk_atoms * 4, 1 << 20) * sizeof(float4), st));
+        }
         MolTable MT;
         MT.n_molecules = Mc;
         MT.atom_off = mol->d_off.as<long long>() + r.m0;
-        MT.x = mol->x.as<double>(); MT.y = mol->y.as<double>(); MT.z = mol->z.as<double>();
+        MT.atoms = mol->atoms.as<AtomRec>();
         MT.name = mol->name.as<uint32_t>(); MT.res = mol->res.as<uint32_t>();
-        MT.resseq = mol->resseq.as<int>(); MT.chain = mol->chain.as<unsigned char>();
-
-        CU(c->ccnt.ensure((size_t)Mc * t->S * sizeof(int), st));
-        CU(c->coff.ensure((size_t)Mc * t->S * sizeof(long long), st));
-        CU(c->recs.ensure((size_t)pairs * sizeof(PairRec), st));
-        if (c->cidx.bytes == 0) {
-            const long long chunk_atoms = mol->atom_off[r.m1] - mol->atom_off[r.m0];
-            const size_t guess = (size_t)std::max<long long>(chunk_atoms * 4, 1 << 20);
-            CU(c->cx.ensure(guess * sizeof(double), st)); CU(c->cy.ensure(guess * sizeof(double), st));
-            CU(c->cz.ensure(guess * sizeof(double), st)); CU(c->cidx.ensure(guess * sizeof(int), st));
-        }
+        MT.ext = c->mext.as<MolExt>();
         CandTable CT;
-        CT.cnt = c->ccnt.as<int>(); CT.off = c->coff.as<long long>();
-        CT.x = c->cx.as<double>(); CT.y = c->cy.as<double>(); CT.z = c->cz.as<double>(); CT.idx = c->cidx.as<int>();
-        CT.cap = (long long)(c->cidx.bytes / sizeof(int));
+        CT.head = c->chead.as<CandHead>(); CT.rec = c->crec.as<float4>();
+        CT.cap = (long long)(c->crec.bytes / sizeof(float4));
         Counters *dc = c->ctr.as<Counters>();
 
         // reset counters; the hit cursor continues after the chunks already done
@@ -494,7 +499,8 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         k_classify<<<Mc, 256, classify_smem, st>>>(MT, ST, CT, dc);
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->evs[1], st));
-        k_pairs<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(Mc, TT, t->S, CT.cnt, q->reorder, c->recs.as<PairRec>(), dc);
+        k_pairs<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(Mc, TT, t->S, CT.head, MT.atom_off, q->reorder,
+                                                                 c->recs.as<PairRec>(), dc);
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->evs[2], st));
 
@@ -502,8 +508,9 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         const long long tuple_cap = (long long)(c->tuples.bytes / sizeof(int)) / tuple_stride;
         for (int l = 0; l < t->nmax; l++) {
             ExpandArgs A;
-            A.level = l; A.n_specs = t->S; A.tuple_stride = tuple_stride;
-            A.recs = c->recs.as<PairRec>();
+            A.level = l; A.n_specs = t->S; A.tuple_stride = tuple_stride; A.ignore_chain = q->ignore_chain;
+            A.recs = c->recs.as<PairRec>(); A.shell = TT.shell; A.atoms = MT.atoms; A.ext = MT.ext;
+            A.head = CT.head; A.cand = CT.rec;
             A.in = l == 0 ? nullptr : c->fr[(l - 1) & 1].as<int>();
             A.in_count = l == 0 ? &dc->live_pairs : &dc->level[l];
             A.in_cap = l == 0 ? pairs : fr_ints[(l - 1) & 1] / (l + 1);
@@ -511,20 +518,22 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
             A.out_count = &dc->level[l + 1];
             A.out_cap = fr_ints[l & 1] / (l + 2);
             A.tuples = c->tuples.as<int>(); A.tuple_cap = tuple_cap;
-            A.ignore_chain = q->ignore_chain; A.ctr = dc;
+            A.ctr = dc;
+            if (c->debug) CU(cudaEventRecord(c->lev[l], st));
             const size_t smem = expand_smem(c->group, l);
             const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(smem, 1)));
             const int grid = c->sm_count * per_sm;
             cudaError_t e;
             switch (c->group) {
-            case 4: e = launch_expand<4>(grid, smem, st, A, TT, MT, CT); break;
-            case 16: e = launch_expand<16>(grid, smem, st, A, TT, MT, CT); break;
-            case 32: e = launch_expand<32>(grid, smem, st, A, TT, MT, CT); break;
-            default: e = launch_expand<8>(grid, smem, st, A, TT, MT, CT); break;
+            case 4: e = launch_expand<4>(grid, smem, st, A); break;
+            case 16: e = launch_expand<16>(grid, smem, st, A); break;
+            case 32: e = launch_expand<32>(grid, smem, st, A); break;
+            default: e = launch_expand<8>(grid, smem, st, A); break;
             }
             CU(e);
         }
         CU(cudaEventRecord(c->evs[3], st));
+        if (c->debug) CU(cudaEventRecord(c->lev[t->nmax], st));
         HitBuf HB;
         HB.mol = c->h_mol.as<int>(); HB.tpl = c->h_tpl.as<int>(); HB.atoms = c->h_atoms.as<int>();
         HB.rmsd = c->h_rmsd.as<double>(); HB.rot = c->h_rot.as<double>(); HB.c0 = c->h_c0.as<double>();
@@ -537,6 +546,16 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         CU(cudaStreamSynchronize(st));
         const Counters &hc = *c->host_ctr;
         attempts++;
+        if (c->debug) {
+            fprintf(stderr, "[jb] chunk [%d,%d) live=%llu cand=%llu tests=%llu box=%llu tuples=%llu\n", r.m0, r.m1,
+                    hc.live_pairs, hc.cand_total, hc.cand_tests, hc.box_pass, hc.tuples);
+            for (int l = 0; l < t->nmax; l++) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, c->lev[l], c->lev[l + 1]);
+                fprintf(stderr, "[jb]   level %2d: in=%12llu out=%12llu  %8.3f ms\n", l,
+                        l == 0 ? hc.live_pairs : hc.level[l], hc.level[l + 1], ms);
+            }
+        }
         S.launches += 3 + t->nmax;
         {
             float ms[4] = { 0, 0, 0, 0 };
@@ -548,8 +567,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         bool retry = false, split = false;
         if ((long long)hc.cand_total > CT.cap) {
             const size_t need = (size_t)hc.cand_total + (size_t)hc.cand_total / 8;
-            CU(c->cx.ensure(need * sizeof(double), st)); CU(c->cy.ensure(need * sizeof(double), st));
-            CU(c->cz.ensure(need * sizeof(double), st)); CU(c->cidx.ensure(need * sizeof(int), st));
+            CU(c->crec.ensure(need * sizeof(float4), st));
             retry = true;
         }
         if (!retry) {
@@ -592,6 +610,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         S.candidate_atoms += (int64_t)hc.cand_atoms;
         S.candidate_records += (int64_t)hc.cand_total;
         S.candidate_tests += (int64_t)hc.cand_tests;
+        S.box_survivors += (int64_t)hc.box_pass;
         S.tuples += (int64_t)hc.tuples;
         S.nan_dropped += (int64_t)hc.nan_dropped;
         S.frontier_items += (int64_t)hc.tuples;

@@ -47,6 +47,7 @@ struct SpecTable {            // de-duplicated template-atom specs
     const uint32_t *res_up;   // upper-cased residue tokens
 };
 
+struct ShellRec;
 struct TemplateTable {
     int n_templates;
     const int *atom_off;       // [T+1]
@@ -57,32 +58,54 @@ struct TemplateTable {
     const double *weight;      // [TA]
     const long long *dist_off; // [T+1]
     const double *dist;        // n*n per template
-    double *lo2;               // same layout as dist: [earlier*n + later]
-    double *hi2;
+    ShellRec *shell;           // same layout as dist: [earlier*n + later]
+};
+
+struct alignas(32) AtomRec {   // one 32-byte sector per gathered atom
+    double x, y, z;
+    int resseq;
+    int chain;
+};
+
+struct alignas(32) MolExt {    // frame of the FP32 candidate records of one structure
+    double ox, oy, oz;         // origin (first atom)
+    double ext;                // max |coordinate - origin| over the structure
 };
 
 struct MolTable {
     int n_molecules;           // of the chunk
     const long long *atom_off; // [M+1] (chunk view, absolute atom offsets)
-    const double *x, *y, *z;
+    const AtomRec *atoms;      // packed at upload by k_pack_atoms
     const uint32_t *name, *res;
-    const int *resseq;
-    const unsigned char *chain;
+    MolExt *ext;               // [M] chunk-local, written by k_classify
+};
+
+struct alignas(16) CandHead {  // one candidate list = one (structure, spec)
+    long long off;
+    int cnt;
+    int pad;
 };
 
 struct CandTable {
-    int *cnt;                  // [M*S]
-    long long *off;            // [M*S] into the arrays below
-    double *x, *y, *z;
-    int *idx;                  // atom index within its molecule
+    CandHead *head;            // [M*S]
+    float4 *rec;               // {x-ox, y-oy, z-oz, atom index bits}: FP32 is ONLY a conservative prefilter
     long long cap;             // capacity (records)
 };
 
-struct alignas(16) PairRec {   // one live (structure, template) pair
+struct alignas(32) ShellRec {  // constraint of an ORDERED template-atom pair (earlier i, later k)
+    double lo2, hi2;           // squared shell radii (eff:Scanner.c:275-290, eff:Annulus.c:40-67)
+    int flags;                 // bit0: same template chain, bit1: same template residue number
+    int pad;
+};
+
+struct alignas(16) PairRec {   // one live (structure, template) pair, 128 bytes
     int m;                     // structure index within the chunk
     int t;                     // template index
     int ta0;                   // first template atom
     int n;                     // template size
+    long long abase;           // first atom of the structure
+    long long shell0;          // first ShellRec of the template
+    unsigned short spec[kMaxN];// spec id of the atom scanned at level l
     unsigned char order[kMaxN];// scan order (eff:Scanner.c:88-99,160-174)
 };
 
@@ -90,7 +113,8 @@ struct Counters {              // device counters of one chunk attempt
     u64 cand_total;            // records reserved in CandTable
     u64 live_pairs;
     u64 cand_atoms;            // sum_k |C_k| over live pairs
-    u64 cand_tests;            // annulus-join evaluations
+    u64 cand_tests;            // (partial match, candidate) evaluations
+    u64 box_pass;              // ... that survived the FP32 join-box prefilter
     u64 tuples;                // full tuples produced
     u64 tuple_ints;            // sum of their sizes
     u64 hits;                  // hits written (absolute, across chunks)
@@ -181,20 +205,40 @@ __device__ __forceinline__ bool spec_match(const SpecTable &S, int s, uint32_t n
     return ok;
 }
 
+// ---- K0: atom records ---------------------------------------------------------
+// Runs once per upload: SoA host image -> one 32-byte record per atom, so that every
+// later gather of an atom costs exactly one sector.
+__global__ void __launch_bounds__(256) k_pack_atoms(long long n, const double *x, const double *y, const double *z,
+                                                    const int *resseq, const unsigned char *chain, AtomRec *out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    AtomRec r;
+    r.x = x[i]; r.y = y[i]; r.z = z[i];
+    r.resseq = resseq[i];
+    r.chain = (int)chain[i];
+    out[i] = r;
+}
+
 // ---- K1: candidate lists ------------------------------------------------------
 // One CTA per structure.  Warp w owns a contiguous slice of the atoms; pass 1
 // counts matches per (warp, spec) in shared memory, a scan over warps gives every
 // warp its write offset, pass 2 re-evaluates and writes the records in ascending
-// atom order (deterministic lists).  List placement in the record arrays is
-// reserved with one atomicAdd per (structure, spec).
+// atom order (deterministic lists).  List placement in the record array is
+// reserved with one atomicAdd per (structure, spec).  Pass 1 also measures the
+// extent of the structure around its first atom: the FP32 records are stored
+// relative to that origin and the extent bounds their rounding error.
 __global__ void __launch_bounds__(256) k_classify(MolTable M, SpecTable S, CandTable C, Counters *ctr)
 {
     extern __shared__ int sh_cnt[];                 // [warps][S]
+    __shared__ double sh_ext[8];
     const int m = blockIdx.x;
     const int nw = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ns = S.n_specs;
     const long long a0 = M.atom_off[m], a1 = M.atom_off[m + 1];
     const int na = (int)(a1 - a0);
+    double ox = 0.0, oy = 0.0, oz = 0.0, ext = 0.0;
+    if (na > 0) { const AtomRec o = M.atoms[a0]; ox = o.x; oy = o.y; oz = o.z; }
     // slice boundaries in multiples of 32 atoms
     const int chunks = (na + 31) >> 5;
     const int c_lo = (int)(((long long)chunks * w) / nw), c_hi = (int)(((long long)chunks * (w + 1)) / nw);
@@ -206,10 +250,15 @@ __global__ void __launch_bounds__(256) k_classify(MolTable M, SpecTable S, CandT
             const int a = (c << 5) + lane;
             const bool valid = a < na;
             uint32_t name = 0, name_up = 0, res_up = 0;
+            float4 rec = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid) {
                 name = M.name[a0 + a];
                 name_up = upper4(name);
                 res_up = upper4(M.res[a0 + a]);
+                const AtomRec ar = M.atoms[a0 + a];
+                const double dx = __dsub_rn(ar.x, ox), dy = __dsub_rn(ar.y, oy), dz = __dsub_rn(ar.z, oz);
+                if (pass == 0) ext = fmax(ext, fmax(fabs(dx), fmax(fabs(dy), fabs(dz))));
+                rec = make_float4(__double2float_rn(dx), __double2float_rn(dy), __double2float_rn(dz), __int_as_float(a));
             }
             for (int s = 0; s < ns; s++) {
                 const bool ok = valid && spec_match(S, s, name, name_up, res_up);
@@ -220,13 +269,8 @@ __global__ void __launch_bounds__(256) k_classify(MolTable M, SpecTable S, CandT
                 } else {
                     const int base = mine[s];
                     if (ok) {
-                        const long long dst = C.off[(long long)m * ns + s] + base + __popc(mask & ((1u << lane) - 1));
-                        if (dst < C.cap) {
-                            C.idx[dst] = a;
-                            C.x[dst] = M.x[a0 + a];
-                            C.y[dst] = M.y[a0 + a];
-                            C.z[dst] = M.z[a0 + a];
-                        }
+                        const long long dst = C.head[(long long)m * ns + s].off + base + __popc(mask & ((1u << lane) - 1));
+                        if (dst < C.cap) C.rec[dst] = rec;
                     }
                     __syncwarp();
                     if (lane == 0) mine[s] = base + __popc(mask);
@@ -235,7 +279,15 @@ __global__ void __launch_bounds__(256) k_classify(MolTable M, SpecTable S, CandT
             }
         }
         if (pass == 0) {
+            for (int o = 16; o > 0; o >>= 1) ext = fmax(ext, __shfl_xor_sync(0xffffffffu, ext, o));
+            if (lane == 0) sh_ext[w] = ext;
             __syncthreads();
+            if (threadIdx.x == 0) {
+                double e = 0.0;
+                for (int v = 0; v < nw; v++) e = fmax(e, sh_ext[v]);
+                MolExt me; me.ox = ox; me.oy = oy; me.oz = oz; me.ext = e;
+                M.ext[m] = me;
+            }
             // exclusive scan over warps, reserve the list, publish count/offset
             for (int s = threadIdx.x; s < ns; s += blockDim.x) {
                 int run = 0;
@@ -244,10 +296,9 @@ __global__ void __launch_bounds__(256) k_classify(MolTable M, SpecTable S, CandT
                     sh_cnt[v * ns + s] = run;
                     run += c;
                 }
-                long long off = 0;
-                if (run > 0) off = (long long)atomicAdd(&ctr->cand_total, (u64)run);
-                C.cnt[(long long)m * ns + s] = run;
-                C.off[(long long)m * ns + s] = off;
+                CandHead h; h.off = 0; h.cnt = run; h.pad = 0;
+                if (run > 0) h.off = (long long)atomicAdd(&ctr->cand_total, (u64)run);
+                C.head[(long long)m * ns + s] = h;
             }
             __syncthreads();
         }
@@ -255,7 +306,7 @@ __global__ void __launch_bounds__(256) k_classify(MolTable M, SpecTable S, CandT
 }
 
 // ---- K: shell radii ------------------------------------------------------------
-// lo2/hi2[earlier i][later k]: the ORDERED pair matters because the dynamic
+// shell[earlier i][later k]: the ORDERED pair matters because the dynamic
 // threshold is summed left to right as (cutoff + w[i]) + w[k] (eff:Scanner.c:279).
 __global__ void k_shells(TemplateTable T, double cutoff, double max_dyn)
 {
@@ -272,8 +323,12 @@ __global__ void k_shells(TemplateTable T, double cutoff, double max_dyn)
         if (b < a) { const double tmp = b; b = a; a = tmp; }   // eff:Annulus.c:46-51
         if (a < 0.0) a = 0.0;
         if (b < 0.0) b = 0.0;
-        T.lo2[d0 + e] = __dmul_rn(a, a);
-        T.hi2[d0 + e] = __dmul_rn(b, b);
+        ShellRec r;
+        r.lo2 = __dmul_rn(a, a);
+        r.hi2 = __dmul_rn(b, b);
+        r.flags = ((T.chain[ta0 + i] == T.chain[ta0 + k]) ? 1 : 0) | ((T.resseq[ta0 + i] == T.resseq[ta0 + k]) ? 2 : 0);
+        r.pad = 0;
+        T.shell[d0 + e] = r;
     }
 }
 
@@ -281,8 +336,8 @@ __global__ void k_shells(TemplateTable T, double cutoff, double max_dyn)
 // Thread per (structure, template).  A pair is live iff every candidate set is
 // non-empty (eff:Scanner.c:145-149); the scan order is argsort(|C_k|, k)
 // (eff:Scanner.c:88-99) or the identity when reorder is off.
-__global__ void __launch_bounds__(256) k_pairs(int n_mol, TemplateTable T, int n_specs, const int *c_cnt, int reorder,
-                                               PairRec *recs, Counters *ctr)
+__global__ void __launch_bounds__(256) k_pairs(int n_mol, TemplateTable T, int n_specs, const CandHead *heads,
+                                               const long long *atom_off, int reorder, PairRec *recs, Counters *ctr)
 {
     const long long total = (long long)n_mol * T.n_templates;
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -299,7 +354,7 @@ __global__ void __launch_bounds__(256) k_pairs(int n_mol, TemplateTable T, int n
         n = T.atom_off[t + 1] - ta0;
         live = n >= 1;
         for (int k = 0; k < n; k++) {
-            const int c = c_cnt[(long long)m * n_specs + T.spec[ta0 + k]];
+            const int c = heads[(long long)m * n_specs + T.spec[ta0 + k]].cnt;
             cnts[k] = c;
             live = live && (c > 0);
             sum += (u64)c;
@@ -320,7 +375,6 @@ __global__ void __launch_bounds__(256) k_pairs(int n_mol, TemplateTable T, int n
     }
     const unsigned mask = __ballot_sync(0xffffffffu, live);
     const int lane = threadIdx.x & 31;
-    // warp totals for the statistics
     u64 wsum = live ? sum : 0;
     for (int o = 16; o > 0; o >>= 1) wsum += __shfl_down_sync(0xffffffffu, wsum, o);
     const unsigned smask = __ballot_sync(0xffffffffu, single);
@@ -334,10 +388,14 @@ __global__ void __launch_bounds__(256) k_pairs(int n_mol, TemplateTable T, int n
     }
     base = __shfl_sync(0xffffffffu, base, 0);
     if (live) {
-        PairRec r;
-        r.m = m; r.t = t; r.ta0 = ta0; r.n = n;
-        for (int k = 0; k < kMaxN; k++) r.order[k] = k < n ? ord[k] : 0;
-        recs[base + __popc(mask & ((1u << lane) - 1))] = r;
+        PairRec *r = recs + base + __popc(mask & ((1u << lane) - 1));
+        r->m = m; r->t = t; r->ta0 = ta0; r->n = n;
+        r->abase = atom_off[m];
+        r->shell0 = T.dist_off[t];
+        for (int k = 0; k < kMaxN; k++) {
+            r->order[k] = k < n ? ord[k] : 0;
+            r->spec[k] = k < n ? (unsigned short)T.spec[ta0 + ord[k]] : 0;
+        }
     }
 }
 
@@ -346,7 +404,13 @@ struct ExpandArgs {
     int level;                   // l = atoms already placed in the input items
     int n_specs;
     int tuple_stride;            // ints per tuple record: 1 + max template size
+    int ignore_chain;
     const PairRec *recs;
+    const ShellRec *shell;
+    const AtomRec *atoms;
+    const MolExt *ext;
+    const CandHead *head;
+    const float4 *cand;
     const int *in;               // items [lp, a_0..a_{l-1}], stride l+1 (unused for l==0)
     const u64 *in_count;         // items available (may exceed in_cap after an overflow)
     long long in_cap;
@@ -355,7 +419,6 @@ struct ExpandArgs {
     long long out_cap;           // items
     int *tuples;
     long long tuple_cap;         // records
-    int ignore_chain;
     Counters *ctr;
 };
 
@@ -375,11 +438,17 @@ __device__ __forceinline__ bool pair_consistent(int ignore, bool mol_same_chain,
 }
 
 // G lanes cooperate on one partial match; a warp handles 32/G of them at a time.
-// Per warp shared memory: scratch for the already-placed atoms of its items and a
-// staging buffer where surviving children are compacted (ballot + prefix popcount)
-// before being flushed to the next frontier with ONE global atomicAdd per flush.
+//  1. the lanes of a group stage the already-placed atoms (one 32-byte AtomRec and
+//     one 32-byte ShellRec each) into shared memory and reduce the axis-aligned box
+//     of the annulus join (the reference's Join_computeBox, eff:Join.c:82-111) with
+//     group shuffles, in FP32, rounded OUTWARD by the record error bound;
+//  2. they stride the candidate list: one LDG.128 + six FP32 compares per candidate;
+//  3. only box survivors take the exact FP64 predicate (_Annulus_po,
+//     eff:Annulus.h:54-68, explicit RN ops, no FMA) and the chain/residue rules;
+//  4. survivors are compacted (ballot + prefix popcount) into a per-warp staging
+//     buffer that is flushed to the next frontier with ONE global atomicAdd.
 template <int G>
-__global__ void __launch_bounds__(kExpandThreads) k_expand(ExpandArgs A, TemplateTable T, MolTable M, CandTable C)
+__global__ void __launch_bounds__(kExpandThreads, 2) k_expand(const ExpandArgs A)
 {
     constexpr int IPW = 32 / G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -402,40 +471,56 @@ __global__ void __launch_bounds__(kExpandThreads) k_expand(ExpandArgs A, Templat
     u64 n_in = *A.in_count;
     if (l > 0 && (long long)n_in > A.in_cap) n_in = (u64)A.in_cap;
     const long long total_warps = (long long)gridDim.x * kExpandWarps;
-    u64 tests = 0;
+    unsigned tests = 0, boxed = 0;
+    const float INF = __int_as_float(0x7f800000);
 
     for (long long base_item = ((long long)blockIdx.x * kExpandWarps + warp) * IPW; base_item < (long long)n_in;
          base_item += total_warps * IPW) {
         const long long item = base_item + grp;
         const bool valid = item < (long long)n_in;
-        int lp = 0, m = 0, ta0 = 0, n = 0, k = 0, cnt = 0;
+        int lp = 0, n = 0, k = 0, cnt = 0;
         long long coff = 0, abase = 0;
-        const PairRec *rec = nullptr;
-        if (valid) {
-            lp = l == 0 ? (int)item : A.in[item * in_stride];
-            rec = A.recs + lp;
-            m = rec->m; ta0 = rec->ta0; n = rec->n;
-            k = rec->order[l];
-            const long long ci = (long long)m * A.n_specs + T.spec[ta0 + k];
-            cnt = C.cnt[ci];
-            coff = C.off[ci];
-            abase = M.atom_off[m];
-        }
+        float bx0 = -INF, by0 = -INF, bz0 = -INF, bx1 = INF, by1 = INF, bz1 = INF;
         __syncwarp();   // previous iteration's readers are done with the scratch
         if (valid) {
-            const long long e0 = T.dist_off[rec->t];
-            for (int j = gl; j < l; j += G) {
-                const int a = A.in[item * in_stride + 1 + j];
-                const long long ga = abase + a;
-                const int oj = rec->order[j];
-                sa[j] = a;
-                sx[j] = M.x[ga]; sy[j] = M.y[ga]; sz[j] = M.z[ga];
-                slo[j] = T.lo2[e0 + (long long)oj * n + k];
-                shi[j] = T.hi2[e0 + (long long)oj * n + k];
-                sres[j] = M.resseq[ga];
-                sflag[j] = (int)M.chain[ga] | ((T.chain[ta0 + oj] == T.chain[ta0 + k]) ? 0x100 : 0) |
-                           ((T.resseq[ta0 + oj] == T.resseq[ta0 + k]) ? 0x200 : 0);
+            lp = l == 0 ? (int)item : A.in[item * in_stride];
+            const PairRec *rec = A.recs + lp;
+            const int4 h0 = *reinterpret_cast<const int4 *>(rec);            // m, t, ta0, n
+            const longlong2 h1 = *reinterpret_cast<const longlong2 *>(&rec->abase);
+            n = h0.w;
+            abase = h1.x;
+            k = rec->order[l];
+            const CandHead hd = A.head[(long long)h0.x * A.n_specs + rec->spec[l]];
+            cnt = hd.cnt;
+            coff = hd.off;
+            if (l > 0) {
+                const MolExt me = A.ext[h0.x];
+                const double err = me.ext * 2.4e-7 + 1e-30;                  // > ext * 2^-22: record rounding
+                for (int j = gl; j < l; j += G) {
+                    const int a = A.in[item * in_stride + 1 + j];
+                    const AtomRec ar = A.atoms[abase + a];
+                    const ShellRec sh = A.shell[h1.y + (long long)rec->order[j] * n + k];
+                    sa[j] = a;
+                    sx[j] = ar.x; sy[j] = ar.y; sz[j] = ar.z;
+                    slo[j] = sh.lo2; shi[j] = sh.hi2;
+                    sres[j] = ar.resseq;
+                    sflag[j] = ar.chain | (sh.flags << 8);
+                    // outer radius, rounded up with a generous relative margin
+                    const double b = __dmul_ru(__dsqrt_ru(sh.hi2), 1.000000001);
+                    bx0 = fmaxf(bx0, __double2float_rd(__dsub_rd(__dsub_rd(__dsub_rd(ar.x, b), me.ox), err)));
+                    by0 = fmaxf(by0, __double2float_rd(__dsub_rd(__dsub_rd(__dsub_rd(ar.y, b), me.oy), err)));
+                    bz0 = fmaxf(bz0, __double2float_rd(__dsub_rd(__dsub_rd(__dsub_rd(ar.z, b), me.oz), err)));
+                    bx1 = fminf(bx1, __double2float_ru(__dadd_ru(__dsub_ru(__dadd_ru(ar.x, b), me.ox), err)));
+                    by1 = fminf(by1, __double2float_ru(__dadd_ru(__dsub_ru(__dadd_ru(ar.y, b), me.oy), err)));
+                    bz1 = fminf(bz1, __double2float_ru(__dadd_ru(__dsub_ru(__dadd_ru(ar.z, b), me.oz), err)));
+                }
             }
+        }
+#pragma unroll
+        for (int o = G >> 1; o > 0; o >>= 1) {   // join box = intersection over the placed atoms
+            bx0 = fmaxf(bx0, __shfl_xor_sync(0xffffffffu, bx0, o)); bx1 = fminf(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
+            by0 = fmaxf(by0, __shfl_xor_sync(0xffffffffu, by0, o)); by1 = fminf(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+            bz0 = fmaxf(bz0, __shfl_xor_sync(0xffffffffu, bz0, o)); bz1 = fminf(bz1, __shfl_xor_sync(0xffffffffu, bz1, o));
         }
         __syncwarp();
         const int maxcnt = __reduce_max_sync(0xffffffffu, cnt);
@@ -445,22 +530,24 @@ __global__ void __launch_bounds__(kExpandThreads) k_expand(ExpandArgs A, Templat
             bool ok = valid && c < cnt;
             int a = 0;
             if (ok) {
-                if (l > 0) tests++;
-                const double px = C.x[coff + c], py = C.y[coff + c], pz = C.z[coff + c];
+                tests++;
+                const float4 cr = __ldg(A.cand + coff + c);
+                a = __float_as_int(cr.w);
+                ok = cr.x >= bx0 && cr.x <= bx1 && cr.y >= by0 && cr.y <= by1 && cr.z >= bz0 && cr.z <= bz1;
+            }
+            if (ok && l > 0) {
+                boxed++;
+                const AtomRec p = A.atoms[abase + a];
                 // _Annulus_po (eff:Annulus.h:54-68): ((dx^2 + dy^2) + dz^2), centre - point
                 for (int j = 0; j < l; j++) {
-                    const double t0 = __dsub_rn(sx[j], px), t1 = __dsub_rn(sy[j], py), t2 = __dsub_rn(sz[j], pz);
+                    const double t0 = __dsub_rn(sx[j], p.x), t1 = __dsub_rn(sy[j], p.y), t2 = __dsub_rn(sz[j], p.z);
                     const double s = __dadd_rn(__dadd_rn(__dmul_rn(t0, t0), __dmul_rn(t1, t1)), __dmul_rn(t2, t2));
                     if (s < slo[j] || s > shi[j]) { ok = false; break; }
                 }
                 if (ok) {
-                    a = C.idx[coff + c];
-                    const long long ga = abase + a;
-                    const int r = M.resseq[ga];
-                    const int ch = (int)M.chain[ga];
                     for (int j = 0; j < l; j++) {
                         const int f = sflag[j];
-                        if (!pair_consistent(A.ignore_chain, (f & 0xff) == ch, (f & 0x100) != 0, sres[j] == r,
+                        if (!pair_consistent(A.ignore_chain, (f & 0xff) == p.chain, (f & 0x100) != 0, sres[j] == p.resseq,
                                              (f & 0x200) != 0)) { ok = false; break; }
                     }
                 }
@@ -521,8 +608,15 @@ __global__ void __launch_bounds__(kExpandThreads) k_expand(ExpandArgs A, Templat
         }
     }
     // statistics: one atomic per warp
-    for (int o = 16; o > 0; o >>= 1) tests += __shfl_down_sync(0xffffffffu, tests, o);
-    if (lane == 0 && tests) atomicAdd(&A.ctr->cand_tests, tests);
+    u64 t64 = tests, b64 = boxed;
+    for (int o = 16; o > 0; o >>= 1) {
+        t64 += __shfl_down_sync(0xffffffffu, t64, o);
+        b64 += __shfl_down_sync(0xffffffffu, b64, o);
+    }
+    if (lane == 0 && t64) {
+        if (l > 0) atomicAdd(&A.ctr->cand_tests, t64);
+        atomicAdd(&A.ctr->box_pass, b64);
+    }
 }
 
 // ---- K4: superposition ----------------------------------------------------------------
@@ -585,20 +679,20 @@ __global__ void __launch_bounds__(128) k_superpose(const int *tuples, const u64 
         rec = recs + tp[0];
         n = rec->n;
         for (int lv = 0; lv < n; lv++) inv[rec->order[lv]] = (unsigned char)lv;
-        const long long abase = M.atom_off[rec->m];
+        const long long abase = rec->abase;
         const double *tpos = T.pos + 3ll * rec->ta0;
         for (int j = 0; j < 3; j++) ca[j] = cb[j] = 0.0;
         for (int k = n - 1; k >= 0; k--) {
-            const long long ga = abase + tp[1 + inv[k]];
-            ca[0] += M.x[ga]; ca[1] += M.y[ga]; ca[2] += M.z[ga];
+            const AtomRec ar = M.atoms[abase + tp[1 + inv[k]]];
+            ca[0] += ar.x; ca[1] += ar.y; ca[2] += ar.z;
             cb[0] += tpos[3 * k]; cb[1] += tpos[3 * k + 1]; cb[2] += tpos[3 * k + 2];
         }
         for (int j = 0; j < 3; j++) { ca[j] /= (double)n; cb[j] /= (double)n; }
         double sa = 0.0, sb = 0.0, X[9];
         for (int j = 0; j < 9; j++) X[j] = 0.0;
         for (int k = n - 1; k >= 0; k--) {
-            const long long ga = abase + tp[1 + inv[k]];
-            const double a[3] = { M.x[ga] - ca[0], M.y[ga] - ca[1], M.z[ga] - ca[2] };
+            const AtomRec ar = M.atoms[abase + tp[1 + inv[k]]];
+            const double a[3] = { ar.x - ca[0], ar.y - ca[1], ar.z - ca[2] };
             const double b[3] = { tpos[3 * k] - cb[0], tpos[3 * k + 1] - cb[1], tpos[3 * k + 2] - cb[2] };
 #pragma unroll
             for (int j = 0; j < 3; j++) {
