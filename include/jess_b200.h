@@ -98,7 +98,10 @@ typedef struct jb_query_params {
     double distance_cutoff;          /* Jess_query t  (eff:Jess.c:119)        */
     double max_dynamic_distance;     /* Jess_query s                          */
     int32_t ignore_chain;            /* jb_ignore_chain                       */
-    int32_t reorder;                 /* Scanner_reuse reorder flag            */
+    int32_t reorder;                 /* scan order: 0 template order, 1 the
+                                      * reference's (Scanner_reuse reorder flag,
+                                      * eff:Scanner.c:88-99), 2 the engine's own
+                                      * fan-out heuristic; the hit SET is the same */
     int32_t best_match;              /* keep min-RMSD hit per (mol, template) */
     int32_t reserved;
 } jb_query_params;
@@ -132,6 +135,7 @@ typedef struct jb_stats {
     int64_t frontier_items;          /* sum_l F_l  (accepted partial matches) */
     int64_t frontier_ints;           /* sum_l l*F_l                           */
     int64_t candidate_tests;         /* (partial match, candidate) evaluations*/
+    int64_t scan_tests;              /* FP32 box tests executed after x-range narrowing */
     int64_t box_survivors;           /* ... passing the FP32 join-box filter  */
     int64_t tuples;                  /* full tuples superposed                */
     int64_t hits;                    /* tuples passing the RMSD threshold     */

@@ -149,7 +149,7 @@ class Result:
     def fetch(self) -> HitTable:
         hits = jb_hits()
         _check(self.ctx.lib.jb_result_fetch(self._h, C.byref(hits)))
-        return HitTable(hits)
+        return HitTable(hits, owner=self)      # zero-copy views; the table keeps this result alive
 
     def stats(self) -> dict:
         st = jb_stats()
@@ -183,10 +183,7 @@ def query_host(ctx: Context, templates: DeviceTemplates, batch: MoleculeBatch, p
     _check(ctx.lib.jb_query_host(ctx._h, templates._h, C.byref(batch.as_struct()), C.byref(params), C.byref(h),
                                  C.byref(hits)))
     res = Result(ctx, h)
-    try:
-        return HitTable(hits), res.stats()
-    finally:
-        res.close()
+    return HitTable(hits, owner=res), res.stats()
 
 
 _default = {}

@@ -93,6 +93,7 @@ class jb_stats(C.Structure):
         ("frontier_items", C.c_int64),
         ("frontier_ints", C.c_int64),
         ("candidate_tests", C.c_int64),
+        ("scan_tests", C.c_int64),
         ("box_survivors", C.c_int64),
         ("tuples", C.c_int64),
         ("hits", C.c_int64),
@@ -242,26 +243,36 @@ class MoleculeBatch:
 
 def query_params(rmsd_threshold, distance_cutoff, max_dynamic_distance, ignore_chain=None,
                  reorder=True, best_match=False) -> jb_query_params:
+    """`reorder`: True -> 1 (the reference's argsort by |C_k|), False -> 0 (template
+    order); an int selects the mode explicitly (2 = experimental fan-out heuristic).
+    The hit set never depends on it."""
     if ignore_chain not in IGNORE_CHAIN:
         raise ValueError(f"invalid value for `ignore_chain`: {ignore_chain!r}")
+    if isinstance(reorder, bool):
+        reorder = 1 if reorder else 0
     return jb_query_params(float(rmsd_threshold), float(distance_cutoff), float(max_dynamic_distance),
-                           IGNORE_CHAIN[ignore_chain], int(bool(reorder)), int(bool(best_match)), 0)
+                           IGNORE_CHAIN[ignore_chain], int(reorder), int(bool(best_match)), 0)
 
 
 class HitTable:
     """Host copy of a `jb_hits` record set as numpy arrays (canonical order)."""
 
-    __slots__ = ("count", "stride", "molecule", "template", "atoms", "rmsd", "rotation", "centre0", "centre1")
+    __slots__ = ("count", "stride", "molecule", "template", "atoms", "rmsd", "rotation", "centre0", "centre1",
+                 "_owner")
 
-    def __init__(self, hits: jb_hits):
+    def __init__(self, hits: jb_hits, owner=None):
+        """With `owner` (the object that keeps the C arrays alive, e.g. a `_capi.Result`)
+        the arrays are zero-copy views; without, they are copied."""
         n, stride = int(hits.count), int(hits.stride)
         self.count, self.stride = n, stride
+        self._owner = owner
 
         def grab(ptr, shape, dtype):
             size = int(np.prod(shape))
             if n == 0 or size == 0:
                 return np.zeros(shape, dtype=dtype)
-            return np.ctypeslib.as_array(ptr, shape=(size,)).reshape(shape).copy()
+            arr = np.ctypeslib.as_array(ptr, shape=(size,)).reshape(shape)
+            return arr if owner is not None else arr.copy()
 
         self.molecule = grab(hits.molecule, (n,), np.int32)
         self.template = grab(hits.template_index, (n,), np.int32)

@@ -67,6 +67,25 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+struct PinBuf {   // grow-only page-locked host staging
+    void *p = nullptr;
+    size_t bytes = 0;
+    cudaError_t ensure(size_t need)
+    {
+        if (need <= bytes) return cudaSuccess;
+        size_t nb = std::max(need, bytes + bytes / 2);
+        void *q = nullptr;
+        cudaError_t e = cudaMallocHost(&q, nb);
+        if (e != cudaSuccess) return e;
+        if (p) cudaFreeHost(p);
+        p = q;
+        bytes = nb;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; bytes = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
 template <class T> static cudaError_t upload(DevBuf &b, const T *src, size_t n, cudaStream_t st)
 {
     cudaError_t e = b.ensure(std::max<size_t>(n, 1) * sizeof(T), st);
@@ -86,8 +105,9 @@ struct jb_context {
     int debug = 0;                // JB_DEBUG: per-level counts and times on stderr
     cudaEvent_t lev[kMaxN + 1] = {};
     // workspace (grow only)
-    DevBuf crec, chead, mext, recs, fr[2], tuples, ctr;
+    DevBuf crec, chead, recs, fr[2], tuples, ctr;
     DevBuf h_mol, h_tpl, h_atoms, h_rmsd, h_rot, h_c0, h_c1;
+    PinBuf p_mol, p_tpl, p_atoms, p_rmsd, p_rot, p_c0, p_c1;   // D2H landing zone of jb_result_fetch
     long long hit_cap = 0;
     int hit_stride = 0;
     Counters *host_ctr = nullptr; // pinned
@@ -99,7 +119,7 @@ struct jb_templates {
     jb_context *ctx = nullptr;
     int T = 0, TA = 0, S = 0, nmax = 0;
     std::vector<int> atom_off;
-    DevBuf d_atom_off, d_spec, d_resseq, d_chain, d_pos, d_weight, d_dist_off, d_dist, d_shell;
+    DevBuf d_atom_off, d_spec, d_resseq, d_chain, d_pos, d_weight, d_dist_off, d_dist, d_shell, d_vol;
     DevBuf s_code, s_noff, s_nraw, s_nup, s_roff, s_rup;
     long long n_dist = 0;
 };
@@ -110,6 +130,8 @@ struct jb_molecules {
     long long NA = 0;
     std::vector<long long> atom_off;
     DevBuf d_off, x, y, z, name, res, resseq, chain, atoms;
+    DevBuf srec, sname, sres, ext, sort_scratch;   // x-sorted FP32 view (k_sort_atoms)
+    std::vector<DevBuf *> all() { return { &d_off, &x, &y, &z, &name, &res, &resseq, &chain, &atoms, &srec, &sname, &sres, &ext, &sort_scratch }; }
 };
 
 struct jb_result {
@@ -117,6 +139,7 @@ struct jb_result {
     long long count = 0;      // hits in the device buffers of ctx (valid until the next run)
     int stride = 0;
     int best_match = 0;
+    int n_templates = 0;
     jb_stats stats{};
     bool fetched = false;
     std::vector<int32_t> mol, tpl, atoms;
@@ -174,17 +197,18 @@ extern "C" void jb_context_destroy(jb_context *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = { &c->crec, &c->chead, &c->mext, &c->recs, &c->fr[0], &c->fr[1],
+    DevBuf *bufs[] = { &c->crec, &c->chead, &c->recs, &c->fr[0], &c->fr[1],
                        &c->tuples, &c->ctr, &c->h_mol, &c->h_tpl, &c->h_atoms, &c->h_rmsd, &c->h_rot, &c->h_c0,
                        &c->h_c1 };
     for (DevBuf *b : bufs) b->release();
     if (c->scratch_mol) {
         jb_molecules *m = c->scratch_mol;
-        DevBuf *mb[] = { &m->d_off, &m->x, &m->y, &m->z, &m->name, &m->res, &m->resseq, &m->chain, &m->atoms };
-        for (DevBuf *b : mb) b->release();
+        for (DevBuf *b : m->all()) b->release();
         delete m;
     }
     if (c->host_ctr) cudaFreeHost(c->host_ctr);
+    PinBuf *pins[] = { &c->p_mol, &c->p_tpl, &c->p_atoms, &c->p_rmsd, &c->p_rot, &c->p_c0, &c->p_c1 };
+    for (PinBuf *b : pins) b->release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (int i = 0; i < 5; i++) if (c->evs[i]) cudaEventDestroy(c->evs[i]);
@@ -288,6 +312,7 @@ extern "C" int jb_templates_create(jb_context *c, const jb_template_table *tb, j
     UP(t->s_rup, s_rup.data(), s_rup.size());
 #undef UP
     if (e == cudaSuccess) e = t->d_shell.ensure(std::max<size_t>(t->n_dist, 1) * sizeof(ShellRec), st);
+    if (e == cudaSuccess) e = t->d_vol.ensure(std::max<size_t>(t->n_dist, 1) * sizeof(double), st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // host vectors die at return
     if (e != cudaSuccess) {
         jb_templates_free(t);
@@ -303,7 +328,7 @@ extern "C" void jb_templates_free(jb_templates *t)
     cudaSetDevice(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
     DevBuf *bufs[] = { &t->d_atom_off, &t->d_spec, &t->d_resseq, &t->d_chain, &t->d_pos, &t->d_weight, &t->d_dist_off,
-                       &t->d_dist, &t->d_shell, &t->s_code, &t->s_noff, &t->s_nraw, &t->s_nup, &t->s_roff,
+                       &t->d_dist, &t->d_shell, &t->d_vol, &t->s_code, &t->s_noff, &t->s_nraw, &t->s_nup, &t->s_roff,
                        &t->s_rup };
     for (DevBuf *b : bufs) b->release();
     delete t;
@@ -342,6 +367,30 @@ static int fill_molecules(jb_context *c, jb_molecules *m, const jb_molecule_batc
                                                                      m->chain.as<unsigned char>(), m->atoms.as<AtomRec>());
         e = cudaGetLastError();
     }
+    // per-structure frame + x-sorted FP32 view (replaces the reference's per-pair k-d tree builds)
+    if (e == cudaSuccess) e = m->srec.ensure(std::max<size_t>((size_t)m->NA, 1) * sizeof(float4), st);
+    if (e == cudaSuccess) e = m->sname.ensure(std::max<size_t>((size_t)m->NA, 1) * sizeof(uint32_t), st);
+    if (e == cudaSuccess) e = m->sres.ensure(std::max<size_t>((size_t)m->NA, 1) * sizeof(uint32_t), st);
+    if (e == cudaSuccess) e = m->ext.ensure(std::max<size_t>((size_t)M, 1) * sizeof(MolExt), st);
+    if (e == cudaSuccess && M > 0) {
+        long long amax = 0;
+        for (int i = 0; i < M; i++) amax = std::max(amax, m->atom_off[i + 1] - m->atom_off[i]);
+        long long npad = 1;
+        while (npad < amax) npad <<= 1;
+        const int smem_keys = (int)std::min<long long>(npad, 16384);      // 8-byte keys: <= 128 KiB
+        if (npad > smem_keys) e = m->sort_scratch.ensure((size_t)m->NA * 2 * sizeof(u64), st);
+        const size_t smem = (size_t)smem_keys * sizeof(u64);
+        if (e == cudaSuccess && smem > 48 * 1024)
+            e = cudaFuncSetAttribute(k_sort_atoms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) {
+            k_sort_atoms<<<M, kSortThreads, smem, st>>>(m->d_off.as<long long>(), m->atoms.as<AtomRec>(),
+                                                        m->name.as<uint32_t>(), m->res.as<uint32_t>(),
+                                                        m->ext.as<MolExt>(), m->srec.as<float4>(),
+                                                        m->sname.as<uint32_t>(), m->sres.as<uint32_t>(),
+                                                        m->sort_scratch.as<u64>(), smem_keys);
+            e = cudaGetLastError();
+        }
+    }
     // the caller's staging buffers must stay valid until the stream reaches the copies:
     // synchronise so that they may be reused immediately.
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -368,18 +417,12 @@ extern "C" void jb_molecules_free(jb_molecules *m)
     if (!m) return;
     cudaSetDevice(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
-    DevBuf *bufs[] = { &m->d_off, &m->x, &m->y, &m->z, &m->name, &m->res, &m->resseq, &m->chain, &m->atoms };
-    for (DevBuf *b : bufs) b->release();
+    for (DevBuf *b : m->all()) b->release();
     delete m;
 }
 
 // ---- query --------------------------------------------------------------------------------
-static size_t expand_smem(int group, int level)
-{
-    const size_t ipw = 32 / group, lpad = level > 0 ? level : 1;
-    const size_t dbl = ipw * lpad * 5, ints = ipw * lpad * 3 + (size_t)kStageItems * (level + 2);
-    return (size_t)kExpandWarps * (dbl * sizeof(double) + ints * sizeof(int));
-}
+static size_t expand_smem(int group, int level) { return (size_t)kExpandWarps * expand_warp_bytes(group, level); }
 
 template <int G> static cudaError_t launch_expand(int grid, size_t smem, cudaStream_t st, const ExpandArgs &a)
 {
@@ -429,6 +472,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
     TT.chain = t->d_chain.as<unsigned char>(); TT.pos = t->d_pos.as<double>(); TT.weight = t->d_weight.as<double>();
     TT.dist_off = t->d_dist_off.as<long long>(); TT.dist = t->d_dist.as<double>();
     TT.shell = t->d_shell.as<ShellRec>();
+    TT.vol = t->d_vol.as<double>();
     SpecTable ST;
     ST.n_specs = t->S; ST.code = t->s_code.as<int>(); ST.name_off = t->s_noff.as<int>();
     ST.name_raw = t->s_nraw.as<uint32_t>(); ST.name_up = t->s_nup.as<uint32_t>();
@@ -473,7 +517,6 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         const int Mc = r.m1 - r.m0;
         const long long pairs = (long long)Mc * t->T;
         CU(c->chead.ensure((size_t)Mc * t->S * sizeof(CandHead), st));
-        CU(c->mext.ensure((size_t)Mc * sizeof(MolExt), st));
         CU(c->recs.ensure((size_t)pairs * sizeof(PairRec), st));
         if (c->crec.bytes == 0) {
             const long long chunk_atoms = mol->atom_off[r.m1] - mol->atom_off[r.m0];
@@ -483,8 +526,9 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         MT.n_molecules = Mc;
         MT.atom_off = mol->d_off.as<long long>() + r.m0;
         MT.atoms = mol->atoms.as<AtomRec>();
-        MT.name = mol->name.as<uint32_t>(); MT.res = mol->res.as<uint32_t>();
-        MT.ext = c->mext.as<MolExt>();
+        MT.srec = mol->srec.as<float4>();
+        MT.sname = mol->sname.as<uint32_t>(); MT.sres = mol->sres.as<uint32_t>();
+        MT.ext = mol->ext.as<MolExt>() + r.m0;
         CandTable CT;
         CT.head = c->chead.as<CandHead>(); CT.rec = c->crec.as<float4>();
         CT.cap = (long long)(c->crec.bytes / sizeof(float4));
@@ -499,7 +543,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         k_classify<<<Mc, 256, classify_smem, st>>>(MT, ST, CT, dc);
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->evs[1], st));
-        k_pairs<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(Mc, TT, t->S, CT.head, MT.atom_off, q->reorder,
+        k_pairs<<<(unsigned)((pairs + 127) / 128), 128, 0, st>>>(Mc, TT, t->S, CT.head, MT.atom_off, q->reorder,
                                                                  c->recs.as<PairRec>(), dc);
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->evs[2], st));
@@ -521,7 +565,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
             A.ctr = dc;
             if (c->debug) CU(cudaEventRecord(c->lev[l], st));
             const size_t smem = expand_smem(c->group, l);
-            const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(smem, 1)));
+            const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(3, (200 * 1024) / std::max<size_t>(smem, 1)));
             const int grid = c->sm_count * per_sm;
             cudaError_t e;
             switch (c->group) {
@@ -547,8 +591,8 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         const Counters &hc = *c->host_ctr;
         attempts++;
         if (c->debug) {
-            fprintf(stderr, "[jb] chunk [%d,%d) live=%llu cand=%llu tests=%llu box=%llu tuples=%llu\n", r.m0, r.m1,
-                    hc.live_pairs, hc.cand_total, hc.cand_tests, hc.box_pass, hc.tuples);
+            fprintf(stderr, "[jb] chunk [%d,%d) live=%llu cand=%llu tests=%llu scanned=%llu box=%llu tuples=%llu\n", r.m0,
+                    r.m1, hc.live_pairs, hc.cand_total, hc.cand_tests, hc.scan_tests, hc.box_pass, hc.tuples);
             for (int l = 0; l < t->nmax; l++) {
                 float ms = 0.f;
                 cudaEventElapsedTime(&ms, c->lev[l], c->lev[l + 1]);
@@ -610,6 +654,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         S.candidate_atoms += (int64_t)hc.cand_atoms;
         S.candidate_records += (int64_t)hc.cand_total;
         S.candidate_tests += (int64_t)hc.cand_tests;
+        S.scan_tests += (int64_t)hc.scan_tests;
         S.box_survivors += (int64_t)hc.box_pass;
         S.tuples += (int64_t)hc.tuples;
         S.nan_dropped += (int64_t)hc.nan_dropped;
@@ -640,14 +685,51 @@ extern "C" int jb_query_run(jb_context *c, const jb_templates *t, const jb_molec
     *out = nullptr;
     if (t->ctx != c || mol->ctx != c) return fail(JB_ERR_INVALID, "templates/molecules belong to another context");
     if (q->ignore_chain < 0 || q->ignore_chain > 2) return fail(JB_ERR_INVALID, "invalid ignore_chain %d", q->ignore_chain);
+    if (q->reorder < 0 || q->reorder > 2) return fail(JB_ERR_INVALID, "invalid reorder %d", q->reorder);
     jb_result *res = new jb_result();
     res->ctx = c;
     res->stride = std::max(t->nmax, 1);
     res->best_match = q->best_match;
+    res->n_templates = t->T;
     const int rc = query_run_impl(c, t, mol, q, res);
     if (rc != JB_OK) { delete res; return rc; }
     *out = res;
     return JB_OK;
+}
+
+// Canonical order (molecule, template, atom tuple): LSD radix sort of the (molecule,
+// template) key in 16-bit digits, then a comparison sort inside each (usually tiny) run.
+static void canonical_order(size_t n, int n_templates, const int32_t *mol, const int32_t *tpl, const int32_t *atoms,
+                            size_t stride, std::vector<uint32_t> &perm)
+{
+    perm.resize(n);
+    std::iota(perm.begin(), perm.end(), 0u);
+    if (n < 2) return;
+    std::vector<uint64_t> key(n);
+    uint64_t kmax = 0;
+    const uint64_t T = (uint64_t)std::max(n_templates, 1);
+    for (size_t i = 0; i < n; i++) { key[i] = (uint64_t)(uint32_t)mol[i] * T + (uint64_t)(uint32_t)tpl[i]; kmax = std::max(kmax, key[i]); }
+    std::vector<uint32_t> tmp(n);
+    std::vector<size_t> count(65537);
+    for (int shift = 0; shift < 64 && (kmax >> shift) != 0; shift += 16) {
+        std::fill(count.begin(), count.end(), (size_t)0);
+        for (size_t i = 0; i < n; i++) count[((key[perm[i]] >> shift) & 0xffff) + 1]++;
+        for (size_t d = 0; d < 65536; d++) count[d + 1] += count[d];
+        for (size_t i = 0; i < n; i++) tmp[count[(key[perm[i]] >> shift) & 0xffff]++] = perm[i];
+        perm.swap(tmp);
+    }
+    for (size_t i = 0; i < n;) {
+        size_t j = i + 1;
+        while (j < n && key[perm[j]] == key[perm[i]]) j++;
+        if (j - i > 1)
+            std::sort(perm.begin() + i, perm.begin() + j, [&](uint32_t a, uint32_t b) {
+                const int32_t *pa = atoms + (size_t)a * stride, *pb = atoms + (size_t)b * stride;
+                for (size_t k = 0; k < stride; k++)
+                    if (pa[k] != pb[k]) return pa[k] < pb[k];
+                return false;
+            });
+        i = j;
+    }
 }
 
 extern "C" int jb_result_fetch(jb_result *r, jb_hits *out)
@@ -657,34 +739,32 @@ extern "C" int jb_result_fetch(jb_result *r, jb_hits *out)
     CU(cudaSetDevice(c->device));
     if (!r->fetched) {
         const size_t n = (size_t)r->count, stride = (size_t)r->stride;
-        std::vector<int32_t> mol(n), tpl(n), atoms(n * stride);
-        std::vector<double> rmsd(n), rot(n * 9), c0(n * 3), c1(n * 3);
+        if (n > 0xffffffffull) return fail(JB_ERR_CAPACITY, "more than 2^32 hits in one result");
+        const int32_t *mol = nullptr, *tpl = nullptr, *atoms = nullptr;
+        const double *rmsd = nullptr, *rot = nullptr, *c0 = nullptr, *c1 = nullptr;
         if (n) {
             cudaStream_t st = c->stream;
-            CU(cudaMemcpyAsync(mol.data(), c->h_mol.p, n * sizeof(int), cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(tpl.data(), c->h_tpl.p, n * sizeof(int), cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(atoms.data(), c->h_atoms.p, n * stride * sizeof(int), cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(rmsd.data(), c->h_rmsd.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(rot.data(), c->h_rot.p, n * 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(c0.data(), c->h_c0.p, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(c1.data(), c->h_c1.p, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CU(c->p_mol.ensure(n * sizeof(int))); CU(c->p_tpl.ensure(n * sizeof(int)));
+            CU(c->p_atoms.ensure(n * stride * sizeof(int))); CU(c->p_rmsd.ensure(n * sizeof(double)));
+            CU(c->p_rot.ensure(n * 9 * sizeof(double))); CU(c->p_c0.ensure(n * 3 * sizeof(double)));
+            CU(c->p_c1.ensure(n * 3 * sizeof(double)));
+            CU(cudaMemcpyAsync(c->p_mol.p, c->h_mol.p, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(c->p_tpl.p, c->h_tpl.p, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(c->p_atoms.p, c->h_atoms.p, n * stride * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(c->p_rmsd.p, c->h_rmsd.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(c->p_rot.p, c->h_rot.p, n * 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(c->p_c0.p, c->h_c0.p, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(c->p_c1.p, c->h_c1.p, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
+            mol = c->p_mol.as<int32_t>(); tpl = c->p_tpl.as<int32_t>(); atoms = c->p_atoms.as<int32_t>();
+            rmsd = c->p_rmsd.as<double>(); rot = c->p_rot.as<double>(); c0 = c->p_c0.as<double>(); c1 = c->p_c1.as<double>();
         }
-        // canonical order: (molecule, template, atom tuple)
-        std::vector<size_t> perm(n);
-        std::iota(perm.begin(), perm.end(), (size_t)0);
-        std::sort(perm.begin(), perm.end(), [&](size_t a, size_t b) {
-            if (mol[a] != mol[b]) return mol[a] < mol[b];
-            if (tpl[a] != tpl[b]) return tpl[a] < tpl[b];
-            const int32_t *pa = &atoms[a * stride], *pb = &atoms[b * stride];
-            for (size_t k = 0; k < stride; k++)
-                if (pa[k] != pb[k]) return pa[k] < pb[k];
-            return false;
-        });
+        std::vector<uint32_t> perm;
+        canonical_order(n, r->n_templates, mol, tpl, atoms, stride, perm);
         if (r->best_match) {
             // keep the smallest RMSD per (molecule, template); ties -> first in canonical
             // order (the reference keeps the first in ITS iteration order, _jess.pyx:2238)
-            std::vector<size_t> keep;
+            std::vector<uint32_t> keep;
             for (size_t i = 0; i < n;) {
                 size_t j = i, best = i;
                 while (j < n && mol[perm[j]] == mol[perm[i]] && tpl[perm[j]] == tpl[perm[i]]) {

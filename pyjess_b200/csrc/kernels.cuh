@@ -59,25 +59,32 @@ struct TemplateTable {
     const long long *dist_off; // [T+1]
     const double *dist;        // n*n per template
     ShellRec *shell;           // same layout as dist: [earlier*n + later]
+    double *vol;               // same layout: shell volume proxy hi^3 - lo^3 (scan-order heuristic)
 };
 
-struct alignas(32) AtomRec {   // one 32-byte sector per gathered atom
+struct alignas(32) AtomRec {   // one 32-byte sector per gathered atom (original atom order)
     double x, y, z;
     int resseq;
     int chain;
 };
 
-struct alignas(32) MolExt {    // frame of the FP32 candidate records of one structure
+struct alignas(32) MolExt {    // frame of the FP32 records of one structure
     double ox, oy, oz;         // origin (first atom)
     double ext;                // max |coordinate - origin| over the structure
 };
 
+// Device image of an uploaded batch.  Two views of the same atoms:
+//   atoms[]            original order, FP64, authoritative for every decision
+//   srec/sname/sres[]  sorted by x within each structure (k_sort_atoms), FP32 coordinates
+//                      relative to the structure origin + original index: conservative
+//                      prefilter data only.  Candidate lists inherit the x order.
 struct MolTable {
     int n_molecules;           // of the chunk
     const long long *atom_off; // [M+1] (chunk view, absolute atom offsets)
-    const AtomRec *atoms;      // packed at upload by k_pack_atoms
-    const uint32_t *name, *res;
-    MolExt *ext;               // [M] chunk-local, written by k_classify
+    const AtomRec *atoms;
+    const float4 *srec;        // {x-ox, y-oy, z-oz, original index bits}
+    const uint32_t *sname, *sres;
+    const MolExt *ext;         // [M] chunk view
 };
 
 struct alignas(16) CandHead {  // one candidate list = one (structure, spec)
@@ -88,14 +95,15 @@ struct alignas(16) CandHead {  // one candidate list = one (structure, spec)
 
 struct CandTable {
     CandHead *head;            // [M*S]
-    float4 *rec;               // {x-ox, y-oy, z-oz, atom index bits}: FP32 is ONLY a conservative prefilter
+    float4 *rec;               // x-sorted copies of srec entries: FP32 is ONLY a conservative prefilter
     long long cap;             // capacity (records)
 };
 
 struct alignas(32) ShellRec {  // constraint of an ORDERED template-atom pair (earlier i, later k)
     double lo2, hi2;           // squared shell radii (eff:Scanner.c:275-290, eff:Annulus.c:40-67)
     int flags;                 // bit0: same template chain, bit1: same template residue number
-    int pad;
+    float rb;                  // outer radius rounded UP to FP32 (join-box prefilter)
+    int pad[2];
 };
 
 struct alignas(16) PairRec {   // one live (structure, template) pair, 128 bytes
@@ -106,15 +114,16 @@ struct alignas(16) PairRec {   // one live (structure, template) pair, 128 bytes
     long long abase;           // first atom of the structure
     long long shell0;          // first ShellRec of the template
     unsigned short spec[kMaxN];// spec id of the atom scanned at level l
-    unsigned char order[kMaxN];// scan order (eff:Scanner.c:88-99,160-174)
+    unsigned char order[kMaxN];// scan order (eff:Scanner.c:88-99,160-174 or the engine's own)
 };
 
 struct Counters {              // device counters of one chunk attempt
     u64 cand_total;            // records reserved in CandTable
     u64 live_pairs;
     u64 cand_atoms;            // sum_k |C_k| over live pairs
-    u64 cand_tests;            // (partial match, candidate) evaluations
-    u64 box_pass;              // ... that survived the FP32 join-box prefilter
+    u64 cand_tests;            // sum over partial matches of |C_level| (algorithm independent)
+    u64 scan_tests;            // FP32 box tests actually executed (after x-range narrowing)
+    u64 box_pass;              // ... that survived and took the exact FP64 predicate
     u64 tuples;                // full tuples produced
     u64 tuple_ints;            // sum of their sizes
     u64 hits;                  // hits written (absolute, across chunks)
@@ -220,25 +229,96 @@ __global__ void __launch_bounds__(256) k_pack_atoms(long long n, const double *x
     out[i] = r;
 }
 
+// ---- K0b: per-structure frame + x-sorted FP32 view (once per upload) ----------------
+// One CTA per structure: origin = first atom, extent = max |coordinate - origin|
+// (bounds the FP32 rounding of the relative coordinates), then a bitonic sort of
+// (orderable bits of float(x - ox), original index) keys -- in shared memory when
+// the padded structure fits, in a global scratch area otherwise.  Replaces the k-d
+// tree build of the reference (eff:KdTree.c:145-186,343-423): every candidate list
+// later cut out of this view is x-sorted, so a range query is a lower-bound search
+// plus a short scan.
+__device__ __forceinline__ uint32_t float_orderable(float f)
+{
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+constexpr int kSortThreads = 512;
+
+__global__ void __launch_bounds__(kSortThreads) k_sort_atoms(const long long *atom_off, const AtomRec *atoms,
+                                                             const uint32_t *name, const uint32_t *res, MolExt *ext,
+                                                             float4 *srec, uint32_t *sname, uint32_t *sres,
+                                                             u64 *scratch, int smem_keys)
+{
+    extern __shared__ __align__(16) unsigned char sort_smem[];
+    __shared__ double sh_ext[kSortThreads / 32];
+    const int m = blockIdx.x;
+    const long long a0 = atom_off[m], a1 = atom_off[m + 1];
+    const int na = (int)(a1 - a0);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    double ox = 0.0, oy = 0.0, oz = 0.0, e = 0.0;
+    if (na > 0) { const AtomRec o = atoms[a0]; ox = o.x; oy = o.y; oz = o.z; }
+    for (int i = tid; i < na; i += kSortThreads) {
+        const AtomRec ar = atoms[a0 + i];
+        e = fmax(e, fmax(fabs(__dsub_rn(ar.x, ox)), fmax(fabs(__dsub_rn(ar.y, oy)), fabs(__dsub_rn(ar.z, oz)))));
+    }
+    for (int o = 16; o > 0; o >>= 1) e = fmax(e, __shfl_xor_sync(0xffffffffu, e, o));
+    if (lane == 0) sh_ext[w] = e;
+    __syncthreads();
+    if (tid == 0) {
+        double v = 0.0;
+        for (int i = 0; i < kSortThreads / 32; i++) v = fmax(v, sh_ext[i]);
+        MolExt me; me.ox = ox; me.oy = oy; me.oz = oz; me.ext = v;
+        ext[m] = me;
+    }
+    if (na == 0) return;
+    int npad = 1;
+    while (npad < na) npad <<= 1;
+    u64 *keys = npad <= smem_keys ? reinterpret_cast<u64 *>(sort_smem) : scratch + 2 * a0;
+    for (int i = tid; i < npad; i += kSortThreads) {
+        u64 k = ~0ull;
+        if (i < na) {
+            const float fx = __double2float_rn(__dsub_rn(atoms[a0 + i].x, ox));
+            k = ((u64)float_orderable(fx) << 32) | (u64)(uint32_t)i;
+        }
+        keys[i] = k;
+    }
+    __syncthreads();
+    for (int k = 2; k <= npad; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < npad; i += kSortThreads) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const u64 x = keys[i], y = keys[p];
+                    if ((x > y) == ((i & k) == 0)) { keys[i] = y; keys[p] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = tid; i < na; i += kSortThreads) {
+        const int a = (int)(uint32_t)keys[i];
+        const AtomRec ar = atoms[a0 + a];
+        srec[a0 + i] = make_float4(__double2float_rn(__dsub_rn(ar.x, ox)), __double2float_rn(__dsub_rn(ar.y, oy)),
+                                   __double2float_rn(__dsub_rn(ar.z, oz)), __int_as_float(a));
+        sname[a0 + i] = name[a0 + a];
+        sres[a0 + i] = res[a0 + a];
+    }
+}
+
 // ---- K1: candidate lists ------------------------------------------------------
-// One CTA per structure.  Warp w owns a contiguous slice of the atoms; pass 1
-// counts matches per (warp, spec) in shared memory, a scan over warps gives every
-// warp its write offset, pass 2 re-evaluates and writes the records in ascending
-// atom order (deterministic lists).  List placement in the record array is
-// reserved with one atomicAdd per (structure, spec).  Pass 1 also measures the
-// extent of the structure around its first atom: the FP32 records are stored
-// relative to that origin and the extent bounds their rounding error.
+// One CTA per structure, atoms visited in x-sorted order.  Warp w owns a contiguous
+// slice; pass 1 counts matches per (warp, spec) in shared memory, a scan over warps
+// gives every warp its write offset, pass 2 re-evaluates and copies the FP32 records,
+// so every list is x-sorted and deterministic.  List placement in the record array is
+// reserved with one atomicAdd per (structure, spec).
 __global__ void __launch_bounds__(256) k_classify(MolTable M, SpecTable S, CandTable C, Counters *ctr)
 {
     extern __shared__ int sh_cnt[];                 // [warps][S]
-    __shared__ double sh_ext[8];
     const int m = blockIdx.x;
     const int nw = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ns = S.n_specs;
     const long long a0 = M.atom_off[m], a1 = M.atom_off[m + 1];
     const int na = (int)(a1 - a0);
-    double ox = 0.0, oy = 0.0, oz = 0.0, ext = 0.0;
-    if (na > 0) { const AtomRec o = M.atoms[a0]; ox = o.x; oy = o.y; oz = o.z; }
     // slice boundaries in multiples of 32 atoms
     const int chunks = (na + 31) >> 5;
     const int c_lo = (int)(((long long)chunks * w) / nw), c_hi = (int)(((long long)chunks * (w + 1)) / nw);
@@ -252,13 +332,10 @@ __global__ void __launch_bounds__(256) k_classify(MolTable M, SpecTable S, CandT
             uint32_t name = 0, name_up = 0, res_up = 0;
             float4 rec = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid) {
-                name = M.name[a0 + a];
+                name = M.sname[a0 + a];
                 name_up = upper4(name);
-                res_up = upper4(M.res[a0 + a]);
-                const AtomRec ar = M.atoms[a0 + a];
-                const double dx = __dsub_rn(ar.x, ox), dy = __dsub_rn(ar.y, oy), dz = __dsub_rn(ar.z, oz);
-                if (pass == 0) ext = fmax(ext, fmax(fabs(dx), fmax(fabs(dy), fabs(dz))));
-                rec = make_float4(__double2float_rn(dx), __double2float_rn(dy), __double2float_rn(dz), __int_as_float(a));
+                res_up = upper4(M.sres[a0 + a]);
+                if (pass == 1) rec = M.srec[a0 + a];
             }
             for (int s = 0; s < ns; s++) {
                 const bool ok = valid && spec_match(S, s, name, name_up, res_up);
@@ -279,15 +356,7 @@ __global__ void __launch_bounds__(256) k_classify(MolTable M, SpecTable S, CandT
             }
         }
         if (pass == 0) {
-            for (int o = 16; o > 0; o >>= 1) ext = fmax(ext, __shfl_xor_sync(0xffffffffu, ext, o));
-            if (lane == 0) sh_ext[w] = ext;
             __syncthreads();
-            if (threadIdx.x == 0) {
-                double e = 0.0;
-                for (int v = 0; v < nw; v++) e = fmax(e, sh_ext[v]);
-                MolExt me; me.ox = ox; me.oy = oy; me.oz = oz; me.ext = e;
-                M.ext[m] = me;
-            }
             // exclusive scan over warps, reserve the list, publish count/offset
             for (int s = threadIdx.x; s < ns; s += blockDim.x) {
                 int run = 0;
@@ -327,16 +396,24 @@ __global__ void k_shells(TemplateTable T, double cutoff, double max_dyn)
         r.lo2 = __dmul_rn(a, a);
         r.hi2 = __dmul_rn(b, b);
         r.flags = ((T.chain[ta0 + i] == T.chain[ta0 + k]) ? 1 : 0) | ((T.resseq[ta0 + i] == T.resseq[ta0 + k]) ? 2 : 0);
-        r.pad = 0;
+        // outer radius for the FP32 join box: rounded up, with a relative margin far above 1 ulp
+        r.rb = __double2float_ru(__dmul_ru(__dsqrt_ru(r.hi2), 1.000000001));
+        r.pad[0] = r.pad[1] = 0;
         T.shell[d0 + e] = r;
+        // scan-order heuristic (reorder == 2): volume proxy hi^3 - lo^3, exactly as the oracle computes it
+        T.vol[d0 + e] = __dsub_rn(__dmul_rn(r.hi2, __dsqrt_rn(r.hi2)), __dmul_rn(r.lo2, __dsqrt_rn(r.lo2)));
     }
 }
 
 // ---- K: pairs --------------------------------------------------------------------
 // Thread per (structure, template).  A pair is live iff every candidate set is
-// non-empty (eff:Scanner.c:145-149); the scan order is argsort(|C_k|, k)
-// (eff:Scanner.c:88-99) or the identity when reorder is off.
-__global__ void __launch_bounds__(256) k_pairs(int n_mol, TemplateTable T, int n_specs, const CandHead *heads,
+// non-empty (eff:Scanner.c:145-149).  Scan order:
+//   reorder 0  template order
+//   reorder 1  the reference's argsort(|C_k|, k) (eff:Scanner.c:88-99)
+//   reorder 2  the engine's own: smallest candidate set first, then greedily the atom
+//              with the smallest expected fan-out |C_k| * min_j vol(j, k).  The hit SET
+//              does not depend on the order (all constraints are pairwise and symmetric).
+__global__ void __launch_bounds__(128) k_pairs(int n_mol, TemplateTable T, int n_specs, const CandHead *heads,
                                                const long long *atom_off, int reorder, PairRec *recs, Counters *ctr)
 {
     const long long total = (long long)n_mol * T.n_templates;
@@ -362,13 +439,34 @@ __global__ void __launch_bounds__(256) k_pairs(int n_mol, TemplateTable T, int n
         if (live && n == 1) { single = true; live = false; }    // see DESIGN.md: n==1 not on the GPU path
         if (live) {
             for (int k = 0; k < n; k++) ord[k] = (unsigned char)k;
-            if (reorder) {
+            if (reorder == 1) {
                 for (int i = 1; i < n; i++) {                   // stable insertion sort by (count, index)
                     const unsigned char v = ord[i];
                     const int cv = cnts[v];
                     int j = i - 1;
                     while (j >= 0 && cnts[ord[j]] > cv) { ord[j + 1] = ord[j]; j--; }
                     ord[j + 1] = v;
+                }
+            } else if (reorder == 2) {
+                const double *vol = T.vol + T.dist_off[t];
+                const double inf = __longlong_as_double(0x7ff0000000000000ll);
+                double minv[kMaxN];
+                unsigned used = 0;
+                int first = 0;
+                for (int k = 1; k < n; k++) if (cnts[k] < cnts[first]) first = k;
+                for (int k = 0; k < n; k++) minv[k] = inf;
+                int last = first;
+                ord[0] = (unsigned char)first; used |= 1u << first;
+                for (int l = 1; l < n; l++) {
+                    int best = -1; double best_score = 0.0;
+                    for (int k = 0; k < n; k++) {
+                        if (used & (1u << k)) continue;
+                        const double v = fmin(minv[k], vol[last * n + k]);
+                        minv[k] = v;
+                        const double score = __dmul_rn((double)cnts[k], v);
+                        if (best < 0 || score < best_score) { best = k; best_score = score; }
+                    }
+                    ord[l] = (unsigned char)best; used |= 1u << best; last = best;
                 }
             }
         }
@@ -437,185 +535,257 @@ __device__ __forceinline__ bool pair_consistent(int ignore, bool mol_same_chain,
     return true;
 }
 
-// G lanes cooperate on one partial match; a warp handles 32/G of them at a time.
-//  1. the lanes of a group stage the already-placed atoms (one 32-byte AtomRec and
-//     one 32-byte ShellRec each) into shared memory and reduce the axis-aligned box
-//     of the annulus join (the reference's Join_computeBox, eff:Join.c:82-111) with
-//     group shuffles, in FP32, rounded OUTWARD by the record error bound;
-//  2. they stride the candidate list: one LDG.128 + six FP32 compares per candidate;
-//  3. only box survivors take the exact FP64 predicate (_Annulus_po,
-//     eff:Annulus.h:54-68, explicit RN ops, no FMA) and the chain/residue rules;
-//  4. survivors are compacted (ballot + prefix popcount) into a per-warp staging
-//     buffer that is flushed to the next frontier with ONE global atomicAdd.
+struct alignas(16) ChainRec {    // one already-placed atom of a partial match, staged in shared memory
+    double x, y, z;              // FP64 centre of the annulus
+    double lo2, hi2;             // squared radii of the shell towards the atom being placed
+    int res;                     // residue number of the placed atom
+    int flag;                    // chain id | template flags << 8
+};
+
+struct alignas(16) GroupMeta {   // per partial match of the current batch
+    long long abase;
+    int lp;
+    int complete;                // this level finishes the template
+};
+
+constexpr int kQueue = 64;       // per-warp survivor queue (entries)
+
+__host__ __device__ constexpr size_t expand_warp_bytes(int group, int level)
+{
+    const size_t ipw = 32 / group, lpad = level > 0 ? level : 1;
+    return ipw * lpad * sizeof(ChainRec) + ipw * sizeof(GroupMeta) + (size_t)kQueue * sizeof(int2) +
+           ((ipw * lpad + (size_t)kStageItems * (level + 2)) * sizeof(int) + 15) / 16 * 16;
+}
+
+// G lanes cooperate on one partial match; a warp handles 32/G of them per batch.
+//  1. the lanes of a group stage the already-placed atoms (one 32-byte AtomRec and one
+//     32-byte ShellRec each) into shared memory and reduce, with group shuffles, the
+//     axis-aligned box of the annulus join (the reference's Join_computeBox,
+//     eff:Join.c:82-111) in FP32, rounded OUTWARD by the record error bound;
+//  2. the candidate list is x-sorted: a G-ary lower-bound search finds the first record
+//     inside the box, the scan stops at the first record beyond it (this pair of steps
+//     is what the k-d tree walk of eff:KdTree.c:238-296 becomes);
+//  3. scan: one LDG.128 + six FP32 compares per candidate; box survivors are pushed to a
+//     per-warp queue in shared memory (ballot + prefix popcount);
+//  4. drain: ONE LANE PER SURVIVOR takes the exact FP64 predicate (_Annulus_po,
+//     eff:Annulus.h:54-68, explicit RN ops, no FMA) against the staged atoms and the
+//     chain/residue rules -- dense lanes instead of a divergent tail in the scan loop;
+//  5. accepted extensions are compacted into a per-warp staging buffer that is flushed
+//     to the next frontier with ONE global atomicAdd; finished tuples go to the tuple list.
 template <int G>
-__global__ void __launch_bounds__(kExpandThreads, 2) k_expand(const ExpandArgs A)
+__global__ void __launch_bounds__(kExpandThreads, 3) k_expand(const ExpandArgs A)
 {
     constexpr int IPW = 32 / G;
+    constexpr unsigned GM = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
+    constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int l = A.level;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = lane / G, gl = lane % G;
     const int in_stride = l + 1, out_stride = l + 2;
     const int lpad = l > 0 ? l : 1;
+    const unsigned lt = (1u << lane) - 1;
 
-    // shared memory carve-up (per warp): doubles first (alignment), then ints
-    const size_t dbl_per_warp = (size_t)IPW * lpad * 5;
-    const size_t int_per_warp = (size_t)IPW * lpad * 3 + (size_t)kStageItems * out_stride;
-    double *wd = reinterpret_cast<double *>(smem_raw) + warp * dbl_per_warp;
-    int *wi = reinterpret_cast<int *>(smem_raw + sizeof(double) * dbl_per_warp * kExpandWarps) + warp * int_per_warp;
-    double *sx = wd + (size_t)grp * lpad * 5, *sy = sx + lpad, *sz = sy + lpad, *slo = sz + lpad, *shi = slo + lpad;
-    int *sa = wi + (size_t)grp * lpad * 3, *sres = sa + lpad, *sflag = sres + lpad;
-    int *stage = wi + (size_t)IPW * lpad * 3;
-    int fill = 0;
+    unsigned char *wbase = smem_raw + (size_t)warp * expand_warp_bytes(G, l);
+    ChainRec *chain = reinterpret_cast<ChainRec *>(wbase);
+    GroupMeta *meta = reinterpret_cast<GroupMeta *>(chain + IPW * lpad);
+    int2 *queue = reinterpret_cast<int2 *>(meta + IPW);
+    int *chain_atom = reinterpret_cast<int *>(queue + kQueue);
+    int *stage = chain_atom + IPW * lpad;
+    int fill = 0, qfill = 0;
 
     u64 n_in = *A.in_count;
     if (l > 0 && (long long)n_in > A.in_cap) n_in = (u64)A.in_cap;
     const long long total_warps = (long long)gridDim.x * kExpandWarps;
-    unsigned tests = 0, boxed = 0;
+    u64 n_cand = 0, n_scan = 0, n_box = 0;           // lane 0 only
     const float INF = __int_as_float(0x7f800000);
+
+    // exact predicate + emission for queue entries [q0, q0 + nq)
+    auto drain = [&](int q0, int nq) {
+        __syncwarp();
+        bool ok = lane < nq;
+        int a = 0, g = 0;
+        GroupMeta gm; gm.abase = 0; gm.lp = 0; gm.complete = 0;
+        if (ok) {
+            const int2 e = queue[q0 + lane];
+            a = e.x; g = e.y;
+            gm = meta[g];
+        }
+        if (ok && l > 0) {
+            const AtomRec p = A.atoms[gm.abase + a];
+            const ChainRec *ch = chain + g * lpad;
+            // _Annulus_po (eff:Annulus.h:54-68): ((dx^2 + dy^2) + dz^2), centre - point
+            for (int j = 0; j < l; j++) {
+                const double t0 = __dsub_rn(ch[j].x, p.x), t1 = __dsub_rn(ch[j].y, p.y), t2 = __dsub_rn(ch[j].z, p.z);
+                const double s = __dadd_rn(__dadd_rn(__dmul_rn(t0, t0), __dmul_rn(t1, t1)), __dmul_rn(t2, t2));
+                if (s < ch[j].lo2 || s > ch[j].hi2) { ok = false; break; }
+            }
+            if (ok) {
+                for (int j = 0; j < l; j++) {
+                    const int f = ch[j].flag;
+                    if (!pair_consistent(A.ignore_chain, (f & 0xff) == p.chain, (f & 0x100) != 0, ch[j].res == p.resseq,
+                                         (f & 0x200) != 0)) { ok = false; break; }
+                }
+            }
+        }
+        const unsigned okm = __ballot_sync(FULL, ok);
+        if (okm == 0) return;
+        const unsigned cm = __ballot_sync(FULL, ok && gm.complete);
+        const unsigned nm = okm & ~cm;
+        if (cm) {   // finished tuples go straight to the tuple list (one atomic per warp)
+            u64 tb = 0;
+            if (lane == 0) {
+                tb = atomicAdd(&A.ctr->tuples, (u64)__popc(cm));
+                atomicAdd(&A.ctr->tuple_ints, (u64)__popc(cm) * (u64)(l + 1));
+            }
+            tb = __shfl_sync(FULL, tb, 0);
+            if (ok && gm.complete) {
+                const long long slot = (long long)tb + __popc(cm & lt);
+                if (slot < A.tuple_cap) {
+                    int *dst = A.tuples + slot * A.tuple_stride;
+                    dst[0] = gm.lp;
+                    for (int j = 0; j < l; j++) dst[1 + j] = chain_atom[g * lpad + j];
+                    dst[1 + l] = a;
+                }
+            }
+        }
+        if (nm) {
+            if (ok && !gm.complete) {
+                int *dst = stage + (size_t)(fill + __popc(nm & lt)) * out_stride;
+                dst[0] = gm.lp;
+                for (int j = 0; j < l; j++) dst[1 + j] = chain_atom[g * lpad + j];
+                dst[1 + l] = a;
+            }
+            fill += __popc(nm);
+            if (fill + 32 > kStageItems) {   // flush
+                __syncwarp();
+                u64 ob = 0;
+                if (lane == 0) ob = atomicAdd(A.out_count, (u64)fill);
+                ob = __shfl_sync(FULL, ob, 0);
+                if ((long long)ob + fill <= A.out_cap) {
+                    int *dst = A.out + (long long)ob * out_stride;
+                    for (int i = lane; i < fill * out_stride; i += 32) dst[i] = stage[i];
+                }
+                fill = 0;
+                __syncwarp();
+            }
+        }
+    };
 
     for (long long base_item = ((long long)blockIdx.x * kExpandWarps + warp) * IPW; base_item < (long long)n_in;
          base_item += total_warps * IPW) {
         const long long item = base_item + grp;
         const bool valid = item < (long long)n_in;
-        int lp = 0, n = 0, k = 0, cnt = 0;
-        long long coff = 0, abase = 0;
+        int cnt = 0;
+        long long coff = 0;
         float bx0 = -INF, by0 = -INF, bz0 = -INF, bx1 = INF, by1 = INF, bz1 = INF;
-        __syncwarp();   // previous iteration's readers are done with the scratch
         if (valid) {
-            lp = l == 0 ? (int)item : A.in[item * in_stride];
+            const int lp = l == 0 ? (int)item : A.in[item * in_stride];
             const PairRec *rec = A.recs + lp;
             const int4 h0 = *reinterpret_cast<const int4 *>(rec);            // m, t, ta0, n
             const longlong2 h1 = *reinterpret_cast<const longlong2 *>(&rec->abase);
-            n = h0.w;
-            abase = h1.x;
-            k = rec->order[l];
+            const int n = h0.w;
+            const int k = rec->order[l];
             const CandHead hd = A.head[(long long)h0.x * A.n_specs + rec->spec[l]];
             cnt = hd.cnt;
             coff = hd.off;
+            if (gl == 0) {
+                GroupMeta gm; gm.abase = h1.x; gm.lp = lp; gm.complete = (l + 1 == n) ? 1 : 0;
+                meta[grp] = gm;
+            }
             if (l > 0) {
                 const MolExt me = A.ext[h0.x];
-                const double err = me.ext * 2.4e-7 + 1e-30;                  // > ext * 2^-22: record rounding
+                const float err = __double2float_ru(me.ext * 2.4e-7 + 1e-30);  // > ext * 2^-22: record rounding
                 for (int j = gl; j < l; j += G) {
                     const int a = A.in[item * in_stride + 1 + j];
-                    const AtomRec ar = A.atoms[abase + a];
+                    const AtomRec ar = A.atoms[h1.x + a];
                     const ShellRec sh = A.shell[h1.y + (long long)rec->order[j] * n + k];
-                    sa[j] = a;
-                    sx[j] = ar.x; sy[j] = ar.y; sz[j] = ar.z;
-                    slo[j] = sh.lo2; shi[j] = sh.hi2;
-                    sres[j] = ar.resseq;
-                    sflag[j] = ar.chain | (sh.flags << 8);
-                    // outer radius, rounded up with a generous relative margin
-                    const double b = __dmul_ru(__dsqrt_ru(sh.hi2), 1.000000001);
-                    bx0 = fmaxf(bx0, __double2float_rd(__dsub_rd(__dsub_rd(__dsub_rd(ar.x, b), me.ox), err)));
-                    by0 = fmaxf(by0, __double2float_rd(__dsub_rd(__dsub_rd(__dsub_rd(ar.y, b), me.oy), err)));
-                    bz0 = fmaxf(bz0, __double2float_rd(__dsub_rd(__dsub_rd(__dsub_rd(ar.z, b), me.oz), err)));
-                    bx1 = fminf(bx1, __double2float_ru(__dadd_ru(__dsub_ru(__dadd_ru(ar.x, b), me.ox), err)));
-                    by1 = fminf(by1, __double2float_ru(__dadd_ru(__dsub_ru(__dadd_ru(ar.y, b), me.oy), err)));
-                    bz1 = fminf(bz1, __double2float_ru(__dadd_ru(__dsub_ru(__dadd_ru(ar.z, b), me.oz), err)));
+                    ChainRec c;
+                    c.x = ar.x; c.y = ar.y; c.z = ar.z; c.lo2 = sh.lo2; c.hi2 = sh.hi2;
+                    c.res = ar.resseq; c.flag = ar.chain | (sh.flags << 8);
+                    chain[grp * lpad + j] = c;
+                    chain_atom[grp * lpad + j] = a;
+                    const double dx = __dsub_rn(ar.x, me.ox), dy = __dsub_rn(ar.y, me.oy), dz = __dsub_rn(ar.z, me.oz);
+                    const float rb = sh.rb;
+                    bx0 = fmaxf(bx0, __fsub_rd(__fsub_rd(__double2float_rd(dx), rb), err));
+                    by0 = fmaxf(by0, __fsub_rd(__fsub_rd(__double2float_rd(dy), rb), err));
+                    bz0 = fmaxf(bz0, __fsub_rd(__fsub_rd(__double2float_rd(dz), rb), err));
+                    bx1 = fminf(bx1, __fadd_ru(__fadd_ru(__double2float_ru(dx), rb), err));
+                    by1 = fminf(by1, __fadd_ru(__fadd_ru(__double2float_ru(dy), rb), err));
+                    bz1 = fminf(bz1, __fadd_ru(__fadd_ru(__double2float_ru(dz), rb), err));
                 }
             }
         }
 #pragma unroll
         for (int o = G >> 1; o > 0; o >>= 1) {   // join box = intersection over the placed atoms
-            bx0 = fmaxf(bx0, __shfl_xor_sync(0xffffffffu, bx0, o)); bx1 = fminf(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
-            by0 = fmaxf(by0, __shfl_xor_sync(0xffffffffu, by0, o)); by1 = fminf(by1, __shfl_xor_sync(0xffffffffu, by1, o));
-            bz0 = fmaxf(bz0, __shfl_xor_sync(0xffffffffu, bz0, o)); bz1 = fminf(bz1, __shfl_xor_sync(0xffffffffu, bz1, o));
+            bx0 = fmaxf(bx0, __shfl_xor_sync(FULL, bx0, o)); bx1 = fminf(bx1, __shfl_xor_sync(FULL, bx1, o));
+            by0 = fmaxf(by0, __shfl_xor_sync(FULL, by0, o)); by1 = fminf(by1, __shfl_xor_sync(FULL, by1, o));
+            bz0 = fmaxf(bz0, __shfl_xor_sync(FULL, bz0, o)); bz1 = fminf(bz1, __shfl_xor_sync(FULL, bz1, o));
         }
-        __syncwarp();
-        const int maxcnt = __reduce_max_sync(0xffffffffu, cnt);
-        const bool complete = (l + 1 == n);
-        for (int c0 = 0; c0 < maxcnt; c0 += G) {
-            const int c = c0 + gl;
-            bool ok = valid && c < cnt;
-            int a = 0;
-            if (ok) {
-                tests++;
-                const float4 cr = __ldg(A.cand + coff + c);
-                a = __float_as_int(cr.w);
-                ok = cr.x >= bx0 && cr.x <= bx1 && cr.y >= by0 && cr.y <= by1 && cr.z >= bz0 && cr.z <= bz1;
-            }
-            if (ok && l > 0) {
-                boxed++;
-                const AtomRec p = A.atoms[abase + a];
-                // _Annulus_po (eff:Annulus.h:54-68): ((dx^2 + dy^2) + dz^2), centre - point
-                for (int j = 0; j < l; j++) {
-                    const double t0 = __dsub_rn(sx[j], p.x), t1 = __dsub_rn(sy[j], p.y), t2 = __dsub_rn(sz[j], p.z);
-                    const double s = __dadd_rn(__dadd_rn(__dmul_rn(t0, t0), __dmul_rn(t1, t1)), __dmul_rn(t2, t2));
-                    if (s < slo[j] || s > shi[j]) { ok = false; break; }
-                }
-                if (ok) {
-                    for (int j = 0; j < l; j++) {
-                        const int f = sflag[j];
-                        if (!pair_consistent(A.ignore_chain, (f & 0xff) == p.chain, (f & 0x100) != 0, sres[j] == p.resseq,
-                                             (f & 0x200) != 0)) { ok = false; break; }
-                    }
-                }
-            }
-            const unsigned okm = __ballot_sync(0xffffffffu, ok);
-            if (okm == 0) continue;
-            const unsigned lt = (1u << lane) - 1;
-            const unsigned cm = __ballot_sync(0xffffffffu, ok && complete);
-            const unsigned nm = okm & ~cm;
-            if (cm) {   // finished tuples go straight to the tuple list (one atomic per warp)
-                u64 tb = 0;
-                if (lane == 0) {
-                    tb = atomicAdd(&A.ctr->tuples, (u64)__popc(cm));
-                    atomicAdd(&A.ctr->tuple_ints, (u64)__popc(cm) * (u64)(l + 1));
-                }
-                tb = __shfl_sync(0xffffffffu, tb, 0);
-                if (ok && complete) {
-                    const long long slot = (long long)tb + __popc(cm & lt);
-                    if (slot < A.tuple_cap) {
-                        int *dst = A.tuples + slot * A.tuple_stride;
-                        dst[0] = lp;
-                        for (int j = 0; j < l; j++) dst[1 + j] = sa[j];
-                        dst[1 + l] = a;
-                    }
-                }
-            }
-            if (nm) {
-                if (ok && !complete) {
-                    int *dst = stage + (size_t)(fill + __popc(nm & lt)) * out_stride;
-                    dst[0] = lp;
-                    for (int j = 0; j < l; j++) dst[1 + j] = sa[j];
-                    dst[1 + l] = a;
-                }
-                fill += __popc(nm);
-                if (fill + 32 > kStageItems) {   // flush
-                    __syncwarp();
-                    u64 ob = 0;
-                    if (lane == 0) ob = atomicAdd(A.out_count, (u64)fill);
-                    ob = __shfl_sync(0xffffffffu, ob, 0);
-                    if ((long long)ob + fill <= A.out_cap) {
-                        int *dst = A.out + (long long)ob * out_stride;
-                        for (int i = lane; i < fill * out_stride; i += 32) dst[i] = stage[i];
-                    }
-                    fill = 0;
-                    __syncwarp();
-                }
+        // an empty join box kills the partial match without touching its candidates
+        const bool boxed = valid && bx0 <= bx1 && by0 <= by1 && bz0 <= bz1;
+        // ---- lower bound of bx0 in the x-sorted list: G-ary search, warp-uniform trip count
+        int s_lo = 0, s_hi = cnt;
+        const bool narrow = boxed && l > 0 && cnt > 2 * G;
+        while (__any_sync(FULL, narrow && s_hi - s_lo > G)) {
+            const bool act = narrow && s_hi - s_lo > G;
+            const long long span = s_hi - s_lo;
+            float x = 0.f;
+            if (act) x = __ldg(&A.cand[coff + s_lo + (int)((span * (gl + 1)) / (G + 1))].x);
+            const unsigned less = (__ballot_sync(FULL, act && x < bx0) >> (grp * G)) & GM;
+            if (act) {
+                const int t = __popc(less);               // probes are monotone: lanes 0..t-1 are below the box
+                const int p_prev = s_lo + (int)((span * t) / (G + 1));
+                const int p_next = s_lo + (int)((span * (t + 1)) / (G + 1));
+                if (t < G) s_hi = p_next;
+                if (t > 0) s_lo = p_prev + 1;
             }
         }
+        // ---- scan ------------------------------------------------------------------------
+        {   // algorithm-independent work counter: every candidate of the level counts once
+            unsigned c_all = (valid && l > 0 && gl == 0) ? (unsigned)cnt : 0u;
+#pragma unroll
+            for (int o = 16; o >= G; o >>= 1) c_all += __shfl_down_sync(FULL, c_all, o);
+            if (lane == 0) n_cand += c_all;
+        }
+        bool live = boxed && s_lo < cnt;
+        int c = s_lo + gl;
+        while (__any_sync(FULL, live)) {
+            const bool in = live && c < cnt;
+            float4 cr = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (in) cr = __ldg(A.cand + coff + c);
+            const bool past = in && cr.x > bx1;
+            const bool ok = in && !past && cr.x >= bx0 && cr.y >= by0 && cr.y <= by1 && cr.z >= bz0 && cr.z <= bz1;
+            const unsigned inm = __ballot_sync(FULL, in);
+            const unsigned pm = __ballot_sync(FULL, past);
+            const unsigned okm = __ballot_sync(FULL, ok);
+            if (lane == 0) { n_scan += __popc(inm); n_box += __popc(okm); }
+            if (okm) {
+                if (ok) queue[qfill + __popc(okm & lt)] = make_int2(__float_as_int(cr.w), grp);
+                qfill += __popc(okm);
+                if (qfill >= 32) { qfill -= 32; drain(qfill, 32); }
+            }
+            if ((pm >> (grp * G)) & GM) live = false;      // sorted by x: nothing further can be inside
+            c += G;
+            if (c - gl >= cnt) live = false;
+        }
+        if (qfill > 0) { drain(0, qfill); qfill = 0; }
+        __syncwarp();   // the next batch overwrites chain/meta
     }
     __syncwarp();
     if (fill > 0) {
         u64 ob = 0;
         if (lane == 0) ob = atomicAdd(A.out_count, (u64)fill);
-        ob = __shfl_sync(0xffffffffu, ob, 0);
+        ob = __shfl_sync(FULL, ob, 0);
         if ((long long)ob + fill <= A.out_cap) {
             int *dst = A.out + (long long)ob * out_stride;
             for (int i = lane; i < fill * out_stride; i += 32) dst[i] = stage[i];
         }
     }
-    // statistics: one atomic per warp
-    u64 t64 = tests, b64 = boxed;
-    for (int o = 16; o > 0; o >>= 1) {
-        t64 += __shfl_down_sync(0xffffffffu, t64, o);
-        b64 += __shfl_down_sync(0xffffffffu, b64, o);
-    }
-    if (lane == 0 && t64) {
-        if (l > 0) atomicAdd(&A.ctr->cand_tests, t64);
-        atomicAdd(&A.ctr->box_pass, b64);
+    if (lane == 0) {   // statistics: lane 0 carries the warp totals
+        if (n_cand) atomicAdd(&A.ctr->cand_tests, n_cand);
+        if (n_scan) atomicAdd(&A.ctr->scan_tests, n_scan);
+        if (n_box) atomicAdd(&A.ctr->box_pass, n_box);
     }
 }
 
