@@ -157,7 +157,7 @@ class Result:
         return st.as_dict()
 
     def close(self):
-        if self._h:
+        if self._h and self.ctx._h:       # a result never outlives its context
             self.ctx.lib.jb_result_free(self._h)
         self._h = C.c_void_p()
 

@@ -6,6 +6,7 @@
 // canonically ordered hits.  No CPU fallback: without a CUDA device every entry
 // point fails with JB_ERR_CUDA.
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -17,6 +18,7 @@
 
 #include "../../include/jess_b200.h"
 #include "kernels.cuh"
+#include "hits.cuh"
 
 using namespace jb;
 
@@ -39,6 +41,11 @@ static int fail(int code, const char *fmt, ...)
             return fail(e_ == cudaErrorMemoryAllocation ? JB_ERR_NOMEM : JB_ERR_CUDA, "%s: %s (%s:%d)", \
                         #call, cudaGetErrorString(e_), __FILE__, __LINE__);                             \
     } while (0)
+
+static double now_ms()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 // ---- device buffers ---------------------------------------------------------------
 struct DevBuf {
@@ -101,13 +108,15 @@ struct jb_context {
     bool own_stream = false;
     int sm_count = 148;
     size_t ws_limit = 0;          // bytes the frontier buffers may use in total
-    int group = 8;                // lanes per partial match (JB_GROUP)
+    int group = 2;                // lanes per partial match (JB_GROUP)
     int debug = 0;                // JB_DEBUG: per-level counts and times on stderr
     cudaEvent_t lev[kMaxN + 1] = {};
     // workspace (grow only)
     DevBuf crec, chead, recs, fr[2], tuples, ctr;
-    DevBuf h_mol, h_tpl, h_atoms, h_rmsd, h_rot, h_c0, h_c1;
-    PinBuf p_mol, p_tpl, p_atoms, p_rmsd, p_rot, p_c0, p_c1;   // D2H landing zone of jb_result_fetch
+    DevBuf h_mol, h_tpl, h_atoms, h_rmsd, h_rot, h_c0, h_c1;   // hits as k_superpose appends them
+    DevBuf f_mol, f_tpl, f_atoms, f_rmsd, f_rot, f_c0, f_c1;   // ... in canonical order (hits.cuh)
+    DevBuf o_off, o_fill, o_grouped, o_order, o_tiles;         // ordering workspace
+    std::vector<std::pair<void *, size_t>> pin_pool;           // page-locked result blocks, recycled
     long long hit_cap = 0;
     int hit_stride = 0;
     Counters *host_ctr = nullptr; // pinned
@@ -142,8 +151,11 @@ struct jb_result {
     int n_templates = 0;
     jb_stats stats{};
     bool fetched = false;
-    std::vector<int32_t> mol, tpl, atoms;
-    std::vector<double> rmsd, rot, c0, c1;
+    void *block = nullptr;    // page-locked host block holding the fetched arrays (from ctx->pin_pool)
+    size_t block_bytes = 0;
+    long long kept = 0;       // records after best_match selection
+    int32_t *mol = nullptr, *tpl = nullptr, *atoms = nullptr;
+    double *rmsd = nullptr, *rot = nullptr, *c0 = nullptr, *c1 = nullptr;
 };
 
 // ---- library -----------------------------------------------------------------------
@@ -179,7 +191,7 @@ extern "C" int jb_context_create(int device, void *stream, int64_t workspace_byt
     c->ws_limit = workspace_bytes > 0 ? (size_t)workspace_bytes : total_b / 8;
     if (const char *g = getenv("JB_GROUP")) {
         int v = atoi(g);
-        if (v == 4 || v == 8 || v == 16 || v == 32) c->group = v;
+        if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) c->group = v;
     }
     if (const char *g = getenv("JB_DEBUG")) c->debug = atoi(g);
     if (c->debug) for (int i = 0; i <= kMaxN; i++) CU(cudaEventCreate(&c->lev[i]));
@@ -199,7 +211,8 @@ extern "C" void jb_context_destroy(jb_context *c)
     cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = { &c->crec, &c->chead, &c->recs, &c->fr[0], &c->fr[1],
                        &c->tuples, &c->ctr, &c->h_mol, &c->h_tpl, &c->h_atoms, &c->h_rmsd, &c->h_rot, &c->h_c0,
-                       &c->h_c1 };
+                       &c->h_c1, &c->f_mol, &c->f_tpl, &c->f_atoms, &c->f_rmsd, &c->f_rot, &c->f_c0, &c->f_c1,
+                       &c->o_off, &c->o_fill, &c->o_grouped, &c->o_order, &c->o_tiles };
     for (DevBuf *b : bufs) b->release();
     if (c->scratch_mol) {
         jb_molecules *m = c->scratch_mol;
@@ -207,8 +220,8 @@ extern "C" void jb_context_destroy(jb_context *c)
         delete m;
     }
     if (c->host_ctr) cudaFreeHost(c->host_ctr);
-    PinBuf *pins[] = { &c->p_mol, &c->p_tpl, &c->p_atoms, &c->p_rmsd, &c->p_rot, &c->p_c0, &c->p_c1 };
-    for (PinBuf *b : pins) b->release();
+    for (auto &blk : c->pin_pool) cudaFreeHost(blk.first);
+    c->pin_pool.clear();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (int i = 0; i < 5; i++) if (c->evs[i]) cudaEventDestroy(c->evs[i]);
@@ -339,6 +352,7 @@ extern "C" int jb_templates_spec_count(const jb_templates *t) { return t ? t->S 
 // ---- molecules --------------------------------------------------------------------------
 static int fill_molecules(jb_context *c, jb_molecules *m, const jb_molecule_batch *b)
 {
+    const double t_0 = now_ms();
     const int M = b->n_molecules;
     if (M < 0) return fail(JB_ERR_INVALID, "negative molecule count");
     m->ctx = c;
@@ -396,6 +410,7 @@ static int fill_molecules(jb_context *c, jb_molecules *m, const jb_molecule_batc
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess)
         return fail(e == cudaErrorMemoryAllocation ? JB_ERR_NOMEM : JB_ERR_CUDA, "molecule upload: %s", cudaGetErrorString(e));
+    if (c->debug) fprintf(stderr, "[jb] upload %d structures, %lld atoms: %.2f ms\n", M, m->NA, now_ms() - t_0);
     return JB_OK;
 }
 
@@ -424,15 +439,15 @@ extern "C" void jb_molecules_free(jb_molecules *m)
 // ---- query --------------------------------------------------------------------------------
 static size_t expand_smem(int group, int level) { return (size_t)kExpandWarps * expand_warp_bytes(group, level); }
 
-template <int G> static cudaError_t launch_expand(int grid, size_t smem, cudaStream_t st, const ExpandArgs &a)
+template <int G, bool STATS> static cudaError_t launch_expand(int grid, size_t smem, cudaStream_t st, const ExpandArgs &a)
 {
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_expand<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_expand<G, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    k_expand<G><<<grid, kExpandThreads, smem, st>>>(a);
+    k_expand<G, STATS><<<grid, kExpandThreads, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -452,6 +467,13 @@ static int grow_hits(jb_context *c, long long need, int stride)
     CU(c->h_rot.ensure(cap * 9 * sizeof(double), st, same ? keep * 9 * sizeof(double) : 0));
     CU(c->h_c0.ensure(cap * 3 * sizeof(double), st, same ? keep * 3 * sizeof(double) : 0));
     CU(c->h_c1.ensure(cap * 3 * sizeof(double), st, same ? keep * 3 * sizeof(double) : 0));
+    CU(c->f_mol.ensure(cap * sizeof(int), st, same ? keep * sizeof(int) : 0));
+    CU(c->f_tpl.ensure(cap * sizeof(int), st, same ? keep * sizeof(int) : 0));
+    CU(c->f_atoms.ensure(cap * sizeof(int) * stride, st, same ? keep * sizeof(int) * stride : 0));
+    CU(c->f_rmsd.ensure(cap * sizeof(double), st, same ? keep * sizeof(double) : 0));
+    CU(c->f_rot.ensure(cap * 9 * sizeof(double), st, same ? keep * 9 * sizeof(double) : 0));
+    CU(c->f_c0.ensure(cap * 3 * sizeof(double), st, same ? keep * 3 * sizeof(double) : 0));
+    CU(c->f_c1.ensure(cap * 3 * sizeof(double), st, same ? keep * 3 * sizeof(double) : 0));
     c->hit_cap = cap;
     c->hit_stride = stride;
     return JB_OK;
@@ -568,11 +590,13 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
             const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(3, (200 * 1024) / std::max<size_t>(smem, 1)));
             const int grid = c->sm_count * per_sm;
             cudaError_t e;
+            const bool stats = c->debug != 0;   // scan_tests / box_survivors are diagnostics (JB_DEBUG)
             switch (c->group) {
-            case 4: e = launch_expand<4>(grid, smem, st, A); break;
-            case 16: e = launch_expand<16>(grid, smem, st, A); break;
-            case 32: e = launch_expand<32>(grid, smem, st, A); break;
-            default: e = launch_expand<8>(grid, smem, st, A); break;
+            case 1: e = stats ? launch_expand<1, true>(grid, smem, st, A) : launch_expand<1, false>(grid, smem, st, A); break;
+            case 8: e = stats ? launch_expand<8, true>(grid, smem, st, A) : launch_expand<8, false>(grid, smem, st, A); break;
+            case 16: e = stats ? launch_expand<16, true>(grid, smem, st, A) : launch_expand<16, false>(grid, smem, st, A); break;
+            case 4: e = stats ? launch_expand<4, true>(grid, smem, st, A) : launch_expand<4, false>(grid, smem, st, A); break;
+            default: e = stats ? launch_expand<2, true>(grid, smem, st, A) : launch_expand<2, false>(grid, smem, st, A); break;
             }
             CU(e);
         }
@@ -646,8 +670,38 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         }
         if (retry) { S.retries++; continue; }
 
-        // ---- chunk done ------------------------------------------------------------------
+        // ---- chunk done: put its hits into canonical order on the device ------------------
         work.pop_back();
+        if (hc.hits > hits_done) {
+            const long long h0 = (long long)hits_done, h1 = (long long)hc.hits, nh = h1 - h0;
+            const int n_tiles = (int)((pairs + 1 + kScanTile - 1) / kScanTile);
+            CU(c->o_off.ensure((size_t)(pairs + 1) * sizeof(unsigned), st));
+            CU(c->o_fill.ensure((size_t)pairs * sizeof(unsigned), st));
+            CU(c->o_grouped.ensure((size_t)nh * sizeof(unsigned), st));
+            CU(c->o_order.ensure((size_t)nh * sizeof(unsigned), st));
+            CU(c->o_tiles.ensure((size_t)n_tiles * sizeof(unsigned), st));
+            CU(cudaMemsetAsync(c->o_off.p, 0, (size_t)(pairs + 1) * sizeof(unsigned), st));
+            CU(cudaMemsetAsync(c->o_fill.p, 0, (size_t)pairs * sizeof(unsigned), st));
+            HitOrderArgs OA;
+            OA.h0 = h0; OA.h1 = h1; OA.mol_base = r.m0; OA.n_templates = t->T; OA.stride = c->hit_stride;
+            OA.mol = HB.mol; OA.tpl = HB.tpl; OA.atoms = HB.atoms;
+            OA.off = c->o_off.as<unsigned>(); OA.fill = c->o_fill.as<unsigned>();
+            OA.grouped = c->o_grouped.as<unsigned>(); OA.order = c->o_order.as<unsigned>();
+            const unsigned hb = (unsigned)((nh + 255) / 256);
+            k_hit_hist<<<hb, 256, 0, st>>>(OA);
+            k_scan_tiles<<<n_tiles, kScanThreads, 0, st>>>(OA.off, pairs + 1, c->o_tiles.as<unsigned>());
+            k_scan_totals<<<1, kScanThreads, 0, st>>>(c->o_tiles.as<unsigned>(), n_tiles);
+            k_scan_add<<<n_tiles, kScanThreads, 0, st>>>(OA.off, pairs + 1, c->o_tiles.as<unsigned>());
+            k_hit_group<<<hb, 256, 0, st>>>(OA);
+            k_hit_rank<<<hb, 256, 0, st>>>(OA);
+            HitBuf FB = HB;
+            FB.mol = c->f_mol.as<int>(); FB.tpl = c->f_tpl.as<int>(); FB.atoms = c->f_atoms.as<int>();
+            FB.rmsd = c->f_rmsd.as<double>(); FB.rot = c->f_rot.as<double>(); FB.c0 = c->f_c0.as<double>();
+            FB.c1 = c->f_c1.as<double>();
+            k_hit_gather<<<(unsigned)((nh * 32 + 255) / 256), 256, 0, st>>>(h0, h1, c->hit_stride, OA.order, HB, FB);
+            CU(cudaGetLastError());
+            S.launches += 7;
+        }
         hits_done = hc.hits;
         S.chunks++;
         S.live_pairs += (int64_t)hc.live_pairs;
@@ -697,40 +751,7 @@ extern "C" int jb_query_run(jb_context *c, const jb_templates *t, const jb_molec
     return JB_OK;
 }
 
-// Canonical order (molecule, template, atom tuple): LSD radix sort of the (molecule,
-// template) key in 16-bit digits, then a comparison sort inside each (usually tiny) run.
-static void canonical_order(size_t n, int n_templates, const int32_t *mol, const int32_t *tpl, const int32_t *atoms,
-                            size_t stride, std::vector<uint32_t> &perm)
-{
-    perm.resize(n);
-    std::iota(perm.begin(), perm.end(), 0u);
-    if (n < 2) return;
-    std::vector<uint64_t> key(n);
-    uint64_t kmax = 0;
-    const uint64_t T = (uint64_t)std::max(n_templates, 1);
-    for (size_t i = 0; i < n; i++) { key[i] = (uint64_t)(uint32_t)mol[i] * T + (uint64_t)(uint32_t)tpl[i]; kmax = std::max(kmax, key[i]); }
-    std::vector<uint32_t> tmp(n);
-    std::vector<size_t> count(65537);
-    for (int shift = 0; shift < 64 && (kmax >> shift) != 0; shift += 16) {
-        std::fill(count.begin(), count.end(), (size_t)0);
-        for (size_t i = 0; i < n; i++) count[((key[perm[i]] >> shift) & 0xffff) + 1]++;
-        for (size_t d = 0; d < 65536; d++) count[d + 1] += count[d];
-        for (size_t i = 0; i < n; i++) tmp[count[(key[perm[i]] >> shift) & 0xffff]++] = perm[i];
-        perm.swap(tmp);
-    }
-    for (size_t i = 0; i < n;) {
-        size_t j = i + 1;
-        while (j < n && key[perm[j]] == key[perm[i]]) j++;
-        if (j - i > 1)
-            std::sort(perm.begin() + i, perm.begin() + j, [&](uint32_t a, uint32_t b) {
-                const int32_t *pa = atoms + (size_t)a * stride, *pb = atoms + (size_t)b * stride;
-                for (size_t k = 0; k < stride; k++)
-                    if (pa[k] != pb[k]) return pa[k] < pb[k];
-                return false;
-            });
-        i = j;
-    }
-}
+static size_t align64(size_t v) { return (v + 63) & ~(size_t)63; }
 
 extern "C" int jb_result_fetch(jb_result *r, jb_hits *out)
 {
@@ -738,62 +759,68 @@ extern "C" int jb_result_fetch(jb_result *r, jb_hits *out)
     jb_context *c = r->ctx;
     CU(cudaSetDevice(c->device));
     if (!r->fetched) {
+        const double t_0 = now_ms();
         const size_t n = (size_t)r->count, stride = (size_t)r->stride;
-        if (n > 0xffffffffull) return fail(JB_ERR_CAPACITY, "more than 2^32 hits in one result");
-        const int32_t *mol = nullptr, *tpl = nullptr, *atoms = nullptr;
-        const double *rmsd = nullptr, *rot = nullptr, *c0 = nullptr, *c1 = nullptr;
+        // one page-locked block for the seven arrays, recycled through the context's pool
+        const size_t o_mol = 0, o_tpl = o_mol + align64(n * 4), o_atoms = o_tpl + align64(n * 4),
+                     o_rmsd = o_atoms + align64(n * stride * 4), o_rot = o_rmsd + align64(n * 8),
+                     o_c0 = o_rot + align64(n * 72), o_c1 = o_c0 + align64(n * 24), total = o_c1 + align64(n * 24) + 64;
+        for (size_t i = 0; i < c->pin_pool.size(); i++)
+            if (c->pin_pool[i].second >= total) {
+                r->block = c->pin_pool[i].first; r->block_bytes = c->pin_pool[i].second;
+                c->pin_pool.erase(c->pin_pool.begin() + i);
+                break;
+            }
+        if (!r->block) {
+            const size_t want = total + total / 4;
+            CU(cudaMallocHost(&r->block, want));
+            r->block_bytes = want;
+        }
+        char *base = static_cast<char *>(r->block);
+        r->mol = reinterpret_cast<int32_t *>(base + o_mol); r->tpl = reinterpret_cast<int32_t *>(base + o_tpl);
+        r->atoms = reinterpret_cast<int32_t *>(base + o_atoms); r->rmsd = reinterpret_cast<double *>(base + o_rmsd);
+        r->rot = reinterpret_cast<double *>(base + o_rot); r->c0 = reinterpret_cast<double *>(base + o_c0);
+        r->c1 = reinterpret_cast<double *>(base + o_c1);
         if (n) {
             cudaStream_t st = c->stream;
-            CU(c->p_mol.ensure(n * sizeof(int))); CU(c->p_tpl.ensure(n * sizeof(int)));
-            CU(c->p_atoms.ensure(n * stride * sizeof(int))); CU(c->p_rmsd.ensure(n * sizeof(double)));
-            CU(c->p_rot.ensure(n * 9 * sizeof(double))); CU(c->p_c0.ensure(n * 3 * sizeof(double)));
-            CU(c->p_c1.ensure(n * 3 * sizeof(double)));
-            CU(cudaMemcpyAsync(c->p_mol.p, c->h_mol.p, n * sizeof(int), cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(c->p_tpl.p, c->h_tpl.p, n * sizeof(int), cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(c->p_atoms.p, c->h_atoms.p, n * stride * sizeof(int), cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(c->p_rmsd.p, c->h_rmsd.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(c->p_rot.p, c->h_rot.p, n * 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(c->p_c0.p, c->h_c0.p, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(c->p_c1.p, c->h_c1.p, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(r->mol, c->f_mol.p, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(r->tpl, c->f_tpl.p, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(r->atoms, c->f_atoms.p, n * stride * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(r->rmsd, c->f_rmsd.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(r->rot, c->f_rot.p, n * 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(r->c0, c->f_c0.p, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(r->c1, c->f_c1.p, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
-            mol = c->p_mol.as<int32_t>(); tpl = c->p_tpl.as<int32_t>(); atoms = c->p_atoms.as<int32_t>();
-            rmsd = c->p_rmsd.as<double>(); rot = c->p_rot.as<double>(); c0 = c->p_c0.as<double>(); c1 = c->p_c1.as<double>();
         }
-        std::vector<uint32_t> perm;
-        canonical_order(n, r->n_templates, mol, tpl, atoms, stride, perm);
-        if (r->best_match) {
-            // keep the smallest RMSD per (molecule, template); ties -> first in canonical
-            // order (the reference keeps the first in ITS iteration order, _jess.pyx:2238)
-            std::vector<uint32_t> keep;
+        r->kept = (long long)n;
+        if (r->best_match && n) {
+            // keep the smallest RMSD per (molecule, template), compacting in place; ties -> first
+            // in canonical order (the reference keeps the first in ITS iteration order, _jess.pyx:2238)
+            size_t w = 0;
             for (size_t i = 0; i < n;) {
                 size_t j = i, best = i;
-                while (j < n && mol[perm[j]] == mol[perm[i]] && tpl[perm[j]] == tpl[perm[i]]) {
-                    if (rmsd[perm[j]] < rmsd[perm[best]]) best = j;
+                while (j < n && r->mol[j] == r->mol[i] && r->tpl[j] == r->tpl[i]) {
+                    if (r->rmsd[j] < r->rmsd[best]) best = j;
                     j++;
                 }
-                keep.push_back(perm[best]);
+                r->mol[w] = r->mol[best]; r->tpl[w] = r->tpl[best]; r->rmsd[w] = r->rmsd[best];
+                memmove(&r->atoms[w * stride], &r->atoms[best * stride], stride * sizeof(int32_t));
+                memmove(&r->rot[w * 9], &r->rot[best * 9], 9 * sizeof(double));
+                memmove(&r->c0[w * 3], &r->c0[best * 3], 3 * sizeof(double));
+                memmove(&r->c1[w * 3], &r->c1[best * 3], 3 * sizeof(double));
+                w++;
                 i = j;
             }
-            perm.swap(keep);
-        }
-        const size_t k = perm.size();
-        r->mol.resize(k); r->tpl.resize(k); r->atoms.resize(k * stride);
-        r->rmsd.resize(k); r->rot.resize(k * 9); r->c0.resize(k * 3); r->c1.resize(k * 3);
-        for (size_t i = 0; i < k; i++) {
-            const size_t s = perm[i];
-            r->mol[i] = mol[s]; r->tpl[i] = tpl[s]; r->rmsd[i] = rmsd[s];
-            memcpy(&r->atoms[i * stride], &atoms[s * stride], stride * sizeof(int32_t));
-            memcpy(&r->rot[i * 9], &rot[s * 9], 9 * sizeof(double));
-            memcpy(&r->c0[i * 3], &c0[s * 3], 3 * sizeof(double));
-            memcpy(&r->c1[i * 3], &c1[s * 3], 3 * sizeof(double));
+            r->kept = (long long)w;
         }
         r->fetched = true;
+        if (c->debug) fprintf(stderr, "[jb] fetch %zu hits: %.2f ms\n", n, now_ms() - t_0);
     }
-    out->count = (int64_t)r->mol.size();
+    out->count = (int64_t)r->kept;
     out->stride = r->stride;
     out->reserved = 0;
-    out->molecule = r->mol.data(); out->template_index = r->tpl.data(); out->atoms = r->atoms.data();
-    out->rmsd = r->rmsd.data(); out->rotation = r->rot.data(); out->centre0 = r->c0.data(); out->centre1 = r->c1.data();
+    out->molecule = r->mol; out->template_index = r->tpl; out->atoms = r->atoms;
+    out->rmsd = r->rmsd; out->rotation = r->rot; out->centre0 = r->c0; out->centre1 = r->c1;
     return JB_OK;
 }
 
@@ -804,7 +831,15 @@ extern "C" int jb_result_stats(jb_result *r, jb_stats *out)
     return JB_OK;
 }
 
-extern "C" void jb_result_free(jb_result *r) { delete r; }
+extern "C" void jb_result_free(jb_result *r)
+{
+    if (!r) return;
+    if (r->block) {   // recycled by the next fetch (bounded pool)
+        if (r->ctx->pin_pool.size() < 4) r->ctx->pin_pool.emplace_back(r->block, r->block_bytes);
+        else cudaFreeHost(r->block);
+    }
+    delete r;
+}
 
 extern "C" int jb_query_host(jb_context *c, const jb_templates *t, const jb_molecule_batch *b, const jb_query_params *q,
                              jb_result **out, jb_hits *hits)

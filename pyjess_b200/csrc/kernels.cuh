@@ -548,7 +548,7 @@ struct alignas(16) GroupMeta {   // per partial match of the current batch
     int complete;                // this level finishes the template
 };
 
-constexpr int kQueue = 64;       // per-warp survivor queue (entries)
+constexpr int kQueue = 96;       // per-warp survivor queue (entries): < 32 carried + 64 new
 
 __host__ __device__ constexpr size_t expand_warp_bytes(int group, int level)
 {
@@ -572,7 +572,7 @@ __host__ __device__ constexpr size_t expand_warp_bytes(int group, int level)
 //     chain/residue rules -- dense lanes instead of a divergent tail in the scan loop;
 //  5. accepted extensions are compacted into a per-warp staging buffer that is flushed
 //     to the next frontier with ONE global atomicAdd; finished tuples go to the tuple list.
-template <int G>
+template <int G, bool STATS>
 __global__ void __launch_bounds__(kExpandThreads, 3) k_expand(const ExpandArgs A)
 {
     constexpr int IPW = 32 / G;
@@ -751,23 +751,31 @@ __global__ void __launch_bounds__(kExpandThreads, 3) k_expand(const ExpandArgs A
         bool live = boxed && s_lo < cnt;
         int c = s_lo + gl;
         while (__any_sync(FULL, live)) {
-            const bool in = live && c < cnt;
-            float4 cr = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (in) cr = __ldg(A.cand + coff + c);
-            const bool past = in && cr.x > bx1;
-            const bool ok = in && !past && cr.x >= bx0 && cr.y >= by0 && cr.y <= by1 && cr.z >= bz0 && cr.z <= bz1;
-            const unsigned inm = __ballot_sync(FULL, in);
-            const unsigned pm = __ballot_sync(FULL, past);
-            const unsigned okm = __ballot_sync(FULL, ok);
-            if (lane == 0) { n_scan += __popc(inm); n_box += __popc(okm); }
-            if (okm) {
-                if (ok) queue[qfill + __popc(okm & lt)] = make_int2(__float_as_int(cr.w), grp);
-                qfill += __popc(okm);
+            // two candidates per lane and iteration: c and c + G (both loads in flight together)
+            const bool in0 = live && c < cnt, in1 = live && c + G < cnt;
+            float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+            if (in0) r0 = __ldg(A.cand + coff + c);
+            if (in1) r1 = __ldg(A.cand + coff + c + G);
+            const bool ok0 = in0 && r0.x >= bx0 && r0.x <= bx1 && r0.y >= by0 && r0.y <= by1 && r0.z >= bz0 && r0.z <= bz1;
+            const bool ok1 = in1 && r1.x >= bx0 && r1.x <= bx1 && r1.y >= by0 && r1.y <= by1 && r1.z >= bz0 && r1.z <= bz1;
+            const unsigned pm = __ballot_sync(FULL, (in0 && r0.x > bx1) || (in1 && r1.x > bx1));
+            const unsigned m0 = __ballot_sync(FULL, ok0);
+            const unsigned m1 = __ballot_sync(FULL, ok1);
+            if (STATS && lane == 0) {
+                n_scan += __popc(__ballot_sync(FULL, in0)) + __popc(__ballot_sync(FULL, in1));
+                n_box += __popc(m0) + __popc(m1);
+            } else if (STATS) { __ballot_sync(FULL, in0); __ballot_sync(FULL, in1); }
+            if (m0 | m1) {
+                const int k0 = __popc(m0);
+                if (ok0) queue[qfill + __popc(m0 & lt)] = make_int2(__float_as_int(r0.w), grp);
+                if (ok1) queue[qfill + k0 + __popc(m1 & lt)] = make_int2(__float_as_int(r1.w), grp);
+                qfill += k0 + __popc(m1);
+                if (qfill >= 64) { qfill -= 32; drain(qfill, 32); }
                 if (qfill >= 32) { qfill -= 32; drain(qfill, 32); }
             }
-            if ((pm >> (grp * G)) & GM) live = false;      // sorted by x: nothing further can be inside
-            c += G;
-            if (c - gl >= cnt) live = false;
+            c += 2 * G;
+            // sorted by x: nothing beyond the first record past the box can be inside
+            if (((pm >> (grp * G)) & GM) || c - gl >= cnt) live = false;
         }
         if (qfill > 0) { drain(0, qfill); qfill = 0; }
         __syncwarp();   // the next batch overwrites chain/meta

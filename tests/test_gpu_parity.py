@@ -51,13 +51,13 @@ def test_engine_matches_oracle(engine, oracle_lib, name):
 
 
 # ---- synthetic BASELINE configs 3-5 at oracle-friendly sizes --------------------------
-SYNTH = [("cfg3", 0.04, {}), ("cfg3dense", 0.05, {}), ("cfg4shard", 0.004, {}),
-         ("cfg5", 0.02, {"ignore_chain": None}), ("cfg5", 0.02, {"ignore_chain": "residues"}),
-         ("cfg5", 0.02, {"ignore_chain": "atoms"})]
+SYNTH = [("cfg3", 0.04, {}, 0), ("cfg3", 0.04, {}, 1), ("cfg3", 0.04, {}, 2),
+         ("cfg3dense", 0.03, {}, 1), ("cfg3dense", 0.03, {}, 2), ("cfg4shard", 0.004, {}, 1),
+         ("cfg5", 0.012, {"ignore_chain": None}, 1), ("cfg5", 0.012, {"ignore_chain": "residues"}, 1),
+         ("cfg5", 0.012, {"ignore_chain": "atoms"}, 2)]
 
 
-@pytest.mark.parametrize("name,scale,kw", SYNTH)
-@pytest.mark.parametrize("reorder", [0, 1, 2])
+@pytest.mark.parametrize("name,scale,kw,reorder", SYNTH)
 def test_synthetic_matches_oracle(engine, oracle_lib, name, scale, kw, reorder):
     from pyjess_b200 import synth
     from pyjess_b200._tables import query_params
