@@ -282,6 +282,18 @@ class HitTable:
         self.centre0 = grab(hits.centre0, (n, 3), np.float64)
         self.centre1 = grab(hits.centre1, (n, 3), np.float64)
 
+    @classmethod
+    def from_arrays(cls, molecule, template, atoms, rmsd, rotation, centre0, centre1) -> "HitTable":
+        self = cls.__new__(cls)
+        self.count, self.stride = int(len(molecule)), int(atoms.shape[1]) if atoms.ndim == 2 else 1
+        self._owner = None
+        self.molecule, self.template, self.atoms, self.rmsd = molecule, template, atoms, rmsd
+        self.rotation, self.centre0, self.centre1 = rotation, centre0, centre1
+        return self
+
+    def arrays(self):
+        return (self.molecule, self.template, self.atoms, self.rmsd, self.rotation, self.centre0, self.centre1)
+
     def keys(self):
         """Canonical hit identities: (molecule, template, atom-index tuple)."""
         return [

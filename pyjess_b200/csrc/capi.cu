@@ -586,17 +586,21 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
             A.tuples = c->tuples.as<int>(); A.tuple_cap = tuple_cap;
             A.ctr = dc;
             if (c->debug) CU(cudaEventRecord(c->lev[l], st));
-            const size_t smem = expand_smem(c->group, l);
-            const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(3, (200 * 1024) / std::max<size_t>(smem, 1)));
+            // lanes per partial match: the configured G, widened at deep levels so that at
+            // least two CTAs per SM fit their staging areas in shared memory
+            int g = c->group;
+            while (g < 16 && 2 * expand_smem(g, l) > 200 * 1024) g <<= 1;
+            const size_t smem = expand_smem(g, l);
+            const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(smem, 1)));
             const int grid = c->sm_count * per_sm;
-            cudaError_t e;
             const bool stats = c->debug != 0;   // scan_tests / box_survivors are diagnostics (JB_DEBUG)
-            switch (c->group) {
+            cudaError_t e;
+            switch (g) {
             case 1: e = stats ? launch_expand<1, true>(grid, smem, st, A) : launch_expand<1, false>(grid, smem, st, A); break;
-            case 8: e = stats ? launch_expand<8, true>(grid, smem, st, A) : launch_expand<8, false>(grid, smem, st, A); break;
-            case 16: e = stats ? launch_expand<16, true>(grid, smem, st, A) : launch_expand<16, false>(grid, smem, st, A); break;
+            case 2: e = stats ? launch_expand<2, true>(grid, smem, st, A) : launch_expand<2, false>(grid, smem, st, A); break;
             case 4: e = stats ? launch_expand<4, true>(grid, smem, st, A) : launch_expand<4, false>(grid, smem, st, A); break;
-            default: e = stats ? launch_expand<2, true>(grid, smem, st, A) : launch_expand<2, false>(grid, smem, st, A); break;
+            case 8: e = stats ? launch_expand<8, true>(grid, smem, st, A) : launch_expand<8, false>(grid, smem, st, A); break;
+            default: e = stats ? launch_expand<16, true>(grid, smem, st, A) : launch_expand<16, false>(grid, smem, st, A); break;
             }
             CU(e);
         }

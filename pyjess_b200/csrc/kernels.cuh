@@ -573,7 +573,7 @@ __host__ __device__ constexpr size_t expand_warp_bytes(int group, int level)
 //  5. accepted extensions are compacted into a per-warp staging buffer that is flushed
 //     to the next frontier with ONE global atomicAdd; finished tuples go to the tuple list.
 template <int G, bool STATS>
-__global__ void __launch_bounds__(kExpandThreads, 3) k_expand(const ExpandArgs A)
+__global__ void __launch_bounds__(kExpandThreads, 4) k_expand(const ExpandArgs A)
 {
     constexpr int IPW = 32 / G;
     constexpr unsigned GM = G == 32 ? 0xffffffffu : ((1u << G) - 1u);

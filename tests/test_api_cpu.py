@@ -1,0 +1,83 @@
+"""CPU-only behaviour of the drop-in surface that needs no engine call (reference:
+src/pyjess/tests/test_jess.py:18-94, test_template.py:128-132, test_atom.py)."""
+import pickle
+
+import pytest
+
+from _util import load_molecule, load_template
+from pyjess_b200 import Atom, Jess, Molecule, Template, TemplateAtom
+
+
+def test_empty_jess_and_empty_molecule_need_no_gpu():
+    jess = Jess()
+    assert len(jess) == 0 and not jess
+    with pytest.raises(StopIteration):
+        next(jess.query(Molecule(), 2, 2, 4))
+    with pytest.raises(StopIteration):
+        next(Jess([load_template("template_01.qry")]).query(Molecule(), 2, 2, 4))
+
+
+def test_jess_container_protocol():
+    t1, t2 = load_template("template_01.qry"), load_template("template_02.qry")
+    j1, j2, j3 = Jess([t1, t2]), Jess([t1, t2]), Jess([t1])
+    assert j1 == j2 and j1 is not j2 and hash(j1) == hash(j2)
+    assert j1 != j3 and hash(j1) != hash(j3)
+    assert j1.copy() == j1 and pickle.loads(pickle.dumps(j1)) == j1
+    assert j1[0] is t1 and j1[-1] is t2 and len(j1[:1]) == 1 and len(j1[2:]) == 0
+    with pytest.raises(IndexError):
+        j1[2]
+    with pytest.raises(TypeError):
+        Jess([object()])
+    assert Jess() == Jess() and hash(Jess()) == hash(Jess())
+
+
+def test_query_argument_validation_matches_reference():
+    jess = Jess([load_template("template_01.qry")])
+    mol = load_molecule("pdb1a0p.ent")
+    with pytest.raises(ValueError):
+        jess.query(mol, 2, 2, 2, ignore_chain="all")
+    with pytest.raises(ValueError):
+        jess.query(mol, 2, 2, 2, max_candidates=-1)
+    with pytest.raises(TypeError):
+        jess.query(object(), 2, 2, 2)
+    q = jess.query(mol, 2, 3, 4, best_match=True, ignore_chain="atoms")
+    assert q.jess is jess and q.molecule is mol and q.rmsd_threshold == 2.0
+    assert q.best_match is True and q.ignore_chain == "atoms" and q.max_candidates is None
+
+
+def test_template_dimension_counts_residues_across_chains():
+    assert load_template("1sur.qry").dimension == 4          # test_template.py:128-132
+    assert load_template("template_01.qry").dimension == 4
+
+
+def test_template_roundtrips():
+    tpl = load_template("1.3.3.tpl")
+    assert Template.loads(tpl.dumps(), id=tpl.id) == tpl
+    assert pickle.loads(pickle.dumps(tpl)) == tpl and tpl.copy() == tpl
+    assert [a.match_mode for a in tpl][:3] == [a.match_mode for a in Template.loads(tpl.dumps())][:3]
+
+
+def test_atom_parse_and_token_rules():
+    """Names shorter than 4 are right-shifted by one '_' (SURVEY 7.3-h)."""
+    atom = Atom.loads("ATOM   1112  ND1 HIS E 142      47.130  25.140  -6.840  1.00 10.22           N")
+    assert (atom.serial, atom.name, atom.residue_name, atom.chain_id, atom.residue_number) == \
+        (1112, "ND1", "HIS", "E", 142)
+    assert (atom.x, atom.y, atom.z) == (47.13, 25.14, -6.84)
+    assert pickle.loads(pickle.dumps(atom)) == atom
+    built = Atom(serial=1112, name="ND1", residue_name="HIS", chain_id="E", residue_number=142,
+                 x=47.13, y=25.14, z=-6.84, occupancy=1.0, temperature_factor=10.22, element="N")
+    assert built.name == "ND1" and bytes(built._rec["name"][0]) == b"_ND1"
+    tatom = TemplateAtom(chain_id="A", residue_number=1, x=0, y=0, z=0, residue_names=["HIS"],
+                         atom_names=["ND1"], distance_weight=0.0, match_mode=0)
+    assert list(tatom.atom_names) == ["ND1"] and list(tatom.residue_names) == ["HIS"]
+    with pytest.raises(ValueError):
+        TemplateAtom(chain_id="A", residue_number=1, x=0, y=0, z=0, residue_names=["HIS"], atom_names=["ND1"],
+                     distance_weight=0.0, match_mode=42)
+
+
+def test_molecule_basics():
+    mol = load_molecule("pdb1lnb.ent")
+    assert mol.id == "1LNB" and len(mol) > 2000
+    assert len(mol.conserved(10.0)) < len(mol)
+    assert pickle.loads(pickle.dumps(mol)) == mol and mol.copy() == mol
+    assert len(mol[:10]) == 10 and mol[0].serial == 1

@@ -1,0 +1,209 @@
+"""The drop-in Python surface (`Jess.query` -> `Query` -> `Hit`) on the GPU, checked against the
+known answers the reference's own test-suite pins for this path (src/pyjess/tests/test_jess.py,
+test_hit.py -- cited per test).  Reads like the reference's tests on purpose: a PyJess user
+switching packages runs the same assertions."""
+import math
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+from _util import DATA, load_molecule, load_template
+from pyjess_b200 import Jess, Molecule, Template
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lnb():
+    return load_molecule("pdb1lnb.ent")
+
+
+def test_query_thresholds_counts_and_scores(lnb):
+    """test_jess.py:158-211: 1/2/3 hits, RMSD 0.555/1.440/1.644, det 1, logE -2.04/0.17/0.68."""
+    template = load_template("template_01.qry")
+    jess = Jess([template])
+    expect = {(1, 2, 2): [(0.555, -2.04)], (2, 5, 3): [(0.555, -2.04), (1.440, 0.17)],
+              (2, 5, 5): [(0.555, -2.04), (1.440, 0.17), (1.644, 0.68)]}
+    for args, rows in expect.items():
+        hits = sorted(jess.query(lnb, *args), key=lambda h: h.rmsd)
+        assert len(hits) == len(rows)
+        for hit, (rmsd, loge) in zip(hits, rows):
+            assert hit.template() is template
+            assert hit.rmsd == pytest.approx(rmsd, abs=5e-4)
+            assert hit.determinant == pytest.approx(1.0, abs=1e-3)
+            assert hit.log_evalue == pytest.approx(loge, abs=0.05)
+            assert hit.evalue == pytest.approx(math.exp(loge), abs=0.05)
+    hits = list(jess.query(lnb.conserved(10.0), 1, 2, 2))
+    assert len(hits) == 1 and hits[0].log_evalue == pytest.approx(-2.10, abs=0.05)
+
+
+def test_best_match_with_repeated_template(lnb):
+    """test_jess.py:213-227: three copies of one template -> three hits, all the best RMSD."""
+    template = load_template("template_01.qry")
+    hits = list(Jess([template, template, template]).query(lnb, 2, 5, 5, best_match=True))
+    assert len(hits) == 3
+    for hit in hits:
+        assert hit.template() is template
+        assert hit.rmsd == pytest.approx(0.555, abs=5e-4)
+
+
+def test_template_subclass_identity(lnb):
+    """test_jess.py:118-133."""
+    class MyTemplate(Template):
+        pass
+    template = MyTemplate.load(os.path.join(DATA, "template_01.qry"))
+    jess = Jess([template])
+    assert isinstance(jess[0], MyTemplate) and jess[0] == template
+    hits = list(jess.query(lnb, 1, 2, 2))
+    assert hits[0].template() is template
+
+
+def _golden_blocks():
+    with open(os.path.join(DATA, "1AMY+1.3.3.txt")) as f:
+        return [b for b in f.read().split("REMARK") if b.strip()]
+
+
+@pytest.mark.parametrize("reorder", [True, False])
+def test_mcsa_query_matches_original_jess_output(reorder):
+    """test_jess.py:229-335: 1.3.3.tpl x 1AMY at (2, 4, 4) against the 156 hit blocks written
+    by the ORIGINAL Jess binary; hits are matched by their atom-serial tuples."""
+    template = load_template("1.3.3.tpl")
+    molecule = load_molecule("1AMY.pdb")
+    blocks = {}
+    for block in _golden_blocks():
+        lines = block.strip().splitlines()
+        blocks[tuple(int(line[6:11]) for line in lines[1:-1])] = lines
+    hits = list(Jess([template]).query(molecule, 2, 4, 4, reorder=reorder))
+    assert len(hits) == len(blocks) == 156
+    seen = set()
+    for hit in hits:
+        serials = tuple(a.serial for a in hit.atoms(transform=False))
+        lines = blocks[serials]
+        seen.add(serials)
+        query_id, rmsd, _tid, _, det, _, loge = lines[0].split()
+        assert query_id == "1AMY"
+        assert hit.rmsd == pytest.approx(float(rmsd), abs=5e-4)
+        assert hit.determinant == pytest.approx(float(det), abs=0.05)
+        assert hit.log_evalue == pytest.approx(float(loge), abs=0.05)
+        for atom, line in zip(hit.atoms(), lines[1:-1]):
+            assert atom.name == line[12:16].strip() and atom.residue_name == line[17:20].strip()
+            assert atom.chain_id == line[20:22].strip() and atom.residue_number == int(line[22:26])
+            assert (atom.x, atom.y, atom.z) == pytest.approx(
+                (float(line[30:38]), float(line[38:46]), float(line[46:54])), abs=1.5e-3)
+    assert len(seen) == 156
+
+
+@pytest.mark.parametrize("mode,count", [(None, 0), ("residues", 2), ("atoms", 7)])
+def test_ignore_chain_modes(mode, count):
+    """test_jess.py:337-372."""
+    template = load_template("4.1.2.tpl")
+    molecule = load_molecule("5ayx.EF.pdb")
+    hits = list(Jess([template]).query(molecule, 3, 3, 3, ignore_chain=mode))
+    assert len(hits) == count
+    if mode == "residues":
+        for hit in hits:
+            atoms = hit.atoms(transform=False)
+            for a, b in zip(atoms, atoms[1:]):
+                if a.residue_number == b.residue_number:
+                    assert a.chain_id == b.chain_id
+
+
+def test_ignore_chain_bool_is_deprecated(lnb):
+    template = load_template("template_01.qry")
+    with pytest.warns(DeprecationWarning):
+        assert len(list(Jess([template]).query(lnb, 1, 2, 2, ignore_chain=True))) == 1
+    with pytest.raises(ValueError):
+        Jess([template]).query(lnb, 1, 2, 2, ignore_chain="all")
+
+
+def test_hit_dump_text_and_pickle(lnb):
+    """test_hit.py:27-57: exact PDB text of the first hit; pickle round trip."""
+    template = Template.load(os.path.join(DATA, "template_01.qry"), id="T1")
+    hit = next(Jess([template]).query(lnb, 1, 2, 2))
+    expected = """REMARK 1LNB 0.555 T1 Det= 1.0 log(E)~ -2.04
+ATOM   1112  ND1 HIS E 142       4.157  -2.574   4.091  1.00 10.22           N
+ATOM   1115  NE2 HIS E 142       3.805  -2.316   1.890  1.00 16.00           N
+ATOM   1123  OE1 GLU E 143       0.480  -4.544  -0.363  1.00 14.72           O
+ATOM   1124  OE2 GLU E 143       1.870  -6.097   0.337  1.00 22.48           O
+ATOM   1145  CG  HIS E 146       0.031   0.017   0.019  1.00 12.45           C
+ATOM   1146  ND1 HIS E 146       0.823   1.160   0.000  1.00 15.79           N
+ATOM   1147  CD2 HIS E 146       0.878  -1.064   0.006  1.00 20.85           C
+ATOM   1148  CE1 HIS E 146       2.115   0.777  -0.013  1.00 13.50           C
+ATOM   1149  NE2 HIS E 146       2.181  -0.553  -0.032  1.00 12.44           N
+ATOM   1298  OE1 GLU E 166       6.432  -0.605   1.056  1.00 16.03           O
+ATOM   1299  OE2 GLU E 166       4.839   0.070  -0.343  1.00 19.31           O
+ENDMDL"""
+    assert hit.dumps().strip() == expected
+    copy = pickle.loads(pickle.dumps(hit))
+    assert copy is not hit and copy.rmsd == hit.rmsd and copy.determinant == hit.determinant
+    assert copy.evalue == hit.evalue
+    assert copy.template(transform=False) == hit.template(transform=False)
+    assert copy.atoms(transform=True) == hit.atoms(transform=True)
+    assert copy.atoms(transform=False) == hit.atoms(transform=False)
+    assert copy.molecule(transform=False) == hit.molecule(transform=False)
+
+
+def test_hit_transformation_maps_atoms_onto_template(lnb):
+    template = load_template("template_01.qry")
+    hit = next(Jess([template]).query(lnb, 1, 2, 2))
+    moved = np.array([[a.x, a.y, a.z] for a in hit.atoms(transform=True)])
+    target = np.array([[a.x, a.y, a.z] for a in template])
+    assert math.sqrt(((moved - target) ** 2).sum() / len(target)) == pytest.approx(hit.rmsd, abs=1e-9)
+    m, inv = np.asarray(hit.transformation), np.asarray(hit.inverse_transformation)
+    assert np.abs(m @ inv - np.eye(4)).max() < 1e-9
+    back = hit.template(transform=True)
+    orig = np.array([[a.x, a.y, a.z] for a in hit.atoms(transform=False)])
+    assert math.sqrt(((np.array([[a.x, a.y, a.z] for a in back]) - orig) ** 2).sum() / len(orig)) == \
+        pytest.approx(hit.rmsd, abs=1e-9)
+
+
+def test_split_and_joint_template_sets_agree():
+    """test_jess.py:96-116: Jess([t1, t2]) finds exactly the hits of Jess([t1]) and Jess([t2])."""
+    t1, t2 = load_template("template_01.qry"), load_template("template_02.qry")
+    molecule = load_molecule("1AMY.pdb")
+    key = lambda h: (h.template().id, tuple(a.serial for a in h.atoms(False)))  # noqa: E731
+    joint = list(Jess([t1, t2]).query(molecule, 2, 5, 5))
+    split = list(Jess([t1]).query(molecule, 2, 5, 5)) + list(Jess([t2]).query(molecule, 2, 5, 5))
+    assert sorted(map(key, joint)) == sorted(map(key, split))
+    # templates come back in REVERSE insertion order (eff:Jess.c:109-117)
+    order = [h.template() for h in joint]
+    assert order == sorted(order, key=lambda t: 0 if t is t2 else 1)
+
+
+def test_query_many_equals_single_queries():
+    templates = [load_template(f"template_0{i}.qry") for i in (1, 2, 3)]
+    from _util import cfg2_molecules
+    mols = cfg2_molecules()[:12] + [Molecule()]
+    jess = Jess(templates)
+    batch = jess.query_many(mols, 2.0, 3.0, 3.0)
+    assert len(batch) == len(mols)
+    total = 0
+    for mol, query in zip(mols, batch):
+        assert query.molecule is mol
+        one = list(jess.query(mol, 2.0, 3.0, 3.0))
+        many = list(query)
+        total += len(many)
+        assert [(h.template().id, h.rmsd, tuple(a.serial for a in h.atoms(False))) for h in many] == \
+               [(h.template().id, h.rmsd, tuple(a.serial for a in h.atoms(False))) for h in one]
+    assert total > 0
+
+
+def test_max_candidates_is_refused_loudly(lnb):
+    """Order-dependent option of the reference's depth-first walk: validated
+    like the reference (test_jess.py:135-156) but not computed by the breadth-first engine."""
+    template = load_template("template_01.qry")
+    with pytest.raises(ValueError):
+        Jess([template]).query(lnb, 2, 5, 5, max_candidates=-1)
+    with pytest.raises(NotImplementedError):
+        next(Jess([template]).query(lnb, 2, 5, 5, max_candidates=2))
+
+
+def test_single_atom_template_is_refused_loudly(lnb):
+    from pyjess_b200 import TemplateAtom
+    from pyjess_b200._capi import EngineError
+    atom = TemplateAtom(chain_id="E", residue_number=142, x=0.0, y=0.0, z=0.0, residue_names=["HIS"],
+                        atom_names=["ND1"], distance_weight=0.0, match_mode=0)
+    with pytest.raises(EngineError):
+        list(Jess([Template([atom], id="one")]).query(lnb, 2, 5, 5))

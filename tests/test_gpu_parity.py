@@ -54,7 +54,7 @@ def test_engine_matches_oracle(engine, oracle_lib, name):
 SYNTH = [("cfg3", 0.04, {}, 0), ("cfg3", 0.04, {}, 1), ("cfg3", 0.04, {}, 2),
          ("cfg3dense", 0.03, {}, 1), ("cfg3dense", 0.03, {}, 2), ("cfg4shard", 0.004, {}, 1),
          ("cfg5", 0.012, {"ignore_chain": None}, 1), ("cfg5", 0.012, {"ignore_chain": "residues"}, 1),
-         ("cfg5", 0.012, {"ignore_chain": "atoms"}, 2)]
+         ("cfg5", 0.012, {"ignore_chain": "atoms"}, 1)]
 
 
 @pytest.mark.parametrize("name,scale,kw,reorder", SYNTH)
