@@ -141,6 +141,35 @@ def _rebuild_hit(state):
     return hit
 
 
+def _reference_first_candidate(molecule: Molecule, tatom, cand: np.ndarray):
+    """Index of the candidate the reference never reports for a SINGLE-ATOM template.
+
+    `Scanner_reuse` pre-selects candidate 0 of the first scan level and `Scanner_next`
+    pre-increments before yielding (eff:Scanner.c:176-181, 212-227), so with n == 1 the
+    first entry of the reference's candidate list is skipped.  That list is built by
+    `TessTemplate_candidates` (eff:TessTemplate.c:141-201): for match modes -1..8 by
+    walking the template atom's residue names in order through the residue index, whose
+    groups are sorted by serial (eff:ResIndex.c:18-27); for the other modes in molecule
+    order.  `cand` = atom indices of all candidates of the pair."""
+    if len(cand) == 0:
+        return None
+    atoms = molecule._atoms
+    if -1 <= tatom._code <= 8:
+        res = np.char.upper(atoms["resName"][cand])
+        done = set()
+        for name in tatom._resnames:
+            tok = name.ljust(4, b"\0")[:4].upper().rstrip(b"\0")
+            if tok in done:
+                continue
+            done.add(tok)
+            sel = cand[res == tok]
+            if len(sel):
+                order = np.lexsort((sel, atoms["serial"][sel]))
+                return int(sel[order[0]])
+        return None
+    return int(cand.min())
+
+
 class _BatchRun:
     """Shared, lazily executed engine call of one `query` / `query_many`."""
 
@@ -172,11 +201,25 @@ class _BatchRun:
         if self.stats["nan_dropped"]:
             warnings.warn("Jess returned a superposition matrix with NaN values", UserWarning, stacklevel=4)
         t = self.table
+        # single-atom templates: the engine reports every candidate, the reference never its first one
+        single = [i for i, tpl in enumerate(jess._templates) if len(tpl) == 1]
+        keep = None
+        if single and t.count:
+            keep = np.ones(t.count, dtype=bool)
+            for i in single:
+                rows = np.nonzero(t.template == i)[0]
+                for m in np.unique(t.molecule[rows]):
+                    sel = rows[t.molecule[rows] == m]
+                    first = _reference_first_candidate(mols[int(m)], jess._templates[i][0], t.atoms[sel, 0])
+                    if first is not None:
+                        keep[sel[t.atoms[sel, 0] == first]] = False
         # iteration order per structure: template DESCENDING (reverse insertion), canonical tuple order within
         slices = []
         bounds = np.searchsorted(t.molecule, np.arange(len(mols) + 1))
         for m in range(len(mols)):
             idx = np.arange(bounds[m], bounds[m + 1])
+            if keep is not None:
+                idx = idx[keep[idx]]
             if len(idx):
                 idx = idx[np.argsort(-t.template[idx], kind="stable")]
             slices.append(idx)

@@ -243,13 +243,13 @@ class MoleculeBatch:
 
 def query_params(rmsd_threshold, distance_cutoff, max_dynamic_distance, ignore_chain=None,
                  reorder=True, best_match=False) -> jb_query_params:
-    """`reorder`: True -> 1 (the reference's argsort by |C_k|), False -> 0 (template
-    order); an int selects the mode explicitly (2 = experimental fan-out heuristic).
-    The hit set never depends on it."""
+    """`reorder`: True -> 2 (the engine's expected-fan-out scan order), False -> 0
+    (template order); an int selects the mode explicitly (1 = the reference's argsort
+    by |C_k|).  The hit set never depends on it."""
     if ignore_chain not in IGNORE_CHAIN:
         raise ValueError(f"invalid value for `ignore_chain`: {ignore_chain!r}")
     if isinstance(reorder, bool):
-        reorder = 1 if reorder else 0
+        reorder = 2 if reorder else 0
     return jb_query_params(float(rmsd_threshold), float(distance_cutoff), float(max_dynamic_distance),
                            IGNORE_CHAIN[ignore_chain], int(reorder), int(bool(best_match)), 0)
 

@@ -112,10 +112,11 @@ struct jb_context {
     int debug = 0;                // JB_DEBUG: per-level counts and times on stderr
     cudaEvent_t lev[kMaxN + 1] = {};
     // workspace (grow only)
-    DevBuf crec, chead, recs, fr[2], tuples, ctr;
+    DevBuf crec, chead, recs, ordbuf, fr[2], tuples, ctr;
     DevBuf h_mol, h_tpl, h_atoms, h_rmsd, h_rot, h_c0, h_c1;   // hits as k_superpose appends them
     DevBuf f_mol, f_tpl, f_atoms, f_rmsd, f_rot, f_c0, f_c1;   // ... in canonical order (hits.cuh)
-    DevBuf o_off, o_fill, o_grouped, o_order, o_tiles;         // ordering workspace
+    DevBuf o_off, o_fill, o_grouped, o_order, o_tiles, o_runs, o_work;   // ordering workspace
+    RunWork *host_work = nullptr;                              // pinned
     std::vector<std::pair<void *, size_t>> pin_pool;           // page-locked result blocks, recycled
     long long hit_cap = 0;
     int hit_stride = 0;
@@ -196,6 +197,8 @@ extern "C" int jb_context_create(int device, void *stream, int64_t workspace_byt
     if (const char *g = getenv("JB_DEBUG")) c->debug = atoi(g);
     if (c->debug) for (int i = 0; i <= kMaxN; i++) CU(cudaEventCreate(&c->lev[i]));
     CU(cudaMallocHost(&c->host_ctr, sizeof(Counters)));
+    CU(cudaMallocHost(&c->host_work, sizeof(RunWork)));
+    CU(c->o_work.ensure(sizeof(RunWork), c->stream));
     CU(c->ctr.ensure(sizeof(Counters), c->stream));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
@@ -209,10 +212,10 @@ extern "C" void jb_context_destroy(jb_context *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = { &c->crec, &c->chead, &c->recs, &c->fr[0], &c->fr[1],
+    DevBuf *bufs[] = { &c->crec, &c->chead, &c->recs, &c->ordbuf, &c->fr[0], &c->fr[1],
                        &c->tuples, &c->ctr, &c->h_mol, &c->h_tpl, &c->h_atoms, &c->h_rmsd, &c->h_rot, &c->h_c0,
                        &c->h_c1, &c->f_mol, &c->f_tpl, &c->f_atoms, &c->f_rmsd, &c->f_rot, &c->f_c0, &c->f_c1,
-                       &c->o_off, &c->o_fill, &c->o_grouped, &c->o_order, &c->o_tiles };
+                       &c->o_off, &c->o_fill, &c->o_grouped, &c->o_order, &c->o_tiles, &c->o_runs, &c->o_work };
     for (DevBuf *b : bufs) b->release();
     if (c->scratch_mol) {
         jb_molecules *m = c->scratch_mol;
@@ -220,6 +223,7 @@ extern "C" void jb_context_destroy(jb_context *c)
         delete m;
     }
     if (c->host_ctr) cudaFreeHost(c->host_ctr);
+    if (c->host_work) cudaFreeHost(c->host_work);
     for (auto &blk : c->pin_pool) cudaFreeHost(blk.first);
     c->pin_pool.clear();
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -565,8 +569,15 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         k_classify<<<Mc, 256, classify_smem, st>>>(MT, ST, CT, dc);
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->evs[1], st));
-        k_pairs<<<(unsigned)((pairs + 127) / 128), 128, 0, st>>>(Mc, TT, t->S, CT.head, MT.atom_off, q->reorder,
-                                                                 c->recs.as<PairRec>(), dc);
+        if (q->reorder == 2) {
+            CU(c->ordbuf.ensure((size_t)pairs * kMaxN, st));
+            k_order<<<dim3((unsigned)t->T, (unsigned)((Mc + 127) / 128)), 128, 0, st>>>(
+                Mc, TT, t->S, CT.head, MT.atom_off, c->ordbuf.as<unsigned char>());
+            CU(cudaGetLastError());
+            S.launches++;
+        }
+        k_pairs<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(Mc, TT, t->S, CT.head, MT.atom_off, q->reorder,
+                                                                 c->ordbuf.as<unsigned char>(), c->recs.as<PairRec>(), dc);
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->evs[2], st));
 
@@ -698,13 +709,41 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
             k_scan_add<<<n_tiles, kScanThreads, 0, st>>>(OA.off, pairs + 1, c->o_tiles.as<unsigned>());
             k_hit_group<<<hb, 256, 0, st>>>(OA);
             k_hit_rank<<<hb, 256, 0, st>>>(OA);
+            S.launches += 7;
+            if (nh > (long long)kShortRun) {
+                // dense-hit pairs: segmented tiled bitonic sort of the long runs (hits.cuh)
+                const unsigned tile_cap = (unsigned)(nh / kTile + std::min<long long>(pairs, nh / kShortRun + 1) + 1);
+                CU(c->o_runs.ensure((size_t)tile_cap * sizeof(RunTile), st));
+                CU(cudaMemsetAsync(c->o_work.p, 0, sizeof(RunWork), st));
+                k_run_tiles<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(OA, pairs, c->o_runs.as<RunTile>(), tile_cap,
+                                                                             c->o_work.as<RunWork>());
+                CU(cudaMemcpyAsync(c->host_work, c->o_work.p, sizeof(RunWork), cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+                const unsigned nt = c->host_work->n_tiles, max_npad = c->host_work->max_npad;
+                if (nt > tile_cap) return fail(JB_ERR_CAPACITY, "hit ordering: %u tiles exceed the work list (%u)", nt, tile_cap);
+                S.launches++;
+                if (nt > 0) {
+                    const RunTile *rt = c->o_runs.as<RunTile>();
+                    k_tile_sort<<<nt, kTileThreads, 0, st>>>(OA, rt);
+                    S.launches++;
+                    for (unsigned k = 2u * kTile; k <= max_npad && k != 0; k <<= 1) {
+                        for (unsigned j = k >> 1; j >= (unsigned)kTile; j >>= 1) {
+                            k_run_stage<<<nt, kTileThreads, 0, st>>>(OA, rt, k, j);
+                            S.launches++;
+                        }
+                        k_tile_merge<<<nt, kTileThreads, 0, st>>>(OA, rt, k);
+                        S.launches++;
+                    }
+                    k_run_publish<<<nt, kTileThreads, 0, st>>>(OA, rt);
+                    S.launches++;
+                }
+            }
             HitBuf FB = HB;
             FB.mol = c->f_mol.as<int>(); FB.tpl = c->f_tpl.as<int>(); FB.atoms = c->f_atoms.as<int>();
             FB.rmsd = c->f_rmsd.as<double>(); FB.rot = c->f_rot.as<double>(); FB.c0 = c->f_c0.as<double>();
             FB.c1 = c->f_c1.as<double>();
             k_hit_gather<<<(unsigned)((nh * 32 + 255) / 256), 256, 0, st>>>(h0, h1, c->hit_stride, OA.order, HB, FB);
             CU(cudaGetLastError());
-            S.launches += 7;
         }
         hits_done = hc.hits;
         S.chunks++;
@@ -722,8 +761,6 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
             S.frontier_items += (int64_t)hc.level[l];
             S.frontier_ints += (int64_t)hc.level[l] * l;
         }
-        if (hc.unsupported)
-            return fail(JB_ERR_INVALID, "single-atom templates are not supported on the GPU path (%llu pairs)", hc.unsupported);
     }
     CU(cudaEventRecord(c->ev1, st));
     CU(cudaEventSynchronize(c->ev1));

@@ -11,7 +11,8 @@
 //   k_hit_hist    count hits per pair                      (atomicAdd, one per hit)
 //   scan          exclusive prefix sum over the pairs      (k_scan_*: 3 small kernels)
 //   k_hit_group   slot = off[pair] + ticket  -> index list grouped by pair
-//   k_hit_rank    rank of every hit inside its run by lexicographic tuple compare
+//   k_hit_rank    short runs: rank of every hit inside its run by lexicographic tuple compare
+//   k_run_* / k_tile_*  long runs (dense-hit pairs): segmented, tiled bitonic sort of the index lists
 //   k_hit_gather  hit records -> final arrays in canonical order (coalesced writes)
 #pragma once
 #include "kernels.cuh"
@@ -124,26 +125,164 @@ __global__ void __launch_bounds__(256) k_hit_group(HitOrderArgs A)
     A.grouped[A.off[p] + atomicAdd(&A.fill[p], 1u)] = (unsigned)(i - A.h0);
 }
 
+constexpr unsigned kShortRun = 48;   // runs up to this length are ranked, longer ones sorted by a CTA
+
+// other < mine in lexicographic tuple order
+__device__ __forceinline__ bool tuple_less(const int *other, const int *mine, int stride)
+{
+    for (int k = 0; k < stride; k++) {
+        const int a = other[k], b = mine[k];
+        if (a != b) return a < b;
+    }
+    return false;
+}
+
 __global__ void __launch_bounds__(256) k_hit_rank(HitOrderArgs A)
 {
     const long long i = A.h0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= A.h1) return;
     const long long p = hit_pair(A, i);
     const unsigned r0 = A.off[p], r1 = A.off[p + 1];
+    if (r1 - r0 > kShortRun) return;                          // k_hit_sort owns this run
     const int *mine = A.atoms + i * A.stride;
     unsigned rank = 0;
     for (unsigned r = r0; r < r1; r++) {
         const long long j = A.h0 + A.grouped[r];
-        if (j == i) continue;
-        const int *other = A.atoms + j * A.stride;
-        bool less = false;                                    // other < mine, lexicographic
-        for (int k = 0; k < A.stride; k++) {
-            const int a = other[k], b = mine[k];
-            if (a != b) { less = a < b; break; }
-        }
-        rank += less ? 1u : 0u;
+        if (j != i && tuple_less(A.atoms + j * A.stride, mine, A.stride)) rank++;
     }
     A.order[r0 + rank] = (unsigned)(i - A.h0);
+}
+
+// ---- long runs (dense-hit pairs: 10^2 .. 10^5 hits of ONE template in ONE structure) ----
+// Segmented bitonic sort of the index lists, tiled: a run of n indices is cut into tiles
+// of kTile; k_run_tiles builds the (run, tile) work list; k_tile_sort sorts every tile in
+// shared memory (all stages with k <= kTile); each larger merge k runs its wide stages
+// (j >= kTile) as one grid-wide launch per stage (k_run_stage) and its narrow stages
+// (j < kTile) again inside shared memory (k_tile_merge).  The network is the all-ascending
+// variant (first stage of a merge pairs i with i ^ (k-1), the rest i ^ j), so positions
+// beyond n act as +infinity and never move: no physical padding.  Comparisons look at a
+// 64-bit prefix (first two atoms) cached in shared memory first and gather the full tuples
+// from L2 only on a tie.
+constexpr int kTile = 2048;
+constexpr int kTileThreads = 512;
+
+struct alignas(16) RunTile {
+    unsigned r0;     // start of the run in grouped[]
+    unsigned n;      // run length
+    unsigned tile;   // tile index inside the run
+    unsigned npad;   // n rounded up to a power of two
+};
+
+struct RunWork {
+    unsigned n_tiles;
+    unsigned max_npad;
+};
+
+__global__ void __launch_bounds__(256) k_run_tiles(HitOrderArgs A, long long n_pairs, RunTile *tiles, unsigned cap,
+                                                   RunWork *work)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const unsigned r0 = A.off[p], n = A.off[p + 1] - r0;
+    if (n <= kShortRun) return;
+    unsigned npad = 1;
+    while (npad < n) npad <<= 1;
+    const unsigned nt = (n + kTile - 1) / kTile;
+    const unsigned base = atomicAdd(&work->n_tiles, nt);
+    atomicMax(&work->max_npad, npad);
+    for (unsigned t = 0; t < nt; t++)
+        if (base + t < cap) { RunTile e; e.r0 = r0; e.n = n; e.tile = t; e.npad = npad; tiles[base + t] = e; }
+}
+
+__device__ __forceinline__ u64 tuple_prefix(const int *row, int stride)
+{
+    const unsigned a = (unsigned)row[0] ^ 0x80000000u;                      // signed order -> unsigned order
+    const unsigned b = stride > 1 ? ((unsigned)row[1] ^ 0x80000000u) : 0u;
+    return ((u64)a << 32) | b;
+}
+
+// x > y for hits x, y (indices relative to h0) with cached prefixes
+__device__ __forceinline__ bool hit_greater(const HitOrderArgs &A, unsigned x, u64 kx, unsigned y, u64 ky)
+{
+    if (kx != ky) return kx > ky;
+    return tuple_less(A.atoms + (A.h0 + y) * A.stride, A.atoms + (A.h0 + x) * A.stride, A.stride);
+}
+
+// stages of one tile in shared memory: merges k_lo..k_hi, each from stage j_hi(k) down to 1
+template <bool FULL_SORT>
+__device__ __forceinline__ void tile_stages(const HitOrderArgs &A, const RunTile e, unsigned k_merge, unsigned *s_idx,
+                                            u64 *s_key)
+{
+    const unsigned base = e.tile * kTile;
+    const unsigned count = min((unsigned)kTile, e.n - base);
+    unsigned *idx = A.grouped + e.r0 + base;
+    for (unsigned i = threadIdx.x; i < count; i += kTileThreads) {
+        const unsigned h = idx[i];
+        s_idx[i] = h;
+        s_key[i] = tuple_prefix(A.atoms + (A.h0 + h) * A.stride, A.stride);
+    }
+    __syncthreads();
+    const unsigned k_first = FULL_SORT ? 2u : k_merge, k_last = FULL_SORT ? (unsigned)kTile : k_merge;
+    for (unsigned k = k_first; k <= k_last && k <= e.npad; k <<= 1) {
+        for (unsigned j = FULL_SORT ? (k >> 1) : (unsigned)(kTile >> 1); j > 0; j >>= 1) {
+            const unsigned flip = (j == (k >> 1)) ? (k - 1) : j;             // global index pairing
+            for (unsigned i = threadIdx.x; i < (unsigned)kTile; i += kTileThreads) {
+                const unsigned gi = base + i, gq = gi ^ flip;                // stays inside the tile: flip < kTile
+                const unsigned q = gq - base;
+                if (gq > gi && gq < e.n) {
+                    const unsigned x = s_idx[i], y = s_idx[q];
+                    const u64 kx = s_key[i], ky = s_key[q];
+                    if (hit_greater(A, x, kx, y, ky)) { s_idx[i] = y; s_idx[q] = x; s_key[i] = ky; s_key[q] = kx; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (unsigned i = threadIdx.x; i < count; i += kTileThreads) idx[i] = s_idx[i];
+}
+
+__global__ void __launch_bounds__(kTileThreads) k_tile_sort(HitOrderArgs A, const RunTile *tiles)
+{
+    __shared__ unsigned s_idx[kTile];
+    __shared__ u64 s_key[kTile];
+    tile_stages<true>(A, tiles[blockIdx.x], 0, s_idx, s_key);
+}
+
+// narrow stages (j < kTile) of merge k > kTile
+__global__ void __launch_bounds__(kTileThreads) k_tile_merge(HitOrderArgs A, const RunTile *tiles, unsigned k)
+{
+    __shared__ unsigned s_idx[kTile];
+    __shared__ u64 s_key[kTile];
+    const RunTile e = tiles[blockIdx.x];
+    if (k > e.npad) return;
+    tile_stages<false>(A, e, k, s_idx, s_key);
+}
+
+// one wide stage (j >= kTile) of merge k, all runs at once
+__global__ void __launch_bounds__(kTileThreads) k_run_stage(HitOrderArgs A, const RunTile *tiles, unsigned k, unsigned j)
+{
+    const RunTile e = tiles[blockIdx.x];
+    if (k > e.npad) return;
+    const unsigned flip = (j == (k >> 1)) ? (k - 1) : j;
+    unsigned *idx = A.grouped + e.r0;
+    for (unsigned t = threadIdx.x; t < (unsigned)kTile; t += kTileThreads) {
+        const unsigned i = e.tile * kTile + t, q = i ^ flip;
+        if (q > i && q < e.n) {
+            const unsigned x = idx[i], y = idx[q];
+            if (tuple_less(A.atoms + (A.h0 + y) * A.stride, A.atoms + (A.h0 + x) * A.stride, A.stride)) {
+                idx[i] = y; idx[q] = x;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kTileThreads) k_run_publish(HitOrderArgs A, const RunTile *tiles)
+{
+    const RunTile e = tiles[blockIdx.x];
+    for (unsigned t = threadIdx.x; t < (unsigned)kTile; t += kTileThreads) {
+        const unsigned i = e.tile * kTile + t;
+        if (i < e.n) A.order[e.r0 + i] = A.grouped[e.r0 + i];
+    }
 }
 
 // One warp per output record: lanes copy the 2 + stride ints and 16 doubles of hit

@@ -129,7 +129,6 @@ struct Counters {              // device counters of one chunk attempt
     u64 hits;                  // hits written (absolute, across chunks)
     u64 nan_dropped;
     u64 level[kMaxN + 1];      // level[l] = items with l atoms (l>=1)
-    u64 unsupported;           // pairs skipped because n == 1
 };
 
 // ---- tokens ------------------------------------------------------------------
@@ -405,25 +404,98 @@ __global__ void k_shells(TemplateTable T, double cutoff, double max_dyn)
     }
 }
 
+// ---- K: scan order (reorder == 2) ---------------------------------------------------
+// The engine's own scan order: an expected fan-out model.  A candidate of template atom
+// k lands in the shell around a placed atom with probability ~ shell volume / structure
+// volume, so placing k multiplies the frontier by f(k) = |C_k| * 4.19 * min_j vol(j,k) / V
+// (V = 19 A^3 per atom); atoms sharing a template residue with a placed atom can only
+// match inside that residue (TessTemplate_check), never prune, and go last, smallest set
+// first.  The first atom minimises |C_c| * (1 + best follow-up fan-out).  On cfg 3 this
+// cuts the accepted partial matches by 29 % against the reference's argsort(|C_k|).
+// One CTA = one template x 128 structures, so the n x n volume table is staged once in
+// shared memory and read as warp-uniform broadcasts.  The arithmetic mirrors
+// oracle/jess_oracle.c operation by operation (explicit RN ops): same order, same counters.
+__global__ void __launch_bounds__(128) k_order(int n_mol, TemplateTable T, int n_specs, const CandHead *heads,
+                                               const long long *atom_off, unsigned char *ordbuf)
+{
+    __shared__ double s_vol[kMaxN * kMaxN];
+    __shared__ unsigned char s_same[kMaxN * kMaxN];
+    __shared__ int s_spec[kMaxN];
+    const int t = blockIdx.x;
+    const int ta0 = T.atom_off[t], n = T.atom_off[t + 1] - ta0;
+    const long long d0 = T.dist_off[t];
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+        s_vol[e] = T.vol[d0 + e];
+        s_same[e] = (T.shell[d0 + e].flags & 3) == 3;
+    }
+    for (int k = threadIdx.x; k < n; k += blockDim.x) s_spec[k] = T.spec[ta0 + k];
+    __syncthreads();
+    const int m = blockIdx.y * blockDim.x + threadIdx.x;
+    if (m >= n_mol || n < 1) return;
+    int cnts[kMaxN];
+    bool live = true;
+    for (int k = 0; k < n; k++) {
+        cnts[k] = heads[(long long)m * n_specs + s_spec[k]].cnt;
+        live = live && cnts[k] > 0;
+    }
+    if (!live) return;
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    const double V = __dmul_rn(19.0, (double)(atom_off[m + 1] - atom_off[m]));
+    int first = 0;
+    double first_score = inf;
+    for (int c = 0; c < n; c++) {
+        double mf = inf;
+        for (int k = 0; k < n; k++) {
+            if (k == c || s_same[c * n + k]) continue;
+            const double f = __ddiv_rn(__dmul_rn(__dmul_rn((double)cnts[k], 4.19), s_vol[c * n + k]), V);
+            if (f < mf) mf = f;
+        }
+        if (mf == inf) mf = 1.0;
+        const double sc = __dmul_rn((double)cnts[c], __dadd_rn(1.0, mf));
+        if (sc < first_score) { first_score = sc; first = c; }
+    }
+    unsigned char *ord = ordbuf + ((long long)m * T.n_templates + t) * kMaxN;
+    double minv[kMaxN];
+    unsigned used = 1u << first, same = 0;
+    for (int k = 0; k < n; k++) minv[k] = inf;
+    ord[0] = (unsigned char)first;
+    int last = first;
+    for (int l = 1; l < n; l++) {
+        int best = -1;
+        double best_score = 0.0;
+        for (int k = 0; k < n; k++) {
+            if (used & (1u << k)) continue;
+            const double v = s_vol[last * n + k];
+            if (v < minv[k]) minv[k] = v;
+            if (s_same[last * n + k]) same |= 1u << k;
+            const double f = (same & (1u << k)) ? __dadd_rn(1e3, (double)cnts[k])
+                                                : __ddiv_rn(__dmul_rn(__dmul_rn((double)cnts[k], 4.19), minv[k]), V);
+            if (best < 0 || f < best_score) { best = k; best_score = f; }
+        }
+        ord[l] = (unsigned char)best;
+        used |= 1u << best;
+        last = best;
+    }
+}
+
 // ---- K: pairs --------------------------------------------------------------------
 // Thread per (structure, template).  A pair is live iff every candidate set is
 // non-empty (eff:Scanner.c:145-149).  Scan order:
 //   reorder 0  template order
 //   reorder 1  the reference's argsort(|C_k|, k) (eff:Scanner.c:88-99)
-//   reorder 2  the engine's own: smallest candidate set first, then greedily the atom
-//              with the smallest expected fan-out |C_k| * min_j vol(j, k).  The hit SET
-//              does not depend on the order (all constraints are pairwise and symmetric).
-__global__ void __launch_bounds__(128) k_pairs(int n_mol, TemplateTable T, int n_specs, const CandHead *heads,
-                                               const long long *atom_off, int reorder, PairRec *recs, Counters *ctr)
+//   reorder 2  the engine's own (k_order above), read from ordbuf.
+// The hit SET does not depend on the order (all constraints are pairwise and symmetric).
+__global__ void __launch_bounds__(256) k_pairs(int n_mol, TemplateTable T, int n_specs, const CandHead *heads,
+                                               const long long *atom_off, int reorder, const unsigned char *ordbuf,
+                                               PairRec *recs, Counters *ctr)
 {
     const long long total = (long long)n_mol * T.n_templates;
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     bool live = false;
     int m = 0, t = 0, ta0 = 0, n = 0;
     int cnts[kMaxN];
-    unsigned char ord[kMaxN];
+    alignas(16) unsigned char ord[kMaxN];
     u64 sum = 0;
-    bool single = false;
     if (p < total) {
         m = (int)(p / T.n_templates);
         t = (int)(p % T.n_templates);
@@ -436,7 +508,6 @@ __global__ void __launch_bounds__(128) k_pairs(int n_mol, TemplateTable T, int n
             live = live && (c > 0);
             sum += (u64)c;
         }
-        if (live && n == 1) { single = true; live = false; }    // see DESIGN.md: n==1 not on the GPU path
         if (live) {
             for (int k = 0; k < n; k++) ord[k] = (unsigned char)k;
             if (reorder == 1) {
@@ -448,26 +519,9 @@ __global__ void __launch_bounds__(128) k_pairs(int n_mol, TemplateTable T, int n
                     ord[j + 1] = v;
                 }
             } else if (reorder == 2) {
-                const double *vol = T.vol + T.dist_off[t];
-                const double inf = __longlong_as_double(0x7ff0000000000000ll);
-                double minv[kMaxN];
-                unsigned used = 0;
-                int first = 0;
-                for (int k = 1; k < n; k++) if (cnts[k] < cnts[first]) first = k;
-                for (int k = 0; k < n; k++) minv[k] = inf;
-                int last = first;
-                ord[0] = (unsigned char)first; used |= 1u << first;
-                for (int l = 1; l < n; l++) {
-                    int best = -1; double best_score = 0.0;
-                    for (int k = 0; k < n; k++) {
-                        if (used & (1u << k)) continue;
-                        const double v = fmin(minv[k], vol[last * n + k]);
-                        minv[k] = v;
-                        const double score = __dmul_rn((double)cnts[k], v);
-                        if (best < 0 || score < best_score) { best = k; best_score = score; }
-                    }
-                    ord[l] = (unsigned char)best; used |= 1u << best; last = best;
-                }
+                const uint4 *src = reinterpret_cast<const uint4 *>(ordbuf + p * kMaxN);
+                uint4 *dst = reinterpret_cast<uint4 *>(ord);
+                dst[0] = src[0]; dst[1] = src[1];
             }
         }
     }
@@ -475,14 +529,10 @@ __global__ void __launch_bounds__(128) k_pairs(int n_mol, TemplateTable T, int n
     const int lane = threadIdx.x & 31;
     u64 wsum = live ? sum : 0;
     for (int o = 16; o > 0; o >>= 1) wsum += __shfl_down_sync(0xffffffffu, wsum, o);
-    const unsigned smask = __ballot_sync(0xffffffffu, single);
     u64 base = 0;
-    if (lane == 0) {
-        if (mask) {
-            base = atomicAdd(&ctr->live_pairs, (u64)__popc(mask));
-            atomicAdd(&ctr->cand_atoms, wsum);
-        }
-        if (smask) atomicAdd(&ctr->unsupported, (u64)__popc(smask));
+    if (lane == 0 && mask) {
+        base = atomicAdd(&ctr->live_pairs, (u64)__popc(mask));
+        atomicAdd(&ctr->cand_atoms, wsum);
     }
     base = __shfl_sync(0xffffffffu, base, 0);
     if (live) {
@@ -857,6 +907,13 @@ __global__ void __launch_bounds__(128) k_superpose(const int *tuples, const u64 
         rec = recs + tp[0];
         n = rec->n;
         for (int lv = 0; lv < n; lv++) inv[rec->order[lv]] = (unsigned char)lv;
+        if (n == 1) {
+            // Superposition_rmsd returns 0 for a single pair and never computes the rotation or
+            // the centroids, which stay zeroed (vendor/jess/src/Super.c:125-130,152)
+            for (int j = 0; j < 9; j++) R[j] = 0.0;
+            for (int j = 0; j < 3; j++) ca[j] = cb[j] = 0.0;
+            hit = 0.0 <= rmsd_threshold;
+        } else {
         const long long abase = rec->abase;
         const double *tpos = T.pos + 3ll * rec->ta0;
         for (int j = 0; j < 3; j++) ca[j] = cb[j] = 0.0;
@@ -932,6 +989,7 @@ __global__ void __launch_bounds__(128) k_superpose(const int *tuples, const u64 
                 }
             hit = !nan;
         }
+        }   // n > 1
     }
     const unsigned hm = __ballot_sync(0xffffffffu, hit);
     const unsigned nm = __ballot_sync(0xffffffffu, nan);

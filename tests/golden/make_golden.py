@@ -148,6 +148,23 @@ def main():
     add("amy_doctest_best", ["1.3.3.tpl", "4.1.2.tpl"], "1AMY.pdb", (2.0, 2.0, 2.0), {"best_match": True})
     add("lnb_t01_x3_best", ["template_01.qry"] * 3, "pdb1lnb.ent", (1.0, 2.0, 2.0), {"best_match": True})
     add("amy_examples_split", ["template_01.qry", "template_02.qry"], "1AMY.pdb", (2.0, 5.0, 5.0), {})
+    # single-atom templates (the reference never reports the first entry of ITS candidate list):
+    # exact name, alternate residue names listed BEFORE/AFTER the primary one, a name-only mode
+    singles = {
+        "single_his.qry": "ATOM      0  ND1 HIS E 142       4.191  -2.584   4.209\n",
+        "single_glu_asp.qry": "ATOM      3  OE1 GLU E 143       0.491  -4.480  -0.456 D\n",
+        "single_any_ca.qry": "ATOM    100  CA  GLY E   1       0.000   0.000   0.000\n",
+    }
+    for fname, text in singles.items():
+        with open(os.path.join(DATA, fname), "w") as f:
+            f.write(text)
+    for fname in singles:
+        for mfile in ("pdb1lnb.ent", "5ayx.EF.pdb"):
+            add(f"{fname[:-4]}_{mfile.split('.')[0]}", [fname], mfile, (2.0, 2.0, 2.0), {})
+            cases[-1]["single_atom"] = True
+    add("single_mixed_lnb", ["single_his.qry", "template_01.qry", "single_glu_asp.qry"], "pdb1lnb.ent",
+        (2.0, 5.0, 5.0), {})
+    cases[-1]["single_atom"] = True
 
     # cfg 2: the three example templates against all 132 structures
     cfg2 = []

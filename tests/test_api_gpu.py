@@ -9,7 +9,7 @@ import pickle
 import numpy as np
 import pytest
 
-from _util import DATA, load_molecule, load_template
+from _util import DATA, golden_cases, load_molecule, load_template
 from pyjess_b200 import Jess, Molecule, Template
 
 pytestmark = pytest.mark.gpu
@@ -200,10 +200,25 @@ def test_max_candidates_is_refused_loudly(lnb):
         next(Jess([template]).query(lnb, 2, 5, 5, max_candidates=2))
 
 
-def test_single_atom_template_is_refused_loudly(lnb):
-    from pyjess_b200 import TemplateAtom
-    from pyjess_b200._capi import EngineError
-    atom = TemplateAtom(chain_id="E", residue_number=142, x=0.0, y=0.0, z=0.0, residue_names=["HIS"],
-                        atom_names=["ND1"], distance_weight=0.0, match_mode=0)
-    with pytest.raises(EngineError):
-        list(Jess([Template([atom], id="one")]).query(lnb, 2, 5, 5))
+SINGLE = sorted(c for c in golden_cases() if golden_cases()[c].get("single_atom"))
+
+
+@pytest.mark.parametrize("name", SINGLE)
+def test_single_atom_templates_match_reference(name):
+    """n == 1: the reference never reports the first entry of its candidate
+    list and returns rmsd 0 with an all-zero rotation; golden hits come from the reference."""
+    case = golden_cases()[name]
+    templates = [load_template(t) for t in case["templates"]]
+    mol = load_molecule(case["molecule"])
+    hits = list(Jess(templates).query(mol, *case["params"], **case["kwargs"]))
+    got = sorted((templates.index(h.template()), tuple(int(np.nonzero(mol._atoms["serial"] == a.serial)[0][0])
+                                                       for a in h.atoms(False))) for h in hits)
+    assert got == sorted((h["template"], tuple(h["atoms"])) for h in case["hits"])
+    gold = {(h["template"], tuple(h["atoms"])): h for h in case["hits"]}
+    for h in hits:
+        g = gold[(templates.index(h.template()), tuple(int(np.nonzero(mol._atoms["serial"] == a.serial)[0][0])
+                                                       for a in h.atoms(False)))]
+        assert h.rmsd == pytest.approx(g["rmsd"], abs=1e-6)
+        assert np.abs(np.asarray(h.transformation) - np.asarray(g["transformation"])).max() <= 1e-6
+        assert h.determinant == pytest.approx(g["determinant"], abs=1e-6)
+        assert h.log_evalue == pytest.approx(g["log_evalue"], abs=1e-9)

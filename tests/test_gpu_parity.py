@@ -10,6 +10,9 @@ from pyjess_b200._tables import MoleculeBatch, TemplateTable
 pytestmark = pytest.mark.gpu
 
 CASES = sorted(golden_cases())
+#: single-atom cases: the C ABI reports every candidate, the reference's skipped first
+#: candidate is removed by the host layer (tests/test_api_gpu.py pins that to the golden)
+ABI_CASES = [c for c in CASES if not golden_cases()[c].get("single_atom")]
 COUNTERS = ("pairs", "live_pairs", "candidate_atoms", "frontier_items", "frontier_ints", "candidate_tests",
             "tuples", "nan_dropped")
 
@@ -24,7 +27,7 @@ def run_engine(engine, templates, mols, params):
         dev.close()
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", ABI_CASES)
 def test_engine_matches_reference_golden(engine, name):
     case = golden_cases()[name]
     templates, mols, params = case_inputs(case)
@@ -54,7 +57,7 @@ def test_engine_matches_oracle(engine, oracle_lib, name):
 SYNTH = [("cfg3", 0.04, {}, 0), ("cfg3", 0.04, {}, 1), ("cfg3", 0.04, {}, 2),
          ("cfg3dense", 0.03, {}, 1), ("cfg3dense", 0.03, {}, 2), ("cfg4shard", 0.004, {}, 1),
          ("cfg5", 0.012, {"ignore_chain": None}, 1), ("cfg5", 0.012, {"ignore_chain": "residues"}, 1),
-         ("cfg5", 0.012, {"ignore_chain": "atoms"}, 1)]
+         ("cfg5", 0.006, {"ignore_chain": "atoms"}, 1)]
 
 
 @pytest.mark.parametrize("name,scale,kw,reorder", SYNTH)

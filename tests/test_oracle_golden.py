@@ -8,7 +8,8 @@ import pytest
 from _util import assert_matches_golden, case_inputs, compare_tables, golden_cases
 from pyjess_b200._tables import MoleculeBatch, TemplateTable
 
-CASES = sorted(golden_cases())
+CASES = sorted(c for c in golden_cases() if not golden_cases()[c].get("single_atom"))
+SINGLE = sorted(c for c in golden_cases() if golden_cases()[c].get("single_atom"))
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -35,3 +36,21 @@ def test_reference_library_matches_golden(oracle_lib, name):
         assert compare_tables(ours, ref, params.rmsd_threshold) == []
         # same arithmetic, same libm: the restatement is bit-identical here
         assert np.array_equal(ours.rmsd, ref.rmsd)
+
+
+@pytest.mark.parametrize("name", SINGLE)
+def test_single_atom_templates_report_every_candidate_but_one(oracle_lib, name):
+    """n == 1: oracle (and engine ABI) list ALL candidates; the reference lists all but the
+    first of its own candidate-list order -- per (molecule, single-atom template) exactly one
+    hit fewer, and a subset."""
+    case = golden_cases()[name]
+    templates, mols, params = case_inputs(case)
+    table, _ = oracle_lib.query(TemplateTable(templates), MoleculeBatch(mols), params, threads=2)
+    gold = {(h.get("molecule", 0), h["template"], tuple(h["atoms"])) for h in case["hits"]}
+    ours = set(table.keys())
+    assert gold <= ours
+    extra = ours - gold
+    singles = [i for i, t in enumerate(templates) if len(t) == 1]
+    assert all(k[1] in singles for k in extra)
+    pairs = {(k[0], k[1]) for k in ours if k[1] in singles}
+    assert len(extra) == len(pairs)
