@@ -172,15 +172,16 @@ def main():
     from pyjess_b200 import _capi, synth
     from pyjess_b200._tables import MoleculeBatch, TemplateTable, query_params
 
+    # ---- inputs (synthetic, seeded; structures differ per rank, templates replicated);
+    # generated before CUDA is initialised: the cfg 4 generator forks worker processes
+    tpl, mols, params, kw = synth.workload(args.workload, scale=args.scale, rank=rank)
+    qp = query_params(*params, **kw)
+
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    # ---- inputs (synthetic, seeded; structures differ per rank, templates replicated)
-    tpl, mols, params, kw = synth.workload(args.workload, scale=args.scale, rank=rank)
-    qp = query_params(*params, **kw)
     stream = torch.cuda.Stream()           # the engine's stream; torch events are recorded on it
     torch.cuda.set_stream(stream)
     ctx = _capi.Context(local, stream=stream.cuda_stream)

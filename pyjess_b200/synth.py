@@ -92,17 +92,26 @@ def _random_rotations(rng, n):
         np.stack([2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], -1)], 1)
 
 
-def _ca_walks(rng, lengths: np.ndarray, trials: int = 10) -> np.ndarray:
-    """(P, Lmax, 3) confined self-avoiding walks, vectorised over the P chains."""
+def _ca_walks(rng, lengths: np.ndarray, trials: int = 10, fast: bool = False) -> np.ndarray:
+    """(P, Lmax, 3) confined self-avoiding walks, vectorised over the P chains.
+    `fast` evaluates the self-avoidance distances through a matmul (different rounding,
+    hence its own deterministic stream of structures: used for the ranged-length cfg 4)."""
     P, Lmax = len(lengths), int(lengths.max())
     radius = (3.0 * lengths * 150.0 / (4.0 * np.pi)) ** (1.0 / 3.0)
     ca = np.zeros((P, Lmax, 3), dtype=np.float32)
+    sq = np.zeros((P, Lmax), dtype=np.float32)
     for i in range(1, Lmax):
         d = rng.normal(size=(P, trials, 3)).astype(np.float32)
         d /= np.linalg.norm(d, axis=2, keepdims=True)
         cand = ca[:, i - 1, None, :] + np.float32(3.8) * d                      # (P, trials, 3)
         inside = np.linalg.norm(cand, axis=2) <= radius[:, None]
-        if i >= 2:
+        if i >= 2 and fast:
+            # |c - p|^2 = |c|^2 + |p|^2 - 2 c.p through one batched matmul (cfg 4's long chains)
+            prev = ca[:, : i - 1, :]
+            d2 = (np.einsum("ptc,ptc->pt", cand, cand)[:, :, None] + sq[:, None, : i - 1]
+                  - np.float32(2.0) * np.matmul(cand, prev.transpose(0, 2, 1)))
+            mind = np.sqrt(np.maximum(np.min(d2, axis=2), np.float32(0.0)))
+        elif i >= 2:
             prev = ca[:, : i - 1, :]                                            # non-adjacent earlier C-alphas
             diff = cand[:, :, None, :] - prev[:, None, :, :]
             mind = np.sqrt(np.min(np.einsum("ptkc,ptkc->ptk", diff, diff), axis=2))
@@ -112,6 +121,7 @@ def _ca_walks(rng, lengths: np.ndarray, trials: int = 10) -> np.ndarray:
         score = score + np.where(inside, 0.0, -np.linalg.norm(cand, axis=2) * 1e-3)
         pick = np.argmax(score, axis=1)                                           # first valid, else best of trials
         ca[:, i, :] = cand[np.arange(P), pick]
+        sq[:, i] = np.einsum("pc,pc->p", ca[:, i, :], ca[:, i, :])
     return ca
 
 
@@ -149,11 +159,27 @@ def _assemble(rng, ca: np.ndarray, seq: np.ndarray, chain: str = "A", resseq0: i
     return arr
 
 
+def _protein_group(args):
+    """Worker of the ranged-length generator: one group of chains from its own RNG stream."""
+    seed, first, count, g0, lens, ids = args
+    rng = np.random.default_rng([seed, first, count, g0])
+    ca = _ca_walks(rng, lens, fast=True)
+    out = []
+    for j in range(len(lens)):
+        L = int(lens[j])
+        seq = rng.choice(20, size=L, p=AA_FREQ)
+        out.append(_assemble(rng, ca[j, :L], seq))
+    return ids, out
+
+
 def proteins(count: int, length=300, seed: int = 1000, first: int = 0) -> List[Molecule]:
     """`count` single-chain proteins; `length` is an int or a (lo, hi) range
-    (cfg 3: 300; cfg 4: (300, 1500))."""
+    (cfg 3: 300; cfg 4: (300, 1500)).  Ranged lengths are generated group by group from
+    independent RNG streams (deterministic whatever the worker count), on a process pool
+    when the set is large (cfg 4: 6,250 structures per GPU)."""
     rng = np.random.default_rng([seed, first, count])
-    if isinstance(length, (tuple, list)):
+    ranged = isinstance(length, (tuple, list))
+    if ranged:
         lengths = rng.integers(length[0], length[1] + 1, size=count)
     else:
         lengths = np.full(count, int(length))
@@ -161,6 +187,20 @@ def proteins(count: int, length=300, seed: int = 1000, first: int = 0) -> List[M
     order = np.argsort(lengths, kind="stable")
     # walk chains of similar length together to bound the (P, trials, L) temporaries
     group = 64 if lengths.max() > 600 else 256
+    if ranged:
+        jobs = [(seed, first, count, g0, lengths[order[g0:g0 + group]], order[g0:g0 + group])
+                for g0 in range(0, count, group)]
+        workers = min(len(jobs), len(os.sched_getaffinity(0)))
+        if count >= 512 and workers > 1:
+            import multiprocessing as mp
+            with mp.get_context("fork").Pool(workers) as pool:
+                results = pool.map(_protein_group, jobs, chunksize=1)
+        else:
+            results = map(_protein_group, jobs)
+        for ids, arrs in results:
+            for i, arr in zip(ids, arrs):
+                out[i] = Molecule._from_records(arr, id=f"S{(first + i) % 1000:03d}")
+        return out
     for g0 in range(0, count, group):
         ids = order[g0:g0 + group]
         ca = _ca_walks(rng, lengths[ids])
