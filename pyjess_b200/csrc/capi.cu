@@ -18,6 +18,7 @@
 
 #include "../../include/jess_b200.h"
 #include "kernels.cuh"
+#include "expand_lv.cuh"
 #include "hits.cuh"
 
 using namespace jb;
@@ -110,6 +111,7 @@ struct jb_context {
     size_t ws_limit = 0;          // bytes the frontier buffers may use in total
     int group = 2;                // lanes per partial match (JB_GROUP)
     int debug = 0;                // JB_DEBUG: per-level counts and times on stderr
+    int legacy = 0;               // JB_LEGACY: run-time-level k_expand at every level (A/B comparisons)
     cudaEvent_t lev[kMaxN + 1] = {};
     // workspace (grow only)
     DevBuf crec, chead, recs, ordbuf, fr[2], tuples, ctr;
@@ -195,6 +197,7 @@ extern "C" int jb_context_create(int device, void *stream, int64_t workspace_byt
         if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) c->group = v;
     }
     if (const char *g = getenv("JB_DEBUG")) c->debug = atoi(g);
+    if (const char *g = getenv("JB_LEGACY")) c->legacy = atoi(g);
     if (c->debug) for (int i = 0; i <= kMaxN; i++) CU(cudaEventCreate(&c->lev[i]));
     CU(cudaMallocHost(&c->host_ctr, sizeof(Counters)));
     CU(cudaMallocHost(&c->host_work, sizeof(RunWork)));
@@ -455,6 +458,35 @@ template <int G, bool STATS> static cudaError_t launch_expand(int grid, size_t s
     return cudaGetLastError();
 }
 
+// level-specialised kernel (expand_lv.cuh): levels 1..kMaxLv, G lanes per partial match
+template <int L, int G> static cudaError_t launch_expand_lv(int sm_count, cudaStream_t st, const ExpandArgs &a, int stats)
+{
+    constexpr size_t smem = expand_lv_smem<L, G>();
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_expand_lv<L, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / smem));
+    k_expand_lv<L, G><<<sm_count * per_sm, kExpandThreads, smem, st>>>(a, stats);
+    return cudaGetLastError();
+}
+
+static cudaError_t dispatch_expand_lv(int level, int g, int sm_count, cudaStream_t st, const ExpandArgs &a, int stats)
+{
+    constexpr size_t budget = 200 * 1024;   // keep at least two CTAs per SM resident
+#define JB_LV_CASE(LL)                                                                                             \
+    case LL:                                                                                                       \
+        if (g <= 1 && 2 * expand_lv_smem<LL, 1>() <= budget) return launch_expand_lv<LL, 1>(sm_count, st, a, stats); \
+        if (g <= 2 && 2 * expand_lv_smem<LL, 2>() <= budget) return launch_expand_lv<LL, 2>(sm_count, st, a, stats); \
+        return launch_expand_lv<LL, 4>(sm_count, st, a, stats);
+    switch (level) {
+        JB_LV_CASE(1) JB_LV_CASE(2) JB_LV_CASE(3) JB_LV_CASE(4)
+        JB_LV_CASE(5) JB_LV_CASE(6) JB_LV_CASE(7) JB_LV_CASE(8)
+    default: return cudaErrorInvalidValue;
+    }
+#undef JB_LV_CASE
+}
+
 struct Range { int m0, m1; };
 
 static int grow_hits(jb_context *c, long long need, int stride)
@@ -600,6 +632,10 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
             // lanes per partial match: the configured G, widened at deep levels so that at
             // least two CTAs per SM fit their staging areas in shared memory
             int g = c->group;
+            if (l >= 1 && l <= kMaxLv && !c->legacy) {
+                CU(dispatch_expand_lv(l, g, c->sm_count, st, A, c->debug != 0));
+                continue;
+            }
             while (g < 16 && 2 * expand_smem(g, l) > 200 * 1024) g <<= 1;
             const size_t smem = expand_smem(g, l);
             const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(smem, 1)));

@@ -1,0 +1,324 @@
+// expand_lv.cuh -- level-specialised frontier expansion for the hot levels.
+//
+// k_expand (kernels.cuh) takes the level as a run-time argument: every shared-memory
+// offset, item stride and inner-loop bound is re-derived in the hot loops (16 % of
+// its warp instructions on BASELINE config 3, profiles/r1n), and its scan loop runs
+// until the LONGEST of the 32/G candidate ranges of a batch is exhausted (14.1
+// iterations per batch where 6.2 would do).  k_expand_lv<L, G> is the same
+// algorithm -- same staging, same FP32 join box, same exact FP64 predicate, same
+// emission -- specialised on the level L (atoms already placed) with
+//
+//   * all strides/offsets compile-time, loops over the placed atoms unrolled;
+//   * BOTH x bounds of the join box located by binary search in the x-sorted
+//     candidate list (the k-d tree walk of eff:KdTree.c:238-296 becomes two
+//     searches), so that every partial match owns an exact record range;
+//   * a LOAD-BALANCED scan: the ranges of a batch are cut into chunks of kChunk
+//     records, the chunks are numbered by a warp prefix sum and dealt to the 32
+//     lanes whatever partial match they belong to (the owner is found by a
+//     branch-free binary search over the chunk offsets in shared memory).
+//
+// Reference semantics are untouched: the decision is still _Annulus_po in FP64
+// with explicit RN operations (eff:Annulus.h:54-68) plus TessTemplate_check
+// (eff:TessTemplate.c:78-119); FP32 only ever rejects records that are provably
+// outside the outward-rounded join box.
+#pragma once
+#include "kernels.cuh"
+
+namespace jb {
+
+constexpr int kMaxLv = 8;        // levels 1..kMaxLv have a specialisation; deeper levels use k_expand
+constexpr int kChunk = 4;        // records per scan chunk (64 bytes: two sectors)
+constexpr int kQueueLv = 160;    // survivor queue: < 32 carried + kChunk x 32 new
+
+template <int L, int G> struct alignas(16) LvWarp {   // per-warp shared memory
+    static constexpr int IPW = 32 / G;                // partial matches per batch
+    ChainRec chain[IPW * L];                          // placed atoms + shells towards the new atom
+    float4 blo[IPW], bhi[IPW];                        // join box (outward rounded)
+    long long cbase[IPW];                             // first record of the x range
+    long long abase[IPW];                             // first atom of the structure
+    int2 meta[IPW];                                   // pair index, "this level completes the template"
+    int clen[IPW];                                    // records in the x range
+    int cstart[IPW];                                  // first chunk of the partial match (exclusive scan)
+    int2 queue[kQueueLv];                             // box survivors: (atom, partial match)
+    int chain_atom[IPW * L];
+    int stage[kStageItems * (L + 2)];                 // accepted extensions awaiting the flush
+};
+
+template <int L, int G> constexpr size_t expand_lv_smem() { return sizeof(LvWarp<L, G>) * kExpandWarps; }
+
+template <int L, int G>
+__global__ void __launch_bounds__(kExpandThreads, 4) k_expand_lv(const ExpandArgs A, const int stats)
+{
+    constexpr int IPW = 32 / G;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int in_stride = L + 1, out_stride = L + 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    LvWarp<L, G> &W = reinterpret_cast<LvWarp<L, G> *>(smem_raw)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = lane / G, gl = lane % G;
+    const unsigned lt = (1u << lane) - 1;
+    int fill = 0, qfill = 0;
+
+    u64 n_in = *A.in_count;
+    if ((long long)n_in > A.in_cap) n_in = (u64)A.in_cap;
+    const long long total_warps = (long long)gridDim.x * kExpandWarps;
+    u64 n_cand = 0;                                   // per-lane partial sums
+    unsigned n_scan = 0, n_box = 0;                   // lane 0 only (diagnostics)
+    const float INF = __int_as_float(0x7f800000);
+
+    // exact predicate + emission for queue entries [q0, q0 + nq)
+    auto drain = [&](int q0, int nq) {
+        __syncwarp();
+        bool ok = lane < nq;
+        int a = 0, g = 0;
+        if (ok) {
+            const int2 e = W.queue[q0 + lane];
+            a = e.x; g = e.y;
+        }
+        const int2 mt = W.meta[g];
+        if (ok) {
+            const AtomRec p = A.atoms[W.abase[g] + a];
+            const ChainRec *ch = W.chain + g * L;
+            // _Annulus_po (eff:Annulus.h:54-68): ((dx^2 + dy^2) + dz^2), centre - point
+#pragma unroll
+            for (int j = 0; j < L; j++) {
+                const double t0 = __dsub_rn(ch[j].x, p.x), t1 = __dsub_rn(ch[j].y, p.y), t2 = __dsub_rn(ch[j].z, p.z);
+                const double s = __dadd_rn(__dadd_rn(__dmul_rn(t0, t0), __dmul_rn(t1, t1)), __dmul_rn(t2, t2));
+                if (s < ch[j].lo2 || s > ch[j].hi2) { ok = false; break; }
+            }
+            if (ok) {
+#pragma unroll
+                for (int j = 0; j < L; j++) {
+                    const int f = ch[j].flag;
+                    if (!pair_consistent(A.ignore_chain, (f & 0xff) == p.chain, (f & 0x100) != 0, ch[j].res == p.resseq,
+                                         (f & 0x200) != 0)) { ok = false; break; }
+                }
+            }
+        }
+        const unsigned okm = __ballot_sync(FULL, ok);
+        if (okm == 0) return;
+        const unsigned cm = __ballot_sync(FULL, ok && mt.y);
+        const unsigned nm = okm & ~cm;
+        if (cm) {   // finished tuples go straight to the tuple list (one atomic per warp)
+            u64 tb = 0;
+            if (lane == 0) {
+                tb = atomicAdd(&A.ctr->tuples, (u64)__popc(cm));
+                atomicAdd(&A.ctr->tuple_ints, (u64)__popc(cm) * (u64)(L + 1));
+            }
+            tb = __shfl_sync(FULL, tb, 0);
+            if (ok && mt.y) {
+                const long long slot = (long long)tb + __popc(cm & lt);
+                if (slot < A.tuple_cap) {
+                    int *dst = A.tuples + slot * A.tuple_stride;
+                    dst[0] = mt.x;
+#pragma unroll
+                    for (int j = 0; j < L; j++) dst[1 + j] = W.chain_atom[g * L + j];
+                    dst[1 + L] = a;
+                }
+            }
+        }
+        if (nm) {
+            if (ok && !mt.y) {
+                int *dst = W.stage + (fill + __popc(nm & lt)) * out_stride;
+                dst[0] = mt.x;
+#pragma unroll
+                for (int j = 0; j < L; j++) dst[1 + j] = W.chain_atom[g * L + j];
+                dst[1 + L] = a;
+            }
+            fill += __popc(nm);
+            if (fill + 32 > kStageItems) {   // flush
+                __syncwarp();
+                u64 ob = 0;
+                if (lane == 0) ob = atomicAdd(A.out_count, (u64)fill);
+                ob = __shfl_sync(FULL, ob, 0);
+                if ((long long)ob + fill <= A.out_cap) {
+                    int *dst = A.out + (long long)ob * out_stride;
+                    for (int i = lane; i < fill * out_stride; i += 32) dst[i] = W.stage[i];
+                }
+                fill = 0;
+                __syncwarp();
+            }
+        }
+    };
+
+    for (long long base_item = ((long long)blockIdx.x * kExpandWarps + warp) * IPW; base_item < (long long)n_in;
+         base_item += total_warps * IPW) {
+        const long long item = base_item + grp;
+        const bool valid = item < (long long)n_in;
+        int cnt = 0;
+        long long coff = 0;
+        float bx0 = -INF, by0 = -INF, bz0 = -INF, bx1 = INF, by1 = INF, bz1 = INF;
+        if (valid) {
+            const int *it = A.in + item * in_stride;
+            const int lp = it[0];
+            const PairRec *rec = A.recs + lp;
+            const int4 h0 = *reinterpret_cast<const int4 *>(rec);            // m, t, ta0, n
+            const longlong2 h1 = *reinterpret_cast<const longlong2 *>(&rec->abase);
+            const int n = h0.w;
+            const int k = rec->order[L];
+            const CandHead hd = A.head[(long long)h0.x * A.n_specs + rec->spec[L]];
+            cnt = hd.cnt;
+            coff = hd.off;
+            if (gl == 0) {
+                W.meta[grp] = make_int2(lp, (L + 1 == n) ? 1 : 0);
+                W.abase[grp] = h1.x;
+            }
+            const MolExt me = A.ext[h0.x];
+            const float err = __double2float_ru(me.ext * 2.4e-7 + 1e-30);    // > ext * 2^-22: record rounding
+#pragma unroll
+            for (int jj = 0; jj < (L + G - 1) / G; jj++) {
+                const int j = jj * G + gl;
+                if (j < L) {
+                    const int a = it[1 + j];
+                    const AtomRec ar = A.atoms[h1.x + a];
+                    const ShellRec sh = A.shell[h1.y + (long long)rec->order[j] * n + k];
+                    ChainRec c;
+                    c.x = ar.x; c.y = ar.y; c.z = ar.z; c.lo2 = sh.lo2; c.hi2 = sh.hi2;
+                    c.res = ar.resseq; c.flag = ar.chain | (sh.flags << 8);
+                    W.chain[grp * L + j] = c;
+                    W.chain_atom[grp * L + j] = a;
+                    const double dx = __dsub_rn(ar.x, me.ox), dy = __dsub_rn(ar.y, me.oy), dz = __dsub_rn(ar.z, me.oz);
+                    const float rb = sh.rb;
+                    bx0 = fmaxf(bx0, __fsub_rd(__fsub_rd(__double2float_rd(dx), rb), err));
+                    by0 = fmaxf(by0, __fsub_rd(__fsub_rd(__double2float_rd(dy), rb), err));
+                    bz0 = fmaxf(bz0, __fsub_rd(__fsub_rd(__double2float_rd(dz), rb), err));
+                    bx1 = fminf(bx1, __fadd_ru(__fadd_ru(__double2float_ru(dx), rb), err));
+                    by1 = fminf(by1, __fadd_ru(__fadd_ru(__double2float_ru(dy), rb), err));
+                    bz1 = fminf(bz1, __fadd_ru(__fadd_ru(__double2float_ru(dz), rb), err));
+                }
+            }
+            if (gl == 0) n_cand += (u64)cnt;     // algorithm-independent work counter
+        }
+#pragma unroll
+        for (int o = G >> 1; o > 0; o >>= 1) {   // join box = intersection over the placed atoms
+            bx0 = fmaxf(bx0, __shfl_xor_sync(FULL, bx0, o)); bx1 = fminf(bx1, __shfl_xor_sync(FULL, bx1, o));
+            by0 = fmaxf(by0, __shfl_xor_sync(FULL, by0, o)); by1 = fminf(by1, __shfl_xor_sync(FULL, by1, o));
+            bz0 = fmaxf(bz0, __shfl_xor_sync(FULL, bz0, o)); bz1 = fminf(bz1, __shfl_xor_sync(FULL, bz1, o));
+        }
+        // an empty join box kills the partial match without touching its candidates
+        const bool boxed = valid && bx0 <= bx1 && by0 <= by1 && bz0 <= bz1;
+        // ---- x range of the box in the x-sorted list: two binary searches, stopped at a span
+        //      of two records (the scan re-tests x, so a slightly wide range is harmless)
+        int lo = 0, hi = cnt;
+        const bool narrow = boxed && cnt > 2 * kChunk;
+        if (G == 1) {
+            int l0 = 0, l1 = cnt, u0 = 0, u1 = cnt;
+            while (__any_sync(FULL, narrow && (l1 - l0 > 2 || u1 - u0 > 2))) {
+                const bool al = narrow && l1 - l0 > 2, au = narrow && u1 - u0 > 2;
+                const int ml = (l0 + l1) >> 1, mu = (u0 + u1) >> 1;
+                float xl = 0.f, xu = 0.f;
+                if (al) xl = __ldg(&A.cand[coff + ml].x);
+                if (au) xu = __ldg(&A.cand[coff + mu].x);
+                if (al) { if (xl < bx0) l0 = ml + 1; else l1 = ml; }
+                if (au) { if (xu <= bx1) u0 = mu + 1; else u1 = mu; }
+            }
+            if (narrow) { lo = l0; hi = u1; }
+        } else {
+            // lane 0 of the group: first record with x >= bx0; lane 1: first record with x > bx1
+            int s0 = 0, s1 = cnt;
+            const bool searcher = narrow && gl < 2;
+            const float key = gl == 0 ? bx0 : bx1;
+            while (__any_sync(FULL, searcher && s1 - s0 > 2)) {
+                const bool act = searcher && s1 - s0 > 2;
+                const int mid = (s0 + s1) >> 1;
+                float x = 0.f;
+                if (act) x = __ldg(&A.cand[coff + mid].x);
+                const bool below = gl == 0 ? (x < key) : (x <= key);
+                if (act) { if (below) s0 = mid + 1; else s1 = mid; }
+            }
+            const int l0 = __shfl_sync(FULL, s0, lane - gl);
+            const int u1 = __shfl_sync(FULL, s1, lane - gl + 1);
+            if (narrow) { lo = l0; hi = u1; }
+        }
+        // ---- chunk numbering: exclusive prefix sum of the chunk counts over the batch ----------
+        const int len = boxed ? max(hi - lo, 0) : 0;
+        const int nch = (len + kChunk - 1) / kChunk;
+        const int mine = gl == 0 ? nch : 0;
+        int inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += t;
+        }
+        const int total = __shfl_sync(FULL, inc, 31);
+        if (gl == 0) {
+            W.cstart[grp] = inc - mine;
+            W.clen[grp] = len;
+            W.cbase[grp] = coff + lo;
+            W.blo[grp] = make_float4(bx0, by0, bz0, 0.f);
+            W.bhi[grp] = make_float4(bx1, by1, bz1, 0.f);
+        }
+        __syncwarp();
+        // ---- load-balanced scan: lane <- chunk, whatever partial match owns it ------------------
+        for (int cb = 0; cb < total; cb += 32) {
+            const int ch = cb + lane;
+            const bool act = ch < total;
+            int g = 0;
+#pragma unroll
+            for (int s = IPW / 2; s > 0; s >>= 1)
+                if (W.cstart[g + s] <= ch) g += s;
+            const int k0 = (ch - W.cstart[g]) * kChunk;
+            const int rem = act ? W.clen[g] - k0 : 0;          // records left from the chunk start
+            const float4 *src = A.cand + W.cbase[g] + k0;
+            float4 r[kChunk];
+#pragma unroll
+            for (int i = 0; i < kChunk; i++) {
+                r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < rem) r[i] = __ldg(src + i);
+            }
+            const float4 b0 = W.blo[g], b1 = W.bhi[g];
+            bool ok[kChunk];
+            unsigned m[kChunk], many = 0;
+#pragma unroll
+            for (int i = 0; i < kChunk; i++) {
+                ok[i] = i < rem && r[i].x >= b0.x && r[i].x <= b1.x && r[i].y >= b0.y && r[i].y <= b1.y &&
+                        r[i].z >= b0.z && r[i].z <= b1.z;
+                m[i] = __ballot_sync(FULL, ok[i]);
+                many |= m[i];
+            }
+            if (stats) {
+                const int tested = min(max(rem, 0), kChunk);
+                int tsum = tested;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) tsum += __shfl_down_sync(FULL, tsum, o);
+                if (lane == 0) {
+                    n_scan += (unsigned)tsum;
+#pragma unroll
+                    for (int i = 0; i < kChunk; i++) n_box += __popc(m[i]);
+                }
+            }
+            if (many) {
+                int pos = qfill;
+#pragma unroll
+                for (int i = 0; i < kChunk; i++) {
+                    if (ok[i]) W.queue[pos + __popc(m[i] & lt)] = make_int2(__float_as_int(r[i].w), g);
+                    pos += __popc(m[i]);
+                }
+                qfill = pos;
+                while (qfill >= 32) { qfill -= 32; drain(qfill, 32); }
+            }
+        }
+        if (qfill > 0) { drain(0, qfill); qfill = 0; }
+        __syncwarp();   // the next batch overwrites the per-warp tables
+        if (stats && lane == 0 && (n_scan | n_box)) {   // unsigned partials: publish per batch
+            atomicAdd(&A.ctr->scan_tests, (u64)n_scan);
+            atomicAdd(&A.ctr->box_pass, (u64)n_box);
+            n_scan = n_box = 0;
+        }
+    }
+    __syncwarp();
+    if (fill > 0) {
+        u64 ob = 0;
+        if (lane == 0) ob = atomicAdd(A.out_count, (u64)fill);
+        ob = __shfl_sync(FULL, ob, 0);
+        if ((long long)ob + fill <= A.out_cap) {
+            int *dst = A.out + (long long)ob * out_stride;
+            for (int i = lane; i < fill * out_stride; i += 32) dst[i] = W.stage[i];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n_cand += __shfl_down_sync(FULL, n_cand, o);
+    if (lane == 0 && n_cand) atomicAdd(&A.ctr->cand_tests, n_cand);
+}
+
+}  // namespace jb

@@ -55,7 +55,7 @@ def test_engine_matches_oracle(engine, oracle_lib, name):
 
 # ---- synthetic BASELINE configs 3-5 at oracle-friendly sizes --------------------------
 SYNTH = [("cfg3", 0.04, {}, 0), ("cfg3", 0.04, {}, 1), ("cfg3", 0.04, {}, 2),
-         ("cfg3dense", 0.03, {}, 1), ("cfg3dense", 0.03, {}, 2), ("cfg4shard", 0.004, {}, 1),
+         ("cfg3dense", 0.03, {}, 1), ("cfg3dense", 0.03, {}, 2), ("cfg4shard", 0.012, {}, 1), ("cfg4shard", 0.012, {}, 2),
          ("cfg5", 0.012, {"ignore_chain": None}, 1), ("cfg5", 0.012, {"ignore_chain": "residues"}, 1),
          ("cfg5", 0.006, {"ignore_chain": "atoms"}, 1)]
 
