@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define JB_ABI_VERSION 1
+#define JB_ABI_VERSION 2
 /* hard limit of the GPU path; larger templates are rejected loudly */
 #define JB_MAX_TEMPLATE_ATOMS 32
 
@@ -89,10 +89,29 @@ typedef struct jb_molecule_batch {
     const uint32_t *residue_name;    /* [NA] Atom.resName[0..3]               */
     const int32_t *residue_number;   /* [NA] Atom.resSeq                      */
     const uint8_t *chain_id2;        /* [NA] Atom.chainID2                    */
+    const int32_t *serial;           /* [NA] Atom.serial (orders the residue index,
+                                      * eff:ResIndex.c:18-27); NULL = 1..n in atom
+                                      * order.  Only read for JB_ORDER_REFERENCE.   */
 } jb_molecule_batch;
 
+/* order of the hit records (jb_hits) inside one (molecule, template) run      */
+typedef enum jb_hit_order {
+    JB_ORDER_CANONICAL = 0,  /* atom tuple ascending (set comparison, default)  */
+    JB_ORDER_REFERENCE = 1,  /* the order in which the reference's depth-first
+                              * Scanner_next yields them (eff:Scanner.c:193-304)
+                              * when run with reorder=True: first scan level in
+                              * candidate-list order (eff:TessTemplate.c:141-201),
+                              * deeper levels in the reverse leaf order of the k-d
+                              * tree built over the candidate set
+                              * (eff:KdTree.c:238-296,343-423, qselect.h.patch).
+                              * Independent of the engine's own `reorder`.        */
+    JB_ORDER_REFERENCE_NOREORDER = 2  /* same for the reference run with
+                              * reorder=False (template atom order)               */
+} jb_hit_order;
+
 /* arguments of Jess.query (src/pyjess/_jess.pyx:2758-2769) that reach the
- * search; max_candidates is order dependent and not part of this ABI.        */
+ * search.  max_candidates (order dependent, :2263-2269) is applied by the host
+ * layer on an all_tuples run in JB_ORDER_REFERENCE.                          */
 typedef struct jb_query_params {
     double rmsd_threshold;
     double distance_cutoff;          /* Jess_query t  (eff:Jess.c:119)        */
@@ -103,11 +122,16 @@ typedef struct jb_query_params {
                                       * eff:Scanner.c:88-99), 2 the engine's own
                                       * fan-out heuristic; the hit SET is the same */
     int32_t best_match;              /* keep min-RMSD hit per (mol, template) */
+    int32_t hit_order;               /* jb_hit_order                          */
+    int32_t all_tuples;              /* 1: report EVERY full tuple with its
+                                      * superposition (no RMSD filter, NaN
+                                      * rotations kept): what JessQuery_next
+                                      * yields before Query.__next__ filters   */
     int32_t reserved;
 } jb_query_params;
 
 /* compacted hits, host memory owned by the jb_result they were fetched from.
- * Canonical order: (molecule, template, atom tuple) ascending.
+ * Order: (molecule, template) ascending, then jb_query_params.hit_order.
  * Record i: atoms[i*stride + k] = index (within its molecule) of the atom
  * matched to template atom k (JessQuery_atoms, eff:Jess.c:169-174); -1 pad.
  * rotation/centre0/centre1 as Superposition_rotation / _centroid(0|1)
@@ -203,6 +227,48 @@ int jb_query_host(jb_context *ctx, const jb_templates *tpl,
                   const jb_molecule_batch *batch,
                   const jb_query_params *params, jb_result **out,
                   jb_hits *hits);
+
+/* ---- structure ingest (HOST code): replaces the per-line
+ * PDBMoleculeParser.load loop (src/pyjess/_io.py:68-103) + Atom.loads
+ * (src/pyjess/_jess.pyx:931-961) + Atom_parse (vendor/jess/src/Atom.c:32-72 as
+ * patched) with ONE pass over the file image.  A record is the reference's
+ * struct _Atom (eff:Atom.h:29-47) without padding, so that it maps 1:1 onto the
+ * host layer's numpy record dtype.                                            */
+#pragma pack(push, 1)
+typedef struct jb_atom_record {
+    double x[3];
+    float occupancy;
+    float temp_factor;
+    int32_t serial;
+    char name[4];                    /* blanks -> '_'                         */
+    uint8_t alt_loc;
+    char res_name[4];                /* 3 chars + NUL                         */
+    uint8_t chain_id1;
+    uint8_t chain_id2;
+    int32_t res_seq;
+    uint8_t i_code;
+    char seg_id[4];
+    char element[2];
+    int8_t charge;
+} jb_atom_record;
+#pragma pack(pop)
+
+#define JB_PDB_SKIP_HETATM 1         /* PDBMoleculeParser(skip_hetatm=True)   */
+#define JB_PDB_IGNORE_ENDMDL 2       /* PDBMoleculeParser(ignore_endmdl=True) */
+
+typedef struct jb_pdb_info {
+    int64_t n_atoms;                 /* ATOM/HETATM records found (may exceed capacity) */
+    int64_t header_offset;           /* first HEADER line, -1 if none         */
+    int64_t header_length;
+    int64_t stop_offset;             /* where the scan stopped (ENDMDL / end) */
+    int32_t mmcif_tags;              /* a data_/loop_ line was met: not PDB   */
+    int32_t reserved;
+} jb_pdb_info;
+
+/* Parses the ATOM/HETATM lines of `text` up to the first ENDMDL into `records`.
+ * JB_ERR_CAPACITY: info->n_atoms tells the capacity to retry with.           */
+int jb_pdb_parse(const char *text, int64_t n_bytes, int32_t flags,
+                 jb_atom_record *records, int64_t capacity, jb_pdb_info *info);
 
 #ifdef __cplusplus
 }

@@ -108,7 +108,7 @@ static int make_molecule(const jb_molecule_batch *B, int m, ref_mol *out)
     for (int i = 0; i < n; i++) {
         Atom *a = &A[i];
         a->x[0] = B->x[a0 + i]; a->x[1] = B->y[a0 + i]; a->x[2] = B->z[a0 + i];
-        a->serial = i + 1; /* unique; ResIndex sorts by (resName, serial) */
+        a->serial = B->serial ? B->serial[a0 + i] : i + 1; /* ResIndex sorts by (resName, serial) */
         memcpy(a->name, &B->name[a0 + i], 4); a->name[4] = 0;
         memcpy(a->resName, &B->residue_name[a0 + i], 4);
         a->altLoc = ' '; a->iCode = ' ';
@@ -200,7 +200,10 @@ int ref_query(const jb_template_table *T, const jb_molecule_batch *B, const jb_q
         if (make_molecule(B, m, &mols[m]) != 0) failed = 1;
 
     double t0 = now_ms();
-    (void)n_threads;
+    /* hit_order != canonical: keep the reference's own iteration order (structures ascending,
+     * templates in reverse insertion order, Scanner_next order inside) -- one thread, no sort */
+    const int ordered = Q->hit_order != 0;
+    if (ordered) n_threads = 1;
 #ifdef _OPENMP
 #pragma omp parallel num_threads(n_threads > 0 ? n_threads : 1)
 #endif
@@ -235,7 +238,7 @@ int ref_query(const jb_template_table *T, const jb_molecule_batch *B, const jb_q
     if (J) Jess_free(J); /* frees the templates it owns */
     free(tpls);
     if (failed) { hb_free(R); return JB_ERR_NOMEM; }
-    hb_sort(R);
+    if (!ordered) hb_sort(R);
     *out = R;
     return JB_OK;
 }

@@ -11,10 +11,12 @@ compacted hit records lazily:
   launch sequence for all structures, one `Query` per structure.
 
 Iteration order: templates in REVERSE insertion order like the reference
-(eff:Jess.c:109-117), hits of one template in canonical atom-tuple order (the
-reference's order is its k-d tree walk; `reorder=True` already changes it there).
-Order-dependent ``max_candidates`` is not reproducible by a breadth-first engine
-and raises `NotImplementedError`.  There is no CPU fallback.
+(eff:Jess.c:109-117), hits of one template in the order the reference's depth-first
+scanner yields them: the engine reconstructs it on the device from the candidate-set
+positions and k-d tree leaf ranks (csrc/order.cuh, `hit_order="reference"`).  That
+makes the two order-dependent features exact: the tie rule of ``best_match`` and
+``max_candidates`` (`Query.__next__` _jess.pyx:2197-2283, replayed by
+`_replay_query` over the ordered stream of ALL tuples).  There is no CPU fallback.
 """
 from __future__ import annotations
 
@@ -141,44 +143,16 @@ def _rebuild_hit(state):
     return hit
 
 
-def _reference_first_candidate(molecule: Molecule, tatom, cand: np.ndarray):
-    """Index of the candidate the reference never reports for a SINGLE-ATOM template.
-
-    `Scanner_reuse` pre-selects candidate 0 of the first scan level and `Scanner_next`
-    pre-increments before yielding (eff:Scanner.c:176-181, 212-227), so with n == 1 the
-    first entry of the reference's candidate list is skipped.  That list is built by
-    `TessTemplate_candidates` (eff:TessTemplate.c:141-201): for match modes -1..8 by
-    walking the template atom's residue names in order through the residue index, whose
-    groups are sorted by serial (eff:ResIndex.c:18-27); for the other modes in molecule
-    order.  `cand` = atom indices of all candidates of the pair."""
-    if len(cand) == 0:
-        return None
-    atoms = molecule._atoms
-    if -1 <= tatom._code <= 8:
-        res = np.char.upper(atoms["resName"][cand])
-        done = set()
-        for name in tatom._resnames:
-            tok = name.ljust(4, b"\0")[:4].upper().rstrip(b"\0")
-            if tok in done:
-                continue
-            done.add(tok)
-            sel = cand[res == tok]
-            if len(sel):
-                order = np.lexsort((sel, atoms["serial"][sel]))
-                return int(sel[order[0]])
-        return None
-    return int(cand.min())
-
-
 class _BatchRun:
     """Shared, lazily executed engine call of one `query` / `query_many`."""
 
-    __slots__ = ("jess", "molecules", "params_args", "table", "stats", "_slices", "done")
+    __slots__ = ("jess", "molecules", "args", "all_tuples", "table", "stats", "_slices", "done")
 
-    def __init__(self, jess, molecules, params_args):
+    def __init__(self, jess, molecules, args, all_tuples):
         self.jess = jess
         self.molecules = molecules
-        self.params_args = params_args
+        self.args = args                  # rmsd, distance, max_dynamic, ignore_chain, reorder, best_match
+        self.all_tuples = all_tuples      # stream of every tuple (max_candidates replay) instead of hits
         self.table: Optional[HitTable] = None
         self.stats = None
         self._slices = None
@@ -195,25 +169,28 @@ class _BatchRun:
         from . import _capi  # raises if the CUDA engine is missing: no fallback
         ctx = _capi.default_context()
         dev_tpl = jess._device_templates(ctx)
-        batch = MoleculeBatch(mols)
-        params = query_params(*self.params_args)
+        batch = MoleculeBatch(mols, serial=True)
+        rmsd, dist, maxdyn, ignore_chain, reorder, best_match = self.args
+        # the engine searches in its own scan order; the ORDER of the records is the
+        # reference's for the `reorder` flag the caller passed
+        params = query_params(rmsd, dist, maxdyn, ignore_chain, 2, best_match and not self.all_tuples,
+                              hit_order="reference" if reorder else "reference-noreorder",
+                              all_tuples=self.all_tuples)
         self.table, self.stats = _capi.query_host(ctx, dev_tpl, batch, params)
         if self.stats["nan_dropped"]:
             warnings.warn("Jess returned a superposition matrix with NaN values", UserWarning, stacklevel=4)
         t = self.table
-        # single-atom templates: the engine reports every candidate, the reference never its first one
-        single = [i for i, tpl in enumerate(jess._templates) if len(tpl) == 1]
+        # single-atom templates: the engine reports every candidate, the reference never the
+        # FIRST of its candidate list (Scanner_reuse pre-selects index 0 and Scanner_next
+        # pre-increments, eff:Scanner.c:176-181,212-227) -- in reference order that is the
+        # first record of the (structure, template) run
         keep = None
-        if single and t.count:
-            keep = np.ones(t.count, dtype=bool)
-            for i in single:
-                rows = np.nonzero(t.template == i)[0]
-                for m in np.unique(t.molecule[rows]):
-                    sel = rows[t.molecule[rows] == m]
-                    first = _reference_first_candidate(mols[int(m)], jess._templates[i][0], t.atoms[sel, 0])
-                    if first is not None:
-                        keep[sel[t.atoms[sel, 0] == first]] = False
-        # iteration order per structure: template DESCENDING (reverse insertion), canonical tuple order within
+        single = np.asarray([len(tpl) == 1 for tpl in jess._templates], dtype=bool)
+        if single.any() and t.count:
+            first = np.ones(t.count, dtype=bool)
+            first[1:] = (t.molecule[1:] != t.molecule[:-1]) | (t.template[1:] != t.template[:-1])
+            keep = ~(first & single[t.template])
+        # iteration order per structure: template DESCENDING (reverse insertion), engine order within
         slices = []
         bounds = np.searchsorted(t.molecule, np.arange(len(mols) + 1))
         for m in range(len(mols)):
@@ -235,15 +212,19 @@ class Query:
 
     def __init__(self, jess, molecule, rmsd_threshold, best_match, ignore_chain, max_candidates, run: _BatchRun,
                  index: int):
+        self._run = run
+        self._index = index
+        self._pos = 0
         self.ignore_chain = ignore_chain
         self.max_candidates = max_candidates
         self._jess = jess
         self._molecule = molecule
         self._rmsd_threshold = float(rmsd_threshold)
         self._best_match = bool(best_match)
-        self._run = run
-        self._index = index
-        self._pos = 0
+        # replay state of Query.__next__ (max_candidates mode)
+        self._partial = False
+        self._candidates = 0
+        self._skip_template = None
 
     jess = property(lambda self: self._jess)
     molecule = property(lambda self: self._molecule)
@@ -268,22 +249,72 @@ class Query:
     def max_candidates(self, value):
         if value is not None and value < 0:
             raise ValueError(f"invalid value for `max_candidates` argument: {value!r}")
+        if value is not None and not self._run.all_tuples:
+            if self._run.done:
+                raise RuntimeError("max_candidates cannot be enabled once the query has started")
+            self._run.all_tuples = True      # lazily executed: switch the shared run to the tuple stream
         self._max_candidates = value
 
     def __iter__(self):
         return self
 
     def __next__(self) -> Hit:
-        if self._max_candidates is not None:
-            raise NotImplementedError(
-                "max_candidates depends on the reference's depth-first k-d tree order and is not "
-                "available on the breadth-first GPU engine; use max_candidates=None")
         idx = self._run.indices(self._index)
+        if self._run.all_tuples:
+            return self._replay_next(idx)
         if self._pos >= len(idx):
             raise StopIteration
         i = int(idx[self._pos])
         self._pos += 1
         return self._make_hit(i)
+
+    def _replay_next(self, idx: np.ndarray) -> Hit:
+        """`Query.__next__` of the reference (_jess.pyx:2197-2283) replayed over the stream
+        of ALL tuples in the reference's iteration order: RMSD filter, NaN drop,
+        best_match, and the max_candidates counter with its quirks (the counter restarts
+        on every call because the local `tpl` starts as NULL, :2203,2222; exceeding it
+        abandons the rest of the template, JessQuery_nextTemplate eff:Jess.c:197-205)."""
+        t = self._run.table
+        limit = -1 if self._max_candidates is None else int(self._max_candidates)
+        tpl = None
+        hit_i, hit_rmsd, hit_tpl = -1, math.inf, None
+        while True:
+            # _advance (:2169-2173)
+            if self._partial:
+                self._partial = False
+            else:
+                self._pos += 1
+                if self._skip_template is not None:
+                    while self._pos <= len(idx) and int(t.template[idx[self._pos - 1]]) == self._skip_template:
+                        self._pos += 1
+                    self._skip_template = None
+            if self._pos > len(idx):
+                self._pos = len(idx) + 1
+                break
+            i = int(idx[self._pos - 1])
+            prev_tpl = tpl
+            tpl = int(t.template[i])
+            if hit_i >= 0 and hit_tpl != tpl:
+                self._partial = True          # _rewind
+                break
+            rmsd = float(t.rmsd[i])
+            if rmsd <= self._rmsd_threshold and rmsd < hit_rmsd:
+                if np.isnan(t.rotation[i]).any():
+                    warnings.warn("Jess returned a superposition matrix with NaN values", UserWarning, stacklevel=3)
+                else:
+                    hit_i, hit_rmsd, hit_tpl = i, rmsd, tpl
+            if tpl != prev_tpl:
+                self._candidates = 0
+            else:
+                self._candidates += 1
+            if limit != -1 and self._candidates > limit:
+                self._candidates = 0
+                self._skip_template = tpl      # JessQuery_nextTemplate
+            if hit_i >= 0 and not self._best_match:
+                break
+        if hit_i < 0:
+            raise StopIteration
+        return self._make_hit(hit_i)
 
     def _make_hit(self, i: int) -> Hit:
         t = self._run.table
@@ -404,7 +435,10 @@ class Jess:
         ignore_chain = self._normalise_ignore_chain(ignore_chain)
         if ignore_chain not in (None, "residues", "atoms"):
             raise ValueError(f"invalid value for `ignore_chain`: {ignore_chain!r}")
+        if max_candidates is not None and max_candidates < 0:
+            raise ValueError(f"invalid value for `max_candidates` argument: {max_candidates!r}")
         run = _BatchRun(self, molecules,
-                        (rmsd_threshold, distance_cutoff, max_dynamic_distance, ignore_chain, reorder, best_match))
+                        (rmsd_threshold, distance_cutoff, max_dynamic_distance, ignore_chain, bool(reorder),
+                         bool(best_match)), all_tuples=max_candidates is not None)
         return [Query(self, m, rmsd_threshold, best_match, ignore_chain, max_candidates, run, i)
                 for i, m in enumerate(molecules)]

@@ -54,6 +54,7 @@ class jb_molecule_batch(C.Structure):
         ("residue_name", c_u32p),
         ("residue_number", c_i32p),
         ("chain_id2", c_u8p),
+        ("serial", c_i32p),
     ]
 
 
@@ -65,6 +66,8 @@ class jb_query_params(C.Structure):
         ("ignore_chain", C.c_int32),
         ("reorder", C.c_int32),
         ("best_match", C.c_int32),
+        ("hit_order", C.c_int32),
+        ("all_tuples", C.c_int32),
         ("reserved", C.c_int32),
     ]
 
@@ -195,7 +198,8 @@ class MoleculeBatch:
     FIELDS = (("x", np.float64), ("y", np.float64), ("z", np.float64), ("name", np.uint32),
               ("resname", np.uint32), ("resseq", np.int32), ("chain", np.uint8))
 
-    def __init__(self, molecules: Sequence[Molecule], pinned: bool = False):
+    def __init__(self, molecules: Sequence[Molecule], pinned: bool = False, serial: bool = False):
+        """`serial=True` also ships Atom.serial (only the reference hit order reads it)."""
         molecules = list(molecules)
         self.molecules = molecules
         self.n_molecules = len(molecules)
@@ -211,6 +215,12 @@ class MoleculeBatch:
             if packs:
                 np.concatenate([p[field] for p in packs], out=buf[:total])
             setattr(self, field, buf)
+        self.serial = None
+        if serial:
+            self.serial = self._alloc(max(total, 1), np.int32, pinned)
+            if molecules:
+                np.concatenate([np.ascontiguousarray(m._atoms["serial"], dtype=np.int32) for m in molecules],
+                               out=self.serial[:total])
         self._struct = None
 
     def _alloc(self, n, dtype, pinned):
@@ -223,7 +233,8 @@ class MoleculeBatch:
 
     @property
     def nbytes(self) -> int:
-        return int(self.atom_offset.nbytes + sum(getattr(self, f).nbytes for f, _ in self.FIELDS))
+        return int(self.atom_offset.nbytes + sum(getattr(self, f).nbytes for f, _ in self.FIELDS)
+                   + (self.serial.nbytes if self.serial is not None else 0))
 
     def as_struct(self) -> jb_molecule_batch:
         if self._struct is None:
@@ -237,21 +248,30 @@ class MoleculeBatch:
             s.residue_name = _ptr(self.resname, c_u32p)
             s.residue_number = _ptr(self.resseq, c_i32p)
             s.chain_id2 = _ptr(self.chain, c_u8p)
+            s.serial = _ptr(self.serial, c_i32p) if self.serial is not None else None
             self._struct = s
         return self._struct
 
 
+HIT_ORDER = {"canonical": 0, "reference": 1, "reference-noreorder": 2}
+
+
 def query_params(rmsd_threshold, distance_cutoff, max_dynamic_distance, ignore_chain=None,
-                 reorder=True, best_match=False) -> jb_query_params:
+                 reorder=True, best_match=False, hit_order="canonical", all_tuples=False) -> jb_query_params:
     """`reorder`: True -> 2 (the engine's expected-fan-out scan order), False -> 0
     (template order); an int selects the mode explicitly (1 = the reference's argsort
-    by |C_k|).  The hit set never depends on it."""
+    by |C_k|).  The hit set never depends on it.  `hit_order`: "canonical" (atom tuple
+    ascending) or the reference's own iteration order for its reorder=True /
+    reorder=False runs ("reference" / "reference-noreorder", include/jess_b200.h)."""
     if ignore_chain not in IGNORE_CHAIN:
         raise ValueError(f"invalid value for `ignore_chain`: {ignore_chain!r}")
     if isinstance(reorder, bool):
         reorder = 2 if reorder else 0
+    if hit_order not in HIT_ORDER:
+        raise ValueError(f"invalid value for `hit_order`: {hit_order!r}")
     return jb_query_params(float(rmsd_threshold), float(distance_cutoff), float(max_dynamic_distance),
-                           IGNORE_CHAIN[ignore_chain], int(reorder), int(bool(best_match)), 0)
+                           IGNORE_CHAIN[ignore_chain], int(reorder), int(bool(best_match)), HIT_ORDER[hit_order],
+                           int(bool(all_tuples)), 0)
 
 
 class HitTable:

@@ -20,6 +20,8 @@
 #include "kernels.cuh"
 #include "expand_lv.cuh"
 #include "hits.cuh"
+#include "order.cuh"
+#include <cub/device/device_radix_sort.cuh>
 
 using namespace jb;
 
@@ -118,6 +120,8 @@ struct jb_context {
     DevBuf h_mol, h_tpl, h_atoms, h_rmsd, h_rot, h_c0, h_c1;   // hits as k_superpose appends them
     DevBuf f_mol, f_tpl, f_atoms, f_rmsd, f_rot, f_c0, f_c1;   // ... in canonical order (hits.cuh)
     DevBuf o_off, o_fill, o_grouped, o_order, o_tiles, o_runs, o_work;   // ordering workspace
+    DevBuf h_pair, h_keys;                                     // reference-order mode: pair of each hit, rank vectors
+    DevBuf q_ocnt, q_keyA, q_keyA2, q_keyB, q_keyB2, q_iota, q_perm, q_setpos, q_kdrank, q_coords, q_kdidx, q_cub;
     RunWork *host_work = nullptr;                              // pinned
     std::vector<std::pair<void *, size_t>> pin_pool;           // page-locked result blocks, recycled
     long long hit_cap = 0;
@@ -133,6 +137,9 @@ struct jb_templates {
     std::vector<int> atom_off;
     DevBuf d_atom_off, d_spec, d_resseq, d_chain, d_pos, d_weight, d_dist_off, d_dist, d_shell, d_vol;
     DevBuf s_code, s_noff, s_nraw, s_nup, s_roff, s_rup;
+    int OS = 0;                                   // ordered specs (order.cuh)
+    bool order_ok = true;                         // false: an atom lists > 31 distinct residue names
+    DevBuf o_spec, o_byres, o_roff, o_res, d_ospec;
     long long n_dist = 0;
 };
 
@@ -141,9 +148,10 @@ struct jb_molecules {
     int M = 0;
     long long NA = 0;
     std::vector<long long> atom_off;
-    DevBuf d_off, x, y, z, name, res, resseq, chain, atoms;
+    DevBuf d_off, x, y, z, name, res, resseq, chain, atoms, serial;
+    bool has_serial = false;
     DevBuf srec, sname, sres, ext, sort_scratch;   // x-sorted FP32 view (k_sort_atoms)
-    std::vector<DevBuf *> all() { return { &d_off, &x, &y, &z, &name, &res, &resseq, &chain, &atoms, &srec, &sname, &sres, &ext, &sort_scratch }; }
+    std::vector<DevBuf *> all() { return { &d_off, &x, &y, &z, &name, &res, &resseq, &chain, &atoms, &serial, &srec, &sname, &sres, &ext, &sort_scratch }; }
 };
 
 struct jb_result {
@@ -218,7 +226,9 @@ extern "C" void jb_context_destroy(jb_context *c)
     DevBuf *bufs[] = { &c->crec, &c->chead, &c->recs, &c->ordbuf, &c->fr[0], &c->fr[1],
                        &c->tuples, &c->ctr, &c->h_mol, &c->h_tpl, &c->h_atoms, &c->h_rmsd, &c->h_rot, &c->h_c0,
                        &c->h_c1, &c->f_mol, &c->f_tpl, &c->f_atoms, &c->f_rmsd, &c->f_rot, &c->f_c0, &c->f_c1,
-                       &c->o_off, &c->o_fill, &c->o_grouped, &c->o_order, &c->o_tiles, &c->o_runs, &c->o_work };
+                       &c->o_off, &c->o_fill, &c->o_grouped, &c->o_order, &c->o_tiles, &c->o_runs, &c->o_work,
+                       &c->h_pair, &c->h_keys, &c->q_ocnt, &c->q_keyA, &c->q_keyA2, &c->q_keyB, &c->q_keyB2, &c->q_iota,
+                       &c->q_perm, &c->q_setpos, &c->q_kdrank, &c->q_coords, &c->q_kdidx, &c->q_cub };
     for (DevBuf *b : bufs) b->release();
     if (c->scratch_mol) {
         jb_molecules *m = c->scratch_mol;
@@ -311,6 +321,35 @@ extern "C" int jb_templates_create(jb_context *c, const jb_template_table *tb, j
         } else spec[a] = it->second;
     }
     t->S = (int)s_code.size();
+    // ordered specs (order.cuh): engine spec + the residue names in the order written
+    // (duplicates skipped like the `done` array of eff:TessTemplate.c:160-176)
+    std::map<std::vector<uint32_t>, int> oseen;
+    std::vector<int> ospec(t->TA), o_spec, o_byres, o_roff{0};
+    std::vector<uint32_t> o_res;
+    for (int a = 0; a < t->TA; a++) {
+        const int code = tb->match_mode[a];
+        const bool by_res = code >= -1 && code <= 8;
+        std::vector<uint32_t> ord;
+        if (by_res)
+            for (int k = tb->resname_offset[a]; k < tb->resname_offset[a + 1]; k++) {
+                const uint32_t v = upper4_host(tb->residue_names[k]);
+                if (std::find(ord.begin(), ord.end(), v) == ord.end()) ord.push_back(v);
+            }
+        if (ord.size() > 31) t->order_ok = false;
+        std::vector<uint32_t> key{ (uint32_t)spec[a] };
+        key.insert(key.end(), ord.begin(), ord.end());
+        auto it = oseen.find(key);
+        if (it == oseen.end()) {
+            const int id = (int)o_spec.size();
+            oseen.emplace(key, id);
+            o_spec.push_back(spec[a]);
+            o_byres.push_back(by_res ? 1 : 0);
+            for (uint32_t v : ord) o_res.push_back(v);
+            o_roff.push_back((int)o_res.size());
+            ospec[a] = id;
+        } else ospec[a] = it->second;
+    }
+    t->OS = (int)o_spec.size();
     t->n_dist = T ? tb->distance_offset[T] : 0;
     cudaStream_t st = c->stream;
     std::vector<long long> dist_off(tb->distance_offset, tb->distance_offset + T + 1);
@@ -330,6 +369,11 @@ extern "C" int jb_templates_create(jb_context *c, const jb_template_table *tb, j
     UP(t->s_nup, s_nup.data(), s_nup.size());
     UP(t->s_roff, s_roff.data(), s_roff.size());
     UP(t->s_rup, s_rup.data(), s_rup.size());
+    UP(t->o_spec, o_spec.data(), o_spec.size());
+    UP(t->o_byres, o_byres.data(), o_byres.size());
+    UP(t->o_roff, o_roff.data(), o_roff.size());
+    UP(t->o_res, o_res.data(), o_res.size());
+    UP(t->d_ospec, ospec.data(), ospec.size());
 #undef UP
     if (e == cudaSuccess) e = t->d_shell.ensure(std::max<size_t>(t->n_dist, 1) * sizeof(ShellRec), st);
     if (e == cudaSuccess) e = t->d_vol.ensure(std::max<size_t>(t->n_dist, 1) * sizeof(double), st);
@@ -349,7 +393,7 @@ extern "C" void jb_templates_free(jb_templates *t)
     cudaStreamSynchronize(t->ctx->stream);
     DevBuf *bufs[] = { &t->d_atom_off, &t->d_spec, &t->d_resseq, &t->d_chain, &t->d_pos, &t->d_weight, &t->d_dist_off,
                        &t->d_dist, &t->d_shell, &t->d_vol, &t->s_code, &t->s_noff, &t->s_nraw, &t->s_nup, &t->s_roff,
-                       &t->s_rup };
+                       &t->s_rup, &t->o_spec, &t->o_byres, &t->o_roff, &t->o_res, &t->d_ospec };
     for (DevBuf *b : bufs) b->release();
     delete t;
 }
@@ -380,6 +424,8 @@ static int fill_molecules(jb_context *c, jb_molecules *m, const jb_molecule_batc
     UP(m->res, b->residue_name, m->NA);
     UP(m->resseq, b->residue_number, m->NA);
     UP(m->chain, b->chain_id2, m->NA);
+    m->has_serial = b->serial != nullptr;
+    if (m->has_serial) UP(m->serial, b->serial, m->NA);
 #undef UP
     if (e == cudaSuccess) e = m->atoms.ensure(std::max<size_t>((size_t)m->NA, 1) * sizeof(AtomRec), st);
     if (e == cudaSuccess && m->NA > 0) {
@@ -487,6 +533,79 @@ static cudaError_t dispatch_expand_lv(int level, int g, int sm_count, cudaStream
 #undef JB_LV_CASE
 }
 
+// Reference iteration order (order.cuh): builds the (structure, ordered spec) rank tables of
+// the chunk and the rank vector of every hit in [h0, h1).
+static int build_reference_keys(jb_context *c, const jb_templates *t, const jb_molecules *mol, const jb_query_params *q,
+                                int m0, int Mc, const MolTable &MT, const CandTable &CT, const TemplateTable &TT,
+                                long long h0, long long h1, jb_stats &S)
+{
+    cudaStream_t st = c->stream;
+    if (!t->order_ok) return fail(JB_ERR_INVALID, "reference hit order: a template atom lists more than 31 residue names");
+    const long long nl = (long long)Mc * t->OS;
+    if (nl >= (1ll << kListBits)) return fail(JB_ERR_INVALID, "reference hit order: %lld candidate lists in one chunk", nl);
+    OrderSpecs O;
+    O.n_ospecs = t->OS; O.spec = t->o_spec.as<int>(); O.by_res = t->o_byres.as<int>(); O.res_off = t->o_roff.as<int>();
+    O.res_up = t->o_res.as<uint32_t>(); O.atom_ospec = t->d_ospec.as<int>();
+    const int n_tiles = (int)((nl + 1 + kScanTile - 1) / kScanTile);
+    CU(c->q_ocnt.ensure((size_t)(nl + 1) * sizeof(unsigned), st));
+    CU(c->o_tiles.ensure((size_t)n_tiles * sizeof(unsigned), st));
+    unsigned *ooff = c->q_ocnt.as<unsigned>();
+    k_olist_count<<<(unsigned)((nl + 1 + 255) / 256), 256, 0, st>>>(Mc, O, t->S, CT.head, ooff);
+    k_scan_tiles<<<n_tiles, kScanThreads, 0, st>>>(ooff, nl + 1, c->o_tiles.as<unsigned>());
+    k_scan_totals<<<1, kScanThreads, 0, st>>>(c->o_tiles.as<unsigned>(), n_tiles);
+    k_scan_add<<<n_tiles, kScanThreads, 0, st>>>(ooff, nl + 1, c->o_tiles.as<unsigned>());
+    CU(cudaGetLastError());
+    unsigned total = 0;
+    CU(cudaMemcpyAsync(&total, ooff + nl, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    S.launches += 4;
+    const size_t n = total;
+    if (n > 0) {
+        CU(c->q_keyA.ensure(n * sizeof(u64), st));  CU(c->q_keyA2.ensure(n * sizeof(u64), st));
+        CU(c->q_keyB.ensure(n * sizeof(u64), st));  CU(c->q_keyB2.ensure(n * sizeof(u64), st));
+        CU(c->q_iota.ensure(n * sizeof(unsigned), st)); CU(c->q_perm.ensure(n * sizeof(unsigned), st));
+        CU(c->q_setpos.ensure(n * sizeof(unsigned), st)); CU(c->q_kdrank.ensure(n * sizeof(unsigned), st));
+        CU(c->q_coords.ensure(n * 3 * sizeof(double), st)); CU(c->q_kdidx.ensure(n * sizeof(int), st));
+        k_olist_fill<<<(unsigned)((nl * 32 + 255) / 256), 256, 0, st>>>(
+            Mc, O, t->S, CT.head, CT.rec, MT.atom_off, mol->res.as<uint32_t>(),
+            mol->has_serial ? mol->serial.as<int>() : nullptr, ooff, c->q_keyA.as<u64>(), c->q_keyB.as<u64>());
+        CU(cudaGetLastError());
+        int list_bits = 1;
+        while ((1ll << list_bits) < nl) list_bits++;
+        // sort 1: (list, atom) ascending; carries the CandidateSet key
+        size_t tmp1 = 0, tmp2 = 0;
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp1, c->q_keyA.as<u64>(), c->q_keyA2.as<u64>(), c->q_keyB.as<u64>(),
+                                           c->q_keyB2.as<u64>(), (int)n, 0, 32 + list_bits, st));
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp2, c->q_keyB2.as<u64>(), c->q_keyB.as<u64>(), c->q_iota.as<unsigned>(),
+                                           c->q_perm.as<unsigned>(), (int)n, 0, 37 + list_bits, st));
+        CU(c->q_cub.ensure(std::max(tmp1, tmp2), st));
+        CU(cub::DeviceRadixSort::SortPairs(c->q_cub.p, tmp1, c->q_keyA.as<u64>(), c->q_keyA2.as<u64>(), c->q_keyB.as<u64>(),
+                                           c->q_keyB2.as<u64>(), (int)n, 0, 32 + list_bits, st));
+        k_iota<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->q_iota.as<unsigned>(), (long long)n);
+        // sort 2 (stable): by (list, residue-name position, serial); ties keep atom order
+        CU(cub::DeviceRadixSort::SortPairs(c->q_cub.p, tmp2, c->q_keyB2.as<u64>(), c->q_keyB.as<u64>(), c->q_iota.as<unsigned>(),
+                                           c->q_perm.as<unsigned>(), (int)n, 0, 37 + list_bits, st));
+        k_olist_ranks<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+            (long long)n, t->OS, c->q_keyB.as<u64>(), c->q_perm.as<unsigned>(), c->q_keyA2.as<u64>(), ooff, MT.atom_off,
+            MT.atoms, c->q_setpos.as<unsigned>(), c->q_coords.as<double>(), c->q_kdidx.as<int>());
+        k_kd_order<<<(unsigned)((nl + 127) / 128), 128, 0, st>>>(nl, ooff, c->q_coords.as<double>(), c->q_kdidx.as<int>(),
+                                                                 c->q_perm.as<unsigned>(), c->q_kdrank.as<unsigned>());
+        CU(cudaGetLastError());
+        S.launches += 6;   // + the radix sort passes (library kernels)
+    }
+    HitKeyArgs K;
+    K.h0 = h0; K.h1 = h1; K.stride = c->hit_stride; K.n_specs = t->S;
+    K.ref_reorder = q->hit_order == JB_ORDER_REFERENCE ? 1 : 0;
+    K.pair = c->h_pair.as<int>(); K.atoms = c->h_atoms.as<int>(); K.recs = c->recs.as<PairRec>(); K.tpl_spec = TT.spec;
+    K.head = CT.head; K.O = O; K.ooff = ooff; K.atom_sorted = c->q_keyA2.as<u64>();
+    K.set_pos = c->q_setpos.as<unsigned>(); K.kd_rank = c->q_kdrank.as<unsigned>(); K.keys = c->h_keys.as<int>();
+    k_hit_keys<<<(unsigned)((h1 - h0 + 127) / 128), 128, 0, st>>>(K);
+    CU(cudaGetLastError());
+    S.launches++;
+    (void)m0;
+    return JB_OK;
+}
+
 struct Range { int m0, m1; };
 
 static int grow_hits(jb_context *c, long long need, int stride)
@@ -496,6 +615,8 @@ static int grow_hits(jb_context *c, long long need, int stride)
     const size_t keep = (size_t)std::min(c->hit_cap, need);
     cudaStream_t st = c->stream;
     const bool same = stride == c->hit_stride;
+    CU(c->h_pair.ensure(cap * sizeof(int), st, same ? keep * sizeof(int) : 0));
+    CU(c->h_keys.ensure(cap * sizeof(int) * stride, st, 0));
     CU(c->h_mol.ensure(cap * sizeof(int), st, same ? keep * sizeof(int) : 0));
     CU(c->h_tpl.ensure(cap * sizeof(int), st, same ? keep * sizeof(int) : 0));
     CU(c->h_atoms.ensure(cap * sizeof(int) * stride, st, same ? keep * sizeof(int) * stride : 0));
@@ -654,11 +775,13 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         CU(cudaEventRecord(c->evs[3], st));
         if (c->debug) CU(cudaEventRecord(c->lev[t->nmax], st));
         HitBuf HB;
+        HB.pair = q->hit_order != JB_ORDER_CANONICAL ? c->h_pair.as<int>() : nullptr;
         HB.mol = c->h_mol.as<int>(); HB.tpl = c->h_tpl.as<int>(); HB.atoms = c->h_atoms.as<int>();
         HB.rmsd = c->h_rmsd.as<double>(); HB.rot = c->h_rot.as<double>(); HB.c0 = c->h_c0.as<double>();
         HB.c1 = c->h_c1.as<double>(); HB.cap = c->hit_cap; HB.stride = c->hit_stride;
         k_superpose<<<c->sm_count * 8, 128, 0, st>>>(c->tuples.as<int>(), &dc->tuples, tuple_cap, tuple_stride,
-                                                    c->recs.as<PairRec>(), TT, MT, r.m0, q->rmsd_threshold, HB, dc);
+                                                    c->recs.as<PairRec>(), TT, MT, r.m0, q->rmsd_threshold, q->all_tuples, HB,
+                                                    dc);
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->evs[4], st));
         CU(cudaMemcpyAsync(c->host_ctr, dc, sizeof(Counters), cudaMemcpyDeviceToHost, st));
@@ -736,6 +859,12 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
             HitOrderArgs OA;
             OA.h0 = h0; OA.h1 = h1; OA.mol_base = r.m0; OA.n_templates = t->T; OA.stride = c->hit_stride;
             OA.mol = HB.mol; OA.tpl = HB.tpl; OA.atoms = HB.atoms;
+            if (q->hit_order != JB_ORDER_CANONICAL) {
+                // rank vectors of the reference's depth-first order replace the atom tuples as sort keys
+                int rc = build_reference_keys(c, t, mol, q, r.m0, Mc, MT, CT, TT, h0, h1, S);
+                if (rc != JB_OK) return rc;
+                OA.atoms = c->h_keys.as<int>();
+            }
             OA.off = c->o_off.as<unsigned>(); OA.fill = c->o_fill.as<unsigned>();
             OA.grouped = c->o_grouped.as<unsigned>(); OA.order = c->o_order.as<unsigned>();
             const unsigned hb = (unsigned)((nh + 255) / 256);
@@ -817,10 +946,11 @@ extern "C" int jb_query_run(jb_context *c, const jb_templates *t, const jb_molec
     if (t->ctx != c || mol->ctx != c) return fail(JB_ERR_INVALID, "templates/molecules belong to another context");
     if (q->ignore_chain < 0 || q->ignore_chain > 2) return fail(JB_ERR_INVALID, "invalid ignore_chain %d", q->ignore_chain);
     if (q->reorder < 0 || q->reorder > 2) return fail(JB_ERR_INVALID, "invalid reorder %d", q->reorder);
+    if (q->hit_order < 0 || q->hit_order > 2) return fail(JB_ERR_INVALID, "invalid hit_order %d", q->hit_order);
     jb_result *res = new jb_result();
     res->ctx = c;
     res->stride = std::max(t->nmax, 1);
-    res->best_match = q->best_match;
+    res->best_match = q->all_tuples ? 0 : q->best_match;
     res->n_templates = t->T;
     const int rc = query_run_impl(c, t, mol, q, res);
     if (rc != JB_OK) { delete res; return rc; }

@@ -849,6 +849,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(const ExpandArgs A
 
 // ---- K4: superposition ----------------------------------------------------------------
 struct HitBuf {
+    int *pair;                   // PairRec index of the hit (reference-order mode), may be NULL
     int *mol, *tpl, *atoms;      // atoms stride = hit_stride
     double *rmsd, *rot, *c0, *c1;
     long long cap;
@@ -887,7 +888,8 @@ __device__ __forceinline__ void plane_rotate(double *W, double *P, int p, int q)
 // structure atoms, set 1 = template positions (eff:Jess.c:189-192).
 __global__ void __launch_bounds__(128) k_superpose(const int *tuples, const u64 *tuple_count, long long tuple_cap,
                                                    int tuple_stride, const PairRec *recs, TemplateTable T, MolTable M,
-                                                   int mol_base, double rmsd_threshold, HitBuf H, Counters *ctr)
+                                                   int mol_base, double rmsd_threshold, int all_tuples, HitBuf H,
+                                                   Counters *ctr)
 {
     u64 n_t = *tuple_count;
     if ((long long)n_t > tuple_cap) n_t = (u64)tuple_cap;
@@ -912,7 +914,7 @@ __global__ void __launch_bounds__(128) k_superpose(const int *tuples, const u64 
             // the centroids, which stay zeroed (vendor/jess/src/Super.c:125-130,152)
             for (int j = 0; j < 9; j++) R[j] = 0.0;
             for (int j = 0; j < 3; j++) ca[j] = cb[j] = 0.0;
-            hit = 0.0 <= rmsd_threshold;
+            hit = all_tuples || 0.0 <= rmsd_threshold;
         } else {
         const long long abase = rec->abase;
         const double *tpos = T.pos + 3ll * rec->ta0;
@@ -965,7 +967,7 @@ __global__ void __launch_bounds__(128) k_superpose(const int *tuples, const u64 
         if (det < 1e-8) { se -= 2.0 * sqrt(fmin(e[0], fmin(e[1], e[2]))); flip = true; }
         rmsd = sa + sb - 2.0 * se;
         rmsd = sqrt(fmax(rmsd, 0.0) / (double)n);
-        if (rmsd <= rmsd_threshold) {
+        if (all_tuples || rmsd <= rmsd_threshold) {
 #pragma unroll
             for (int a = 0; a < 3; a++)
 #pragma unroll
@@ -988,6 +990,7 @@ __global__ void __launch_bounds__(128) k_superpose(const int *tuples, const u64 
                     nan = nan || (v != v);
                 }
             hit = !nan;
+            if (all_tuples) { hit = true; nan = false; }   // the host layer applies Query.__next__'s filters
         }
         }   // n > 1
     }
@@ -1002,6 +1005,7 @@ __global__ void __launch_bounds__(128) k_superpose(const int *tuples, const u64 
     if (hit) {
         const long long slot = (long long)hb + __popc(hm & ((1u << lane) - 1));
         if (slot < H.cap) {
+            if (H.pair) H.pair[slot] = tp[0];
             H.mol[slot] = mol_base + rec->m;
             H.tpl[slot] = rec->t;
             for (int k = 0; k < H.stride; k++) H.atoms[slot * H.stride + k] = k < n ? tp[1 + inv[k]] : -1;

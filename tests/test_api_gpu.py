@@ -190,14 +190,18 @@ def test_query_many_equals_single_queries():
     assert total > 0
 
 
-def test_max_candidates_is_refused_loudly(lnb):
-    """Order-dependent option of the reference's depth-first walk: validated
-    like the reference (test_jess.py:135-156) but not computed by the breadth-first engine."""
-    template = load_template("template_01.qry")
+def test_query_max_candidates(lnb):
+    """The reference's own test (src/pyjess/tests/test_jess.py:135-156)."""
+    jess = Jess([load_template("template_01.qry")])
+    assert len(list(jess.query(lnb, 2, 5, 5))) == 3
+    assert len(list(jess.query(lnb, 2, 5, 5, max_candidates=3))) == 3
+    assert len(list(jess.query(lnb, 2, 5, 5, max_candidates=2))) == 2
+    assert len(list(jess.query(lnb, 2, 5, 5, max_candidates=1))) == 1
     with pytest.raises(ValueError):
-        Jess([template]).query(lnb, 2, 5, 5, max_candidates=-1)
-    with pytest.raises(NotImplementedError):
-        next(Jess([template]).query(lnb, 2, 5, 5, max_candidates=2))
+        list(jess.query(lnb, 2, 5, 5, max_candidates=-1))
+    q = jess.query(lnb, 2, 5, 5)
+    q.max_candidates = 2                 # settable before the first hit is pulled, like the reference's property
+    assert q.max_candidates == 2 and len(list(q)) == 2
 
 
 SINGLE = sorted(c for c in golden_cases() if golden_cases()[c].get("single_atom"))
