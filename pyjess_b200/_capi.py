@@ -10,8 +10,8 @@ import os
 import threading
 from typing import Optional
 
-from ._tables import (HitTable, MoleculeBatch, TemplateTable, jb_hits, jb_molecule_batch, jb_query_params,
-                      jb_stats, jb_template_table)
+from ._tables import (HitTable, MoleculeBatch, TemplateTable, jb_hits, jb_molecule_batch, jb_pdb_info,
+                      jb_query_params, jb_stats, jb_template_table)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libjess_b200.so")
@@ -22,6 +22,7 @@ EXPORTS = [
     "jb_templates_create", "jb_templates_free", "jb_templates_spec_count",
     "jb_molecules_upload", "jb_molecules_free",
     "jb_query_run", "jb_result_fetch", "jb_result_stats", "jb_result_free", "jb_query_host",
+    "jb_pdb_parse",
 ]
 
 _lib = None
@@ -65,6 +66,7 @@ def load_library():
                 "jb_result_stats": (i32, [vp, P(jb_stats)]),
                 "jb_result_free": (None, [vp]),
                 "jb_query_host": (i32, [vp, vp, P(jb_molecule_batch), P(jb_query_params), P(vp), P(jb_hits)]),
+                "jb_pdb_parse": (i32, [C.c_char_p, i64, i32, vp, i64, P(jb_pdb_info)]),
             }
             for name, (res, args) in sig.items():
                 fn = getattr(lib, name)
@@ -184,6 +186,18 @@ def query_host(ctx: Context, templates: DeviceTemplates, batch: MoleculeBatch, p
                                  C.byref(hits)))
     res = Result(ctx, h)
     return HitTable(hits, owner=res), res.stats()
+
+
+def pdb_parse(data: bytes, records, skip_hetatm: bool = False, ignore_endmdl: bool = False) -> jb_pdb_info:
+    """One-pass native PDB parser (host code of the engine library, include/jess_b200.h:
+    jb_pdb_parse): fills the numpy record array `records` (dtype `_model.ATOM_DTYPE`)."""
+    lib = load_library()
+    info = jb_pdb_info()
+    flags = (1 if skip_hetatm else 0) | (2 if ignore_endmdl else 0)
+    rc = lib.jb_pdb_parse(data, len(data), flags, C.c_void_p(records.ctypes.data), len(records), C.byref(info))
+    if rc not in (0, -4):
+        _check(rc)
+    return info
 
 
 _default = {}

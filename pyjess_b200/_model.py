@@ -67,7 +67,7 @@ def _copy_token(src: bytes, n: int) -> bytes:
     if nul >= 0:
         src = src[:nul]
     out = bytes(0x5F if c in b" \t\n\v\f\r" else c for c in src)
-    return out
+    return out.ljust(n, b"_")          # the NUL padding of strncpy is turned into '_' as well
 
 
 def _api_atom_name(name) -> bytes:
@@ -87,11 +87,17 @@ def _atoi(b: bytes) -> int:
     m = _INT_RE.match(b)
     if not m:
         return 0
-    v = int(m.group(1))
-    return max(-(2**31), min(2**31 - 1, v))
+    v = max(-(2**63), min(2**63 - 1, int(m.group(1))))     # atoi = (int) strtol: saturates in long ...
+    return ((v + 2**31) % 2**32) - 2**31                      # ... and truncates to int
+
+
+_HEX_RE = re.compile(rb"[ \t\n\v\f\r]*([+-]?0[xX](?:[0-9a-fA-F]+\.?[0-9a-fA-F]*|\.[0-9a-fA-F]+)(?:[pP][+-]?\d+)?)")
 
 
 def _atof(b: bytes) -> float:
+    m = _HEX_RE.match(b)           # strtod also reads C99 hexadecimal floats
+    if m:
+        return float.fromhex(m.group(1).decode("ascii"))
     m = _FLT_RE.match(b)
     return float(m.group(1)) if m else 0.0
 
@@ -488,8 +494,38 @@ class Molecule:
 
     @classmethod
     def _parse_pdb(cls, data: bytes, *, id, date, name, ignore_endmdl, skip_hetatm, format):
+        """One pass of the engine library's native parser (`jb_pdb_parse`, csrc/ingest.cu)
+        over the file image; only the optional HEADER line is decoded in Python."""
         if format not in ("pdb", "detect"):
             raise ValueError(f"unsupported format on the B200 path: {format!r} (PDB only)")
+        from . import _capi
+        data = bytes(data)
+        cap = data.count(b"ATOM") + data.count(b"HETATM")
+        arr = np.zeros(cap, dtype=ATOM_DTYPE)
+        info = _capi.pdb_parse(data, arr, skip_hetatm=skip_hetatm, ignore_endmdl=ignore_endmdl)
+        if info.mmcif_tags:
+            raise ValueError("mmCIF data tags found, file is not in PDB format")
+        arr = arr[:info.n_atoms]
+        pos = info.header_offset
+        while pos >= 0 and pos < info.stop_offset and (id is None or date is None or name is None):
+            end = data.find(b"\n", pos)
+            text = data[pos:end if end >= 0 else len(data)].decode("utf-8", "replace")
+            if id is None:
+                id = text[62:66].strip() or None
+            if date is None:
+                date_text = text[50:59].strip()
+                if date_text:
+                    date = datetime.datetime.strptime(date_text, "%d-%b-%y").date()
+            if name is None:
+                name = text[10:50].strip() or None
+            pos = data.find(b"\nHEADER", pos + 1, info.stop_offset)
+            pos = pos + 1 if pos >= 0 else -1
+        return cls._from_records(arr, id=id, date=date, name=name)
+
+    @classmethod
+    def _parse_pdb_python(cls, data: bytes, *, id=None, date=None, name=None, ignore_endmdl=False, skip_hetatm=False):
+        """Line-by-line Python restatement of the same loader (test reference for the
+        native parser; `Atom.loads` shares `_parse_atom_line`)."""
         lines = []
         for line in data.splitlines(keepends=True):
             if line.startswith(b"HEADER"):

@@ -72,6 +72,17 @@ class jb_query_params(C.Structure):
     ]
 
 
+class jb_pdb_info(C.Structure):
+    _fields_ = [
+        ("n_atoms", C.c_int64),
+        ("header_offset", C.c_int64),
+        ("header_length", C.c_int64),
+        ("stop_offset", C.c_int64),
+        ("mmcif_tags", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
 class jb_hits(C.Structure):
     _fields_ = [
         ("count", C.c_int64),

@@ -1,0 +1,79 @@
+"""Structure ingest: the native one-pass PDB parser `jb_pdb_parse`
+(csrc/ingest.cu, host code of the engine library -- needs no GPU) against the line-by-line
+Python restatement of PDBMoleculeParser.load + Atom_parse, and against the atoms the
+REFERENCE parsed (tests/golden/cfg2_structures.npz was written by the reference's loader)."""
+import io
+import os
+
+import numpy as np
+import pytest
+
+from _util import DATA, cfg2_molecules
+from pyjess_b200 import Molecule
+from pyjess_b200._model import ATOM_DTYPE
+
+FILES = ["1AMY.pdb", "pdb1lnb.ent", "pdb1a0p.ent", "5ayx.EF.pdb"]
+
+
+def both(data: bytes, **kw):
+    native = Molecule.loads(data, **kw)
+    python = Molecule._parse_pdb_python(data, **kw)
+    return native, python
+
+
+@pytest.mark.parametrize("name", FILES)
+def test_native_parser_is_byte_identical_on_fixtures(name):
+    with open(os.path.join(DATA, name), "rb") as f:
+        data = f.read()
+    for kw in ({}, {"skip_hetatm": True}, {"ignore_endmdl": True}):
+        a, b = both(data, **kw)
+        assert len(a) == len(b) > 0
+        assert a._atoms.tobytes() == b._atoms.tobytes()
+        assert (a.id, a.name, a.date) == (b.id, b.name, b.date)
+
+
+def test_native_parser_matches_reference_parsed_atoms():
+    ref = {m.id.upper(): m for m in cfg2_molecules()}
+    for name, key in (("pdb1a0p.ent", "1A0P"), ("pdb1lnb.ent", "1LNB")):
+        ours, theirs = Molecule.load(os.path.join(DATA, name)), ref[key]
+        assert len(ours) == len(theirs)
+        for field in ("x", "serial", "name", "resName", "resSeq", "chainID1", "chainID2"):
+            assert np.array_equal(ours._atoms[field], theirs._atoms[field]), field
+
+
+ODD_LINES = [
+    b"ATOM      1  N   MET A   1      27.340  24.430   2.614  1.00  9.67           N  \n",
+    b"ATOM      2  CA  MET A   1      26.266  25.413   2.842  1.00 10.38           C1+\r\n",     # CRLF + charge
+    b"HETATM    3 ZN    ZN A 317      1.5e1   -.5     +3.     0.50 20.00      SEG1ZN\n",       # exponent, bare dot
+    b"ATOM      4  CB  MET\n",                                                                    # short line
+    b"ATOM  \n",
+    b"ATOM",                                                                                      # no newline at EOF
+]
+
+
+def test_native_parser_semantics_on_odd_lines():
+    data = b"HEADER    HYDROLASE                               01-JAN-99   1ABC\n" + b"".join(ODD_LINES[:-1]) + \
+           b"REMARK nothing\nATOM      5  C   GLY B  22A   -100.123-200.456 300.789\n" \
+           b"ATOM  12345678901234567890\n" \
+           b"ATOM      6  O\tGLY\tB\t 23      1.0     2.0     3.0\n" \
+           b"ATOM      7  X\x00 GLY B  24      1.0     2.0     3.0\n" \
+           b"ATOM      8  C   GLY B  25  1234567.12345678901234567 0x1p3  nan  inf\n" \
+           b"ENDMDL\nATOM      9  N   ALA A   2       0.0     0.0     0.0\n" + ODD_LINES[-1]
+    for kw in ({}, {"skip_hetatm": True}, {"ignore_endmdl": True}):
+        a, b = both(data, **kw)
+        assert len(a) == len(b)
+        for field in ATOM_DTYPE.names:
+            x, y = a._atoms[field], b._atoms[field]
+            same = np.array_equal(x, y, equal_nan=True) if x.dtype.kind == "f" else np.array_equal(x, y)
+            assert same, (kw, field, x, y)
+        assert (a.id, a.name, a.date) == (b.id, b.name, b.date) == ("1ABC", "HYDROLASE", a.date)
+    full = Molecule.loads(data, ignore_endmdl=True)
+    assert len(full) == len(Molecule.loads(data)) + 2
+
+
+def test_native_parser_rejects_mmcif_and_handles_empty():
+    with pytest.raises(ValueError):
+        Molecule.loads(b"data_1ABC\nloop_\n_atom_site.id\n")
+    assert len(Molecule.loads(b"")) == 0
+    assert len(Molecule.load(io.BytesIO(b"REMARK only\n"))) == 0
+    assert len(Molecule.load(io.StringIO("ATOM      1  N   MET A   1      27.340  24.430   2.614\n"))) == 1
