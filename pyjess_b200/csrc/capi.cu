@@ -116,7 +116,7 @@ struct jb_context {
     int legacy = 0;               // JB_LEGACY: run-time-level k_expand at every level (A/B comparisons)
     cudaEvent_t lev[kMaxN + 1] = {};
     // workspace (grow only)
-    DevBuf crec, chead, recs, ordbuf, fr[2], tuples, ctr;
+    DevBuf crec, chead, cxtab, recs, ordbuf, fr[2], tuples, ctr;
     DevBuf h_mol, h_tpl, h_atoms, h_rmsd, h_rot, h_c0, h_c1;   // hits as k_superpose appends them
     DevBuf f_mol, f_tpl, f_atoms, f_rmsd, f_rot, f_c0, f_c1;   // ... in canonical order (hits.cuh)
     DevBuf o_off, o_fill, o_grouped, o_order, o_tiles, o_runs, o_work;   // ordering workspace
@@ -223,7 +223,7 @@ extern "C" void jb_context_destroy(jb_context *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = { &c->crec, &c->chead, &c->recs, &c->ordbuf, &c->fr[0], &c->fr[1],
+    DevBuf *bufs[] = { &c->crec, &c->chead, &c->cxtab, &c->recs, &c->ordbuf, &c->fr[0], &c->fr[1],
                        &c->tuples, &c->ctr, &c->h_mol, &c->h_tpl, &c->h_atoms, &c->h_rmsd, &c->h_rot, &c->h_c0,
                        &c->h_c1, &c->f_mol, &c->f_tpl, &c->f_atoms, &c->f_rmsd, &c->f_rot, &c->f_c0, &c->f_c1,
                        &c->o_off, &c->o_fill, &c->o_grouped, &c->o_order, &c->o_tiles, &c->o_runs, &c->o_work,
@@ -696,6 +696,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         const int Mc = r.m1 - r.m0;
         const long long pairs = (long long)Mc * t->T;
         CU(c->chead.ensure((size_t)Mc * t->S * sizeof(CandHead), st));
+        CU(c->cxtab.ensure((size_t)Mc * t->S * kXBuckets * sizeof(unsigned short), st));
         CU(c->recs.ensure((size_t)pairs * sizeof(PairRec), st));
         if (c->crec.bytes == 0) {
             const long long chunk_atoms = mol->atom_off[r.m1] - mol->atom_off[r.m0];
@@ -709,7 +710,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         MT.sname = mol->sname.as<uint32_t>(); MT.sres = mol->sres.as<uint32_t>();
         MT.ext = mol->ext.as<MolExt>() + r.m0;
         CandTable CT;
-        CT.head = c->chead.as<CandHead>(); CT.rec = c->crec.as<float4>();
+        CT.head = c->chead.as<CandHead>(); CT.rec = c->crec.as<float4>(); CT.xtab = c->cxtab.as<unsigned short>();
         CT.cap = (long long)(c->crec.bytes / sizeof(float4));
         Counters *dc = c->ctr.as<Counters>();
 
@@ -720,6 +721,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
 
         CU(cudaEventRecord(c->evs[0], st));
         k_classify<<<Mc, 256, classify_smem, st>>>(MT, ST, CT, dc);
+        k_xindex<<<(unsigned)(((long long)Mc * t->S * 32 + 255) / 256), 256, 0, st>>>((long long)Mc * t->S, CT);
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->evs[1], st));
         if (q->reorder == 2) {
@@ -740,7 +742,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
             ExpandArgs A;
             A.level = l; A.n_specs = t->S; A.tuple_stride = tuple_stride; A.ignore_chain = q->ignore_chain;
             A.recs = c->recs.as<PairRec>(); A.shell = TT.shell; A.atoms = MT.atoms; A.ext = MT.ext;
-            A.head = CT.head; A.cand = CT.rec;
+            A.head = CT.head; A.xtab = CT.xtab; A.cand = CT.rec;
             A.in = l == 0 ? nullptr : c->fr[(l - 1) & 1].as<int>();
             A.in_count = l == 0 ? &dc->live_pairs : &dc->level[l];
             A.in_cap = l == 0 ? pairs : fr_ints[(l - 1) & 1] / (l + 1);
@@ -798,7 +800,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
                         l == 0 ? hc.live_pairs : hc.level[l], hc.level[l + 1], ms);
             }
         }
-        S.launches += 3 + t->nmax;
+        S.launches += 4 + t->nmax;
         {
             float ms[4] = { 0, 0, 0, 0 };
             for (int i = 0; i < 4; i++) CU(cudaEventElapsedTime(&ms[i], c->evs[i], c->evs[i + 1]));

@@ -9,13 +9,17 @@
 // emission -- specialised on the level L (atoms already placed) with
 //
 //   * all strides/offsets compile-time, loops over the placed atoms unrolled;
-//   * BOTH x bounds of the join box located by binary search in the x-sorted
-//     candidate list (the k-d tree walk of eff:KdTree.c:238-296 becomes two
-//     searches), so that every partial match owns an exact record range;
-//   * a LOAD-BALANCED scan: the ranges of a batch are cut into chunks of kChunk
-//     records, the chunks are numbered by a warp prefix sum and dealt to the 32
-//     lanes whatever partial match they belong to (the owner is found by a
-//     branch-free binary search over the chunk offsets in shared memory).
+//   * BOTH x bounds of the join box located through the list's x-bucket index
+//     (k_xindex: two independent 2-byte loads instead of two chains of 5-6 dependent
+//     probes; a short binary search only refines buckets holding > 4 records), so
+//     that every partial match owns a record range (the k-d tree walk of
+//     eff:KdTree.c:238-296 becomes a range);
+//   * a LOAD-BALANCED, COALESCED scan: the ranges of a batch are cut into chunks of
+//     kChunk records, numbered by a warp prefix sum and dealt to QUADS of lanes
+//     whatever partial match they belong to (owner found by a branch-free binary
+//     search over the chunk offsets in shared memory).  A quad reads 64 contiguous
+//     bytes per load instruction: profiles/r1t showed the lane-per-chunk layout
+//     (32 different lines per LDG) saturating the L1 data stage at 90-93 %.
 //
 // Reference semantics are untouched: the decision is still _Annulus_po in FP64
 // with explicit RN operations (eff:Annulus.h:54-68) plus TessTemplate_check
@@ -27,8 +31,9 @@
 namespace jb {
 
 constexpr int kMaxLv = 8;        // levels 1..kMaxLv have a specialisation; deeper levels use k_expand
-constexpr int kChunk = 4;        // records per scan chunk (64 bytes: two sectors)
-constexpr int kQueueLv = 160;    // survivor queue: < 32 carried + kChunk x 32 new
+constexpr int kChunk = 8;        // records per scan chunk, read by a QUAD of lanes (two 64-byte pieces)
+constexpr int kQuad = 4;         // lanes per chunk: one LDG.128 of a quad covers 64 contiguous bytes
+constexpr int kQueueLv = 96;     // survivor queue: < 32 carried + 64 new per scan iteration
 
 template <int L, int G> struct alignas(16) LvWarp {   // per-warp shared memory
     static constexpr int IPW = 32 / G;                // partial matches per batch
@@ -146,7 +151,8 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_lv(const ExpandArg
         const long long item = base_item + grp;
         const bool valid = item < (long long)n_in;
         int cnt = 0;
-        long long coff = 0;
+        long long coff = 0, lidx = 0;
+        float hx0 = 0.f, hinv = 0.f;
         float bx0 = -INF, by0 = -INF, bz0 = -INF, bx1 = INF, by1 = INF, bz1 = INF;
         if (valid) {
             const int *it = A.in + item * in_stride;
@@ -156,9 +162,11 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_lv(const ExpandArg
             const longlong2 h1 = *reinterpret_cast<const longlong2 *>(&rec->abase);
             const int n = h0.w;
             const int k = rec->order[L];
-            const CandHead hd = A.head[(long long)h0.x * A.n_specs + rec->spec[L]];
+            lidx = (long long)h0.x * A.n_specs + rec->spec[L];
+            const CandHead hd = A.head[lidx];
             cnt = hd.cnt;
             coff = hd.off;
+            hx0 = hd.x0; hinv = hd.inv_w;
             if (gl == 0) {
                 W.meta[grp] = make_int2(lp, (L + 1 == n) ? 1 : 0);
                 W.abase[grp] = h1.x;
@@ -200,35 +208,37 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_lv(const ExpandArg
         // ---- x range of the box in the x-sorted list: two binary searches, stopped at a span
         //      of two records (the scan re-tests x, so a slightly wide range is harmless)
         int lo = 0, hi = cnt;
-        const bool narrow = boxed && cnt > 2 * kChunk;
-        if (G == 1) {
-            int l0 = 0, l1 = cnt, u0 = 0, u1 = cnt;
-            while (__any_sync(FULL, narrow && (l1 - l0 > 2 || u1 - u0 > 2))) {
-                const bool al = narrow && l1 - l0 > 2, au = narrow && u1 - u0 > 2;
-                const int ml = (l0 + l1) >> 1, mu = (u0 + u1) >> 1;
-                float xl = 0.f, xu = 0.f;
-                if (al) xl = __ldg(&A.cand[coff + ml].x);
-                if (au) xu = __ldg(&A.cand[coff + mu].x);
-                if (al) { if (xl < bx0) l0 = ml + 1; else l1 = ml; }
-                if (au) { if (xu <= bx1) u0 = mu + 1; else u1 = mu; }
+        const bool narrow = boxed && cnt > 2 * kChunk && cnt <= 65535;
+        {
+            // searcher s of the group: s == 0 first record with x >= bx0, s == 1 first record with x > bx1
+            // (G == 1: the lane runs both searches one after the other)
+            const unsigned short *tab = A.xtab + ((long long)lidx) * kXBuckets;
+#pragma unroll
+            for (int pass = 0; pass < (G == 1 ? 2 : 1); pass++) {
+                const int which = G == 1 ? pass : gl;
+                const bool searcher = narrow && which < 2;
+                const float key = which == 0 ? bx0 : bx1;
+                int s0 = 0, s1 = cnt;
+                if (searcher) {
+                    const int b = x_bucket(key, hx0, hinv);
+                    s0 = min((int)tab[b], cnt);
+                    s1 = b == kXBuckets - 1 ? cnt : min(max((int)tab[b + 1], s0), cnt);   // clamped: the table
+                }                                                   // is undefined while a chunk is re-run larger
+                while (__any_sync(FULL, searcher && s1 - s0 > 4)) {
+                    const bool act = searcher && s1 - s0 > 4;
+                    const int mid = (s0 + s1) >> 1;
+                    float x = 0.f;
+                    if (act) x = __ldg(&A.cand[coff + mid].x);
+                    const bool below = which == 0 ? (x < key) : (x <= key);
+                    if (act) { if (below) s0 = mid + 1; else s1 = mid; }
+                }
+                if (G == 1) { if (narrow) { if (pass == 0) lo = s0; else hi = s1; } }
+                else {
+                    const int l0 = __shfl_sync(FULL, s0, lane - gl);
+                    const int u1 = __shfl_sync(FULL, s1, lane - gl + 1);
+                    if (narrow) { lo = l0; hi = u1; }
+                }
             }
-            if (narrow) { lo = l0; hi = u1; }
-        } else {
-            // lane 0 of the group: first record with x >= bx0; lane 1: first record with x > bx1
-            int s0 = 0, s1 = cnt;
-            const bool searcher = narrow && gl < 2;
-            const float key = gl == 0 ? bx0 : bx1;
-            while (__any_sync(FULL, searcher && s1 - s0 > 2)) {
-                const bool act = searcher && s1 - s0 > 2;
-                const int mid = (s0 + s1) >> 1;
-                float x = 0.f;
-                if (act) x = __ldg(&A.cand[coff + mid].x);
-                const bool below = gl == 0 ? (x < key) : (x <= key);
-                if (act) { if (below) s0 = mid + 1; else s1 = mid; }
-            }
-            const int l0 = __shfl_sync(FULL, s0, lane - gl);
-            const int u1 = __shfl_sync(FULL, s1, lane - gl + 1);
-            if (narrow) { lo = l0; hi = u1; }
         }
         // ---- chunk numbering: exclusive prefix sum of the chunk counts over the batch ----------
         const int len = boxed ? max(hi - lo, 0) : 0;
@@ -250,8 +260,8 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_lv(const ExpandArg
         }
         __syncwarp();
         // ---- load-balanced scan: lane <- chunk, whatever partial match owns it ------------------
-        for (int cb = 0; cb < total; cb += 32) {
-            const int ch = cb + lane;
+        for (int cb = 0; cb < total; cb += 32 / kQuad) {
+            const int ch = cb + (lane >> 2), sub = lane & (kQuad - 1);
             const bool act = ch < total;
             int g = 0;
 #pragma unroll
@@ -260,37 +270,39 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_lv(const ExpandArg
             const int k0 = (ch - W.cstart[g]) * kChunk;
             const int rem = act ? W.clen[g] - k0 : 0;          // records left from the chunk start
             const float4 *src = A.cand + W.cbase[g] + k0;
-            float4 r[kChunk];
+            constexpr int NR = kChunk / kQuad;                 // records per lane
+            float4 r[NR];
 #pragma unroll
-            for (int i = 0; i < kChunk; i++) {
+            for (int i = 0; i < NR; i++) {
                 r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i < rem) r[i] = __ldg(src + i);
+                if (sub + kQuad * i < rem) r[i] = __ldg(src + sub + kQuad * i);
             }
             const float4 b0 = W.blo[g], b1 = W.bhi[g];
-            bool ok[kChunk];
-            unsigned m[kChunk], many = 0;
+            bool ok[NR];
+            unsigned m[NR], many = 0;
 #pragma unroll
-            for (int i = 0; i < kChunk; i++) {
-                ok[i] = i < rem && r[i].x >= b0.x && r[i].x <= b1.x && r[i].y >= b0.y && r[i].y <= b1.y &&
+            for (int i = 0; i < NR; i++) {
+                ok[i] = sub + kQuad * i < rem && r[i].x >= b0.x && r[i].x <= b1.x && r[i].y >= b0.y && r[i].y <= b1.y &&
                         r[i].z >= b0.z && r[i].z <= b1.z;
                 m[i] = __ballot_sync(FULL, ok[i]);
                 many |= m[i];
             }
             if (stats) {
-                const int tested = min(max(rem, 0), kChunk);
-                int tsum = tested;
+                int tsum = 0;
+#pragma unroll
+                for (int i = 0; i < NR; i++) tsum += (sub + kQuad * i < rem) ? 1 : 0;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) tsum += __shfl_down_sync(FULL, tsum, o);
                 if (lane == 0) {
                     n_scan += (unsigned)tsum;
 #pragma unroll
-                    for (int i = 0; i < kChunk; i++) n_box += __popc(m[i]);
+                    for (int i = 0; i < NR; i++) n_box += __popc(m[i]);
                 }
             }
             if (many) {
                 int pos = qfill;
 #pragma unroll
-                for (int i = 0; i < kChunk; i++) {
+                for (int i = 0; i < NR; i++) {
                     if (ok[i]) W.queue[pos + __popc(m[i] & lt)] = make_int2(__float_as_int(r[i].w), g);
                     pos += __popc(m[i]);
                 }

@@ -87,14 +87,26 @@ struct MolTable {
     const MolExt *ext;         // [M] chunk view
 };
 
-struct alignas(16) CandHead {  // one candidate list = one (structure, spec)
+constexpr int kXBuckets = 32;  // x-bucket index of a candidate list (k_xindex)
+
+struct alignas(32) CandHead {  // one candidate list = one (structure, spec): one sector
     long long off;
     int cnt;
-    int pad;
+    float x0;                  // x of the first (smallest-x) record
+    float inv_w;               // kXBuckets / (x range of the list); 0: a single bucket
+    int pad[3];
 };
+
+// bucket of an x coordinate: monotone non-decreasing in x (no FMA: the TU is built with
+// -fmad=false, and k_xindex and the scans call this very function)
+__device__ __forceinline__ int x_bucket(float x, float x0, float inv_w)
+{
+    return (int)fminf(fmaxf((x - x0) * inv_w, 0.f), (float)(kXBuckets - 1));
+}
 
 struct CandTable {
     CandHead *head;            // [M*S]
+    unsigned short *xtab;      // [M*S][kXBuckets]: first record whose x bucket is >= b (lists <= 65535 records)
     float4 *rec;               // x-sorted copies of srec entries: FP32 is ONLY a conservative prefilter
     long long cap;             // capacity (records)
 };
@@ -364,13 +376,42 @@ __global__ void __launch_bounds__(256) k_classify(MolTable M, SpecTable S, CandT
                     sh_cnt[v * ns + s] = run;
                     run += c;
                 }
-                CandHead h; h.off = 0; h.cnt = run; h.pad = 0;
+                CandHead h; h.off = 0; h.cnt = run; h.x0 = 0.f; h.inv_w = 0.f; h.pad[0] = h.pad[1] = h.pad[2] = 0;
                 if (run > 0) h.off = (long long)atomicAdd(&ctr->cand_total, (u64)run);
                 C.head[(long long)m * ns + s] = h;
             }
             __syncthreads();
         }
     }
+}
+
+// ---- K1b: x-bucket index of every candidate list ---------------------------------------
+// The lists are x-sorted; the frontier sweep needs, per partial match, the record range whose
+// x lies inside the join box.  Instead of two binary searches (5-6 DEPENDENT scattered loads
+// each, 9 % of the sweep's stall samples in profiles/r1g) every list gets a table of
+// kXBuckets uniform x buckets: tab[b] = first record with bucket >= b.  One warp per list.
+__global__ void __launch_bounds__(256) k_xindex(long long n_lists, CandTable C)
+{
+    const long long L = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (L >= n_lists) return;
+    CandHead hd = C.head[L];
+    unsigned short *tab = C.xtab + L * kXBuckets;
+    if (hd.cnt <= 0 || hd.off + hd.cnt > C.cap) return;        // empty, or the chunk is being re-run larger
+    const float4 *rec = C.rec + hd.off;
+    const float x0 = rec[0].x, x1 = rec[hd.cnt - 1].x;
+    float inv_w = 0.f;
+    if (hd.cnt <= 65535 && x1 > x0) inv_w = (float)kXBuckets / (x1 - x0);
+    if (!(inv_w > 0.f) || !(inv_w < 3.0e38f)) inv_w = 0.f;      // NaN / overflow: one bucket
+    if (lane == 0) { hd.x0 = x0; hd.inv_w = inv_w; C.head[L] = hd; }
+    if (hd.cnt > 65535) return;                                // scans fall back to the whole list
+    for (int p = lane; p < hd.cnt; p += 32) {
+        const int b = x_bucket(rec[p].x, x0, inv_w);
+        const int bp = p > 0 ? x_bucket(rec[p - 1].x, x0, inv_w) : -1;
+        for (int q = bp + 1; q <= b; q++) tab[q] = (unsigned short)p;
+    }
+    const int bl = x_bucket(x1, x0, inv_w);
+    for (int q = bl + 1 + lane; q < kXBuckets; q += 32) tab[q] = (unsigned short)hd.cnt;
 }
 
 // ---- K: shell radii ------------------------------------------------------------
@@ -558,6 +599,7 @@ struct ExpandArgs {
     const AtomRec *atoms;
     const MolExt *ext;
     const CandHead *head;
+    const unsigned short *xtab;  // x-bucket index of the lists (k_xindex)
     const float4 *cand;
     const int *in;               // items [lp, a_0..a_{l-1}], stride l+1 (unused for l==0)
     const u64 *in_count;         // items available (may exceed in_cap after an overflow)
