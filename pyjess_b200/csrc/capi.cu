@@ -658,9 +658,14 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
     ST.res_off = t->s_roff.as<int>(); ST.res_up = t->s_rup.as<uint32_t>();
 
     const int tuple_stride = t->nmax + 1;
-    const size_t classify_smem = (size_t)8 * t->S * sizeof(int);
-    if (classify_smem > 200 * 1024 || t->S > 65535)
+    // k_classify: [warps][S] counters + (when it fits) the class set and its spec masks
+    const size_t cnt_bytes = ((size_t)8 * t->S + 1) / 2 * 2 * sizeof(int);
+    if (cnt_bytes > 200 * 1024 || t->S > 65535)
         return fail(JB_ERR_INVALID, "%d distinct atom specs exceed the classify kernel's shared memory", t->S);
+    int class_words = (t->S + 31) / 32;
+    size_t classify_smem = cnt_bytes + (size_t)kClassSlots * (sizeof(u64) + (size_t)class_words * sizeof(unsigned));
+    if (classify_smem > 200 * 1024) { class_words = 0; classify_smem = cnt_bytes; }
+    if (getenv("JB_CLASSIFY_PLAIN")) { class_words = 0; classify_smem = cnt_bytes; }
     if (classify_smem > 48 * 1024)
         CU(cudaFuncSetAttribute(k_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)classify_smem));
 
@@ -720,7 +725,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         CU(cudaMemcpyAsync(dc, c->host_ctr, sizeof(Counters), cudaMemcpyHostToDevice, st));
 
         CU(cudaEventRecord(c->evs[0], st));
-        k_classify<<<Mc, 256, classify_smem, st>>>(MT, ST, CT, dc);
+        k_classify<<<Mc, 256, classify_smem, st>>>(MT, ST, CT, dc, class_words);
         k_xindex<<<(unsigned)(((long long)Mc * t->S * 32 + 255) / 256), 256, 0, st>>>((long long)Mc * t->S, CT);
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->evs[1], st));
