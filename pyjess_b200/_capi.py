@@ -14,7 +14,7 @@ from ._tables import (HitTable, MoleculeBatch, TemplateTable, jb_hits, jb_molecu
                       jb_query_params, jb_stats, jb_template_table)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libjess_b200.so")
+LIB_PATH = os.environ.get("JB_LIB_PATH") or os.path.join(HERE, "libjess_b200.so")   # JB_LIB_PATH: A/B builds
 
 EXPORTS = [
     "jb_abi_version", "jb_last_error", "jb_device_count",

@@ -31,9 +31,12 @@
 namespace jb {
 
 constexpr int kMaxLv = 8;        // levels 1..kMaxLv have a specialisation; deeper levels use k_expand
-constexpr int kChunk = 8;        // records per scan chunk, read by a QUAD of lanes (two 64-byte pieces)
+#ifndef JB_CHUNK
+#define JB_CHUNK 16
+#endif
+constexpr int kChunk = JB_CHUNK; // records per scan chunk, read by a QUAD of lanes (64-byte pieces)
 constexpr int kQuad = 4;         // lanes per chunk: one LDG.128 of a quad covers 64 contiguous bytes
-constexpr int kQueueLv = 96;     // survivor queue: < 32 carried + 64 new per scan iteration
+constexpr int kQueueLv = 32 + 8 * kChunk;   // survivor queue: < 32 carried + 8 chunks new per scan iteration
 
 template <int L, int G> struct alignas(16) LvWarp {   // per-warp shared memory
     static constexpr int IPW = 32 / G;                // partial matches per batch

@@ -563,41 +563,61 @@ __global__ void __launch_bounds__(128) k_order(int n_mol, TemplateTable T, int n
     if (!live) return;
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
     const double V = __dmul_rn(19.0, (double)(atom_off[m + 1] - atom_off[m]));
+    // all fan-outs share the divisor V: candidates are compared by their NUMERATORS
+    // (|C_k| * 4.19) * vol and only the winner is divided (division by a positive constant is
+    // monotone, so min over quotients == quotient of the min numerator, bit for bit)
+    double c419[kMaxN];
+    for (int k = 0; k < n; k++) c419[k] = __dmul_rn((double)cnts[k], 4.19);
     int first = 0;
     double first_score = inf;
     for (int c = 0; c < n; c++) {
-        double mf = inf;
+        double mnum = inf;
         for (int k = 0; k < n; k++) {
             if (k == c || s_same[c * n + k]) continue;
-            const double f = __ddiv_rn(__dmul_rn(__dmul_rn((double)cnts[k], 4.19), s_vol[c * n + k]), V);
-            if (f < mf) mf = f;
+            const double num = __dmul_rn(c419[k], s_vol[c * n + k]);
+            if (num < mnum) mnum = num;
         }
-        if (mf == inf) mf = 1.0;
+        const double mf = mnum == inf ? 1.0 : __ddiv_rn(mnum, V);
         const double sc = __dmul_rn((double)cnts[c], __dadd_rn(1.0, mf));
         if (sc < first_score) { first_score = sc; first = c; }
     }
-    unsigned char *ord = ordbuf + ((long long)m * T.n_templates + t) * kMaxN;
+    alignas(16) unsigned char ord[kMaxN];
     double minv[kMaxN];
     unsigned used = 1u << first, same = 0;
-    for (int k = 0; k < n; k++) minv[k] = inf;
+    for (int k = 0; k < kMaxN; k++) { minv[k] = inf; ord[k] = 0; }
     ord[0] = (unsigned char)first;
     int last = first;
     for (int l = 1; l < n; l++) {
-        int best = -1;
-        double best_score = 0.0;
+        // best atom of each class: outside the placed residues by numerator, inside by 1e3 + |C_k|
+        int bn = -1, bs = -1;
+        double bnum = 0.0, bsf = 0.0;
         for (int k = 0; k < n; k++) {
             if (used & (1u << k)) continue;
             const double v = s_vol[last * n + k];
             if (v < minv[k]) minv[k] = v;
             if (s_same[last * n + k]) same |= 1u << k;
-            const double f = (same & (1u << k)) ? __dadd_rn(1e3, (double)cnts[k])
-                                                : __ddiv_rn(__dmul_rn(__dmul_rn((double)cnts[k], 4.19), minv[k]), V);
-            if (best < 0 || f < best_score) { best = k; best_score = f; }
+            if (same & (1u << k)) {
+                const double f = __dadd_rn(1e3, (double)cnts[k]);
+                if (bs < 0 || f < bsf) { bs = k; bsf = f; }
+            } else {
+                const double num = __dmul_rn(c419[k], minv[k]);
+                if (bn < 0 || num < bnum) { bn = k; bnum = num; }
+            }
+        }
+        int best;
+        if (bn < 0) best = bs;
+        else if (bs < 0) best = bn;
+        else {
+            const double fn = __ddiv_rn(bnum, V);
+            best = fn < bsf ? bn : (bsf < fn ? bs : min(bn, bs));
         }
         ord[l] = (unsigned char)best;
         used |= 1u << best;
         last = best;
     }
+    uint4 *dst = reinterpret_cast<uint4 *>(ordbuf + ((long long)m * T.n_templates + t) * kMaxN);
+    const uint4 *src = reinterpret_cast<const uint4 *>(ord);
+    dst[0] = src[0]; dst[1] = src[1];
 }
 
 // ---- K: pairs --------------------------------------------------------------------
@@ -659,13 +679,20 @@ __global__ void __launch_bounds__(256) k_pairs(int n_mol, TemplateTable T, int n
     base = __shfl_sync(0xffffffffu, base, 0);
     if (live) {
         PairRec *r = recs + base + __popc(mask & ((1u << lane) - 1));
-        r->m = m; r->t = t; r->ta0 = ta0; r->n = n;
-        r->abase = atom_off[m];
-        r->shell0 = T.dist_off[t];
+        // the 128-byte record leaves as eight 16-byte stores
+        alignas(16) unsigned short spc[kMaxN];
         for (int k = 0; k < kMaxN; k++) {
-            r->order[k] = k < n ? ord[k] : 0;
-            r->spec[k] = k < n ? (unsigned short)T.spec[ta0 + ord[k]] : 0;
+            if (k >= n) ord[k] = 0;
+            spc[k] = k < n ? (unsigned short)T.spec[ta0 + ord[k]] : (unsigned short)0;
         }
+        uint4 *dst = reinterpret_cast<uint4 *>(r);
+        const long long ab = atom_off[m], sh0 = T.dist_off[t];
+        dst[0] = make_uint4((unsigned)m, (unsigned)t, (unsigned)ta0, (unsigned)n);
+        dst[1] = make_uint4((unsigned)(u64)ab, (unsigned)((u64)ab >> 32), (unsigned)(u64)sh0, (unsigned)((u64)sh0 >> 32));
+        const uint4 *sp = reinterpret_cast<const uint4 *>(spc);
+        const uint4 *op = reinterpret_cast<const uint4 *>(ord);
+        dst[2] = sp[0]; dst[3] = sp[1]; dst[4] = sp[2]; dst[5] = sp[3];
+        dst[6] = op[0]; dst[7] = op[1];
     }
 }
 
