@@ -154,10 +154,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; invalid as a result)")
-    ap.add_argument("--cpu-structures", type=int, default=100, help="structures in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-structures", type=int, default=0,
+                    help="structures in the bounded CPU-baseline sample (0: per-workload default, ~10-20 s of "
+                         "host time at N=1; a third of it per step of --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.cpu_structures <= 0:
+        full = {"cfg3": 1000, "cfg3dense": 1000, "cfg4shard": 300, "cfg5": 60}.get(args.workload, 100)
+        args.cpu_structures = full if args.impl == "b200" else max(1, full // 3)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
