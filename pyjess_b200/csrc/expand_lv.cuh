@@ -35,6 +35,7 @@ constexpr int kMaxLv = 8;        // levels 1..kMaxLv have a specialisation; deep
 #define JB_CHUNK 16
 #endif
 constexpr int kChunk = JB_CHUNK; // records per scan chunk, read by a QUAD of lanes (64-byte pieces)
+constexpr int kOwnerCap = 128;   // batches of up to this many chunks get a direct chunk -> owner table
 constexpr int kQuad = 4;         // lanes per chunk: one LDG.128 of a quad covers 64 contiguous bytes
 constexpr int kQueueLv = 32 + 8 * kChunk;   // survivor queue: < 32 carried + 8 chunks new per scan iteration
 
@@ -48,6 +49,7 @@ template <int L, int G> struct alignas(16) LvWarp {   // per-warp shared memory
     int clen[IPW];                                    // records in the x range
     int cstart[IPW];                                  // first chunk of the partial match (exclusive scan)
     int2 queue[kQueueLv];                             // box survivors: (atom, partial match)
+    unsigned char owner[kOwnerCap];                   // chunk -> partial match of the batch (short batches)
     int chain_atom[IPW * L];
     int stage[kStageItems * (L + 2)];                 // accepted extensions awaiting the flush
 };
@@ -254,7 +256,10 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_lv(const ExpandArg
             if (lane >= o) inc += t;
         }
         const int total = __shfl_sync(FULL, inc, 31);
+        const bool mapped = total <= kOwnerCap;            // warp uniform
         if (gl == 0) {
+            if (mapped)
+                for (int c = 0; c < nch; c++) W.owner[inc - mine + c] = (unsigned char)grp;
             W.cstart[grp] = inc - mine;
             W.clen[grp] = len;
             W.cbase[grp] = coff + lo;
@@ -267,9 +272,13 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_lv(const ExpandArg
             const int ch = cb + (lane >> 2), sub = lane & (kQuad - 1);
             const bool act = ch < total;
             int g = 0;
+            if (mapped) {
+                g = act ? (int)W.owner[ch] : 0;
+            } else {
 #pragma unroll
-            for (int s = IPW / 2; s > 0; s >>= 1)
-                if (W.cstart[g + s] <= ch) g += s;
+                for (int s = IPW / 2; s > 0; s >>= 1)
+                    if (W.cstart[g + s] <= ch) g += s;
+            }
             const int k0 = (ch - W.cstart[g]) * kChunk;
             const int rem = act ? W.clen[g] - k0 : 0;          // records left from the chunk start
             const float4 *src = A.cand + W.cbase[g] + k0;
