@@ -270,6 +270,13 @@ typedef struct jb_pdb_info {
 int jb_pdb_parse(const char *text, int64_t n_bytes, int32_t flags,
                  jb_atom_record *records, int64_t capacity, jb_pdb_info *info);
 
+/* ---- hit output (HOST code): the per-atom sprintf loop of Hit.dump
+ * (src/pyjess/_jess.pyx:2589-2620) for n records at once.  `xyz` (n*3, may be
+ * NULL) overrides the coordinates (the transformed ones).  Needs 96 bytes of
+ * `out` per record; returns the bytes written or a negative jb_status.        */
+int64_t jb_format_atoms_pdb(const jb_atom_record *atoms, int64_t n,
+                            const double *xyz, char *out, int64_t capacity);
+
 #ifdef __cplusplus
 }
 #endif

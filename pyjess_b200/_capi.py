@@ -22,7 +22,7 @@ EXPORTS = [
     "jb_templates_create", "jb_templates_free", "jb_templates_spec_count",
     "jb_molecules_upload", "jb_molecules_free",
     "jb_query_run", "jb_result_fetch", "jb_result_stats", "jb_result_free", "jb_query_host",
-    "jb_pdb_parse",
+    "jb_pdb_parse", "jb_format_atoms_pdb",
 ]
 
 _lib = None
@@ -67,6 +67,7 @@ def load_library():
                 "jb_result_free": (None, [vp]),
                 "jb_query_host": (i32, [vp, vp, P(jb_molecule_batch), P(jb_query_params), P(vp), P(jb_hits)]),
                 "jb_pdb_parse": (i32, [C.c_char_p, i64, i32, vp, i64, P(jb_pdb_info)]),
+                "jb_format_atoms_pdb": (i64, [vp, i64, vp, vp, i64]),
             }
             for name, (res, args) in sig.items():
                 fn = getattr(lib, name)
@@ -198,6 +199,31 @@ def pdb_parse(data: bytes, records, skip_hetatm: bool = False, ignore_endmdl: bo
     if rc not in (0, -4):
         _check(rc)
     return info
+
+
+_fmt_buf = None
+
+
+def format_atoms_pdb(records, xyz=None) -> str:
+    """ATOM lines of a block of atom records (`jb_format_atoms_pdb`): the sprintf loop of
+    Hit.dump.  `records`: C-contiguous `ATOM_DTYPE` array; `xyz`: C-contiguous float64 (n, 3)."""
+    global _fmt_buf
+    lib = _lib or load_library()
+    n = len(records)
+    if _fmt_buf is None or len(_fmt_buf) < 96 * n + 1:
+        _fmt_buf = C.create_string_buffer(max(96 * n + 1, 1 << 14))
+    buf = _fmt_buf
+    if not records.flags.c_contiguous:
+        records = records.copy()
+    xp = None
+    if xyz is not None:
+        if not (xyz.flags.c_contiguous and xyz.dtype.str == "<f8"):
+            xyz = xyz.astype("<f8", order="C")
+        xp = xyz.ctypes.data
+    got = lib.jb_format_atoms_pdb(records.ctypes.data, n, xp, buf, len(buf))
+    if got < 0:
+        _check(int(got))
+    return buf.raw[:got].decode("ascii", "replace") if got > (1 << 12) else buf.value.decode("ascii", "replace")
 
 
 _default = {}

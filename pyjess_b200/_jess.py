@@ -34,9 +34,33 @@ __all__ = ["Jess", "Query", "Hit"]
 
 
 class Hit:
-    """One (template, atom tuple) match with its superposition (_jess.pyx:2286-2621)."""
+    """One (template, atom tuple) match with its superposition (_jess.pyx:2286-2621).
 
-    __slots__ = ("rmsd", "_rotation", "_centre", "_atoms", "_template", "_molecule")
+    A hit produced by a query is a lazy VIEW of one record of the engine's hit table: the
+    atom records, the rotation and the centroids are only cut out of the table when they are
+    first read, so iterating a query costs ~1 us per hit instead of a handful of numpy
+    copies."""
+
+    __slots__ = ("rmsd", "_rot", "_cen", "_at", "_template", "_molecule", "_table", "_row")
+
+    @property
+    def _rotation(self):
+        if self._rot is None:
+            self._rot = self._table.rotation[self._row].copy()
+        return self._rot
+
+    @property
+    def _centre(self):
+        if self._cen is None:
+            self._cen = np.stack([self._table.centre0[self._row], self._table.centre1[self._row]])
+        return self._cen
+
+    @property
+    def _atoms(self):
+        if self._at is None:
+            n = len(self._template)
+            self._at = self._molecule._atoms[self._table.atoms[self._row, :n]]      # fancy index: a copy
+        return self._at
 
     def __getstate__(self):
         return {
@@ -52,12 +76,13 @@ class Hit:
         self.rmsd = state["rmsd"]
         self._template = state["template"]
         self._molecule = state["molecule"]
-        self._rotation = np.asarray(state["rotation"], dtype=np.float64).reshape(3, 3)
-        self._centre = np.asarray(state["centre"], dtype=np.float64).reshape(2, 3)
+        self._table, self._row = None, -1
+        self._rot = np.asarray(state["rotation"], dtype=np.float64).reshape(3, 3)
+        self._cen = np.asarray(state["centre"], dtype=np.float64).reshape(2, 3)
         atoms = state["atoms"]
         if len(atoms) != len(self._template):
             raise ValueError(f"unexpected number of atoms: {len(atoms)!r} (expected {len(self._template)!r})")
-        self._atoms = np.concatenate([a._rec for a in atoms]) if atoms else np.zeros(0, dtype=self._molecule._atoms.dtype)
+        self._at = np.concatenate([a._rec for a in atoms]) if atoms else np.zeros(0, dtype=self._molecule._atoms.dtype)
 
     def __reduce__(self):
         return _rebuild_hit, (self.__getstate__(),)
@@ -129,11 +154,9 @@ class Hit:
         file.write(f" {self.rmsd:5.3f} ")
         file.write(self._template.id)
         file.write(f" Det={self.determinant:4,.1f} log(E)~ {self.log_evalue:4.2f}\n")
-        xyz = self._atoms["x"]
-        if transform:
-            xyz = _transform_points(xyz.copy(), np.asarray(self.transformation))
-        for k in range(len(self._atoms)):
-            file.write(_format_atom(self._atoms[k], xyz[k]))
+        from . import _capi
+        xyz = _transform_points(self._atoms["x"].copy(), np.asarray(self.transformation)) if transform else None
+        file.write(_capi.format_atoms_pdb(self._atoms, xyz))          # the per-atom sprintf loop, natively
         file.write("ENDMDL\n")
 
 
@@ -190,17 +213,13 @@ class _BatchRun:
             first = np.ones(t.count, dtype=bool)
             first[1:] = (t.molecule[1:] != t.molecule[:-1]) | (t.template[1:] != t.template[:-1])
             keep = ~(first & single[t.template])
-        # iteration order per structure: template DESCENDING (reverse insertion), engine order within
-        slices = []
-        bounds = np.searchsorted(t.molecule, np.arange(len(mols) + 1))
-        for m in range(len(mols)):
-            idx = np.arange(bounds[m], bounds[m + 1])
-            if keep is not None:
-                idx = idx[keep[idx]]
-            if len(idx):
-                idx = idx[np.argsort(-t.template[idx], kind="stable")]
-            slices.append(idx)
-        self._slices = slices
+        # iteration order per structure: template DESCENDING (reverse insertion), engine order within;
+        # one stable sort for the whole batch, the per-structure slices are views of it
+        rows = np.arange(t.count, dtype=np.int64) if keep is None else np.nonzero(keep)[0]
+        mol, tpl = t.molecule[rows], t.template[rows]
+        rows = rows[np.lexsort((-tpl.astype(np.int64), mol))]
+        bounds = np.searchsorted(t.molecule[rows], np.arange(len(mols) + 1))
+        self._slices = [rows[bounds[m]:bounds[m + 1]] for m in range(len(mols))]
 
     def indices(self, m: int) -> np.ndarray:
         self.run()
@@ -318,15 +337,11 @@ class Query:
 
     def _make_hit(self, i: int) -> Hit:
         t = self._run.table
-        tpl_index = int(t.template[i])
-        template = self._jess._templates[tpl_index]
-        n = len(template)
         hit = Hit.__new__(Hit)
         hit.rmsd = float(t.rmsd[i])
-        hit._rotation = t.rotation[i].copy()
-        hit._centre = np.stack([t.centre0[i], t.centre1[i]])
-        hit._atoms = self._molecule._atoms[t.atoms[i, :n]].copy()
-        hit._template = template
+        hit._rot = hit._cen = hit._at = None
+        hit._table, hit._row = t, i
+        hit._template = self._jess._templates[t.template[i]]
         hit._molecule = self._molecule
         return hit
 

@@ -9,6 +9,7 @@
 // C atoi/atof PREFIX parsing from the field's first column, fields beyond the end of the
 // line keep their zero value, tokens copied with blanks/NULs turned into '_'.
 #include <cctype>
+#include <cstdio>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -144,4 +145,35 @@ extern "C" int jb_pdb_parse(const char *text, int64_t n_bytes, int32_t flags, jb
     info->n_atoms = n_atoms;
     info->stop_offset = pos;
     return n_atoms > capacity ? JB_ERR_CAPACITY : JB_OK;
+}
+
+// ---- output: ATOM lines of a hit ---------------------------------------------------------
+// Hit.dump (src/pyjess/_jess.pyx:2541-2621) writes one sprintf'd line per matched atom; this
+// is that loop for a whole block of records (decode_token :141-148: '_' and NUL -> ' ').
+static inline void decode_token(char *d, const char *s, int n)
+{
+    for (int i = 0; i < n; i++) d[i] = (s[i] == '_' || s[i] == 0) ? ' ' : s[i];
+    d[n] = 0;
+}
+
+extern "C" int64_t jb_format_atoms_pdb(const jb_atom_record *atoms, int64_t n, const double *xyz, char *out,
+                                       int64_t capacity)
+{
+    if (!atoms || !out || n < 0) return JB_ERR_INVALID;
+    int64_t pos = 0;
+    char name[5], res[4], elem[3];
+    for (int64_t k = 0; k < n; k++) {
+        const jb_atom_record *a = &atoms[k];
+        if (capacity - pos < 96) return JB_ERR_CAPACITY;
+        decode_token(name, a->name, 4);
+        decode_token(res, a->res_name, 3);
+        decode_token(elem, a->element, 2);
+        const double *x = xyz ? xyz + 3 * k : a->x;
+        pos += snprintf(out + pos, (size_t)(capacity - pos),
+                        "ATOM  %5i%5s%c%-3s%c%c%4i%-4c%8.3f%8.3f%8.3f%6.2f%6.2f          %2s\n", a->serial, name,
+                        a->alt_loc ? a->alt_loc : ' ', res, a->chain_id1 ? a->chain_id1 : ' ',
+                        a->chain_id2 ? a->chain_id2 : ' ', a->res_seq, a->i_code ? a->i_code : ' ', x[0], x[1], x[2],
+                        (double)a->occupancy, (double)a->temp_factor, elem);
+    }
+    return pos;
 }
