@@ -270,6 +270,15 @@ typedef struct jb_pdb_info {
 int jb_pdb_parse(const char *text, int64_t n_bytes, int32_t flags,
                  jb_atom_record *records, int64_t capacity, jb_pdb_info *info);
 
+/* ---- packing (HOST code): the per-molecule _Atom arrays of M Molecules -> the
+ * SoA staging image of jb_molecule_batch (what Molecule.__init__,
+ * src/pyjess/_jess.pyx:632-684, hands to the C library one struct at a time).
+ * Output arrays hold sum(counts) entries (atom_offset: M+1); serial may be NULL. */
+int jb_molecules_pack(const jb_atom_record *const *molecules, const int64_t *counts,
+                      int32_t n_molecules, int64_t *atom_offset, double *x, double *y,
+                      double *z, uint32_t *name, uint32_t *residue_name,
+                      int32_t *residue_number, uint8_t *chain_id2, int32_t *serial);
+
 /* ---- hit output (HOST code): the per-atom sprintf loop of Hit.dump
  * (src/pyjess/_jess.pyx:2589-2620) for n records at once.  `xyz` (n*3, may be
  * NULL) overrides the coordinates (the transformed ones).  Needs 96 bytes of

@@ -22,7 +22,7 @@ EXPORTS = [
     "jb_templates_create", "jb_templates_free", "jb_templates_spec_count",
     "jb_molecules_upload", "jb_molecules_free",
     "jb_query_run", "jb_result_fetch", "jb_result_stats", "jb_result_free", "jb_query_host",
-    "jb_pdb_parse", "jb_format_atoms_pdb",
+    "jb_pdb_parse", "jb_format_atoms_pdb", "jb_molecules_pack",
 ]
 
 _lib = None
@@ -68,6 +68,7 @@ def load_library():
                 "jb_query_host": (i32, [vp, vp, P(jb_molecule_batch), P(jb_query_params), P(vp), P(jb_hits)]),
                 "jb_pdb_parse": (i32, [C.c_char_p, i64, i32, vp, i64, P(jb_pdb_info)]),
                 "jb_format_atoms_pdb": (i64, [vp, i64, vp, vp, i64]),
+                "jb_molecules_pack": (i32, [vp, vp, i32] + [vp] * 9),
             }
             for name, (res, args) in sig.items():
                 fn = getattr(lib, name)
@@ -89,6 +90,10 @@ class Context:
         self._h = C.c_void_p()
         _check(self.lib.jb_context_create(int(device), C.c_void_p(stream or 0), int(workspace_bytes), C.byref(self._h)))
         self.device = int(device)
+        # one stream + one grow-only workspace per context: engine calls are serialised.  The
+        # reference's `Jess.query` is re-entrant (README thread-pool recipe); here concurrent
+        # threads simply queue on the GPU (ctypes drops the GIL while a call runs).
+        self.lock = threading.RLock()
 
     def close(self):
         if self._h:
@@ -109,7 +114,8 @@ class DeviceTemplates:
     def __init__(self, ctx: Context, table: TemplateTable):
         self.ctx, self.table = ctx, table
         self._h = C.c_void_p()
-        _check(ctx.lib.jb_templates_create(ctx._h, C.byref(table.as_struct()), C.byref(self._h)))
+        with ctx.lock:
+            _check(ctx.lib.jb_templates_create(ctx._h, C.byref(table.as_struct()), C.byref(self._h)))
 
     @property
     def spec_count(self) -> int:
@@ -151,7 +157,8 @@ class Result:
 
     def fetch(self) -> HitTable:
         hits = jb_hits()
-        _check(self.ctx.lib.jb_result_fetch(self._h, C.byref(hits)))
+        with self.ctx.lock:
+            _check(self.ctx.lib.jb_result_fetch(self._h, C.byref(hits)))
         return HitTable(hits, owner=self)      # zero-copy views; the table keeps this result alive
 
     def stats(self) -> dict:
@@ -174,7 +181,8 @@ class Result:
 def query_run(ctx: Context, templates: DeviceTemplates, molecules: DeviceMolecules, params: jb_query_params) -> Result:
     """Kernels only: inputs already resident in HBM, hits stay in HBM."""
     h = C.c_void_p()
-    _check(ctx.lib.jb_query_run(ctx._h, templates._h, molecules._h, C.byref(params), C.byref(h)))
+    with ctx.lock:
+        _check(ctx.lib.jb_query_run(ctx._h, templates._h, molecules._h, C.byref(params), C.byref(h)))
     return Result(ctx, h)
 
 
@@ -183,8 +191,9 @@ def query_host(ctx: Context, templates: DeviceTemplates, batch: MoleculeBatch, p
     Returns (HitTable, stats)."""
     h = C.c_void_p()
     hits = jb_hits()
-    _check(ctx.lib.jb_query_host(ctx._h, templates._h, C.byref(batch.as_struct()), C.byref(params), C.byref(h),
-                                 C.byref(hits)))
+    with ctx.lock:
+        _check(ctx.lib.jb_query_host(ctx._h, templates._h, C.byref(batch.as_struct()), C.byref(params), C.byref(h),
+                                     C.byref(hits)))
     res = Result(ctx, h)
     return HitTable(hits, owner=res), res.stats()
 

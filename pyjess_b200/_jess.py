@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import io
 import math
+import threading
 import warnings
 from typing import Iterable, List, Optional, Sequence
 
@@ -166,6 +167,17 @@ def _rebuild_hit(state):
     return hit
 
 
+_tls = threading.local()
+
+
+def _staging_pool() -> dict:
+    """Per-thread staging arrays of the host -> device upload (re-used between queries)."""
+    pool = getattr(_tls, "pool", None)
+    if pool is None:
+        pool = _tls.pool = {}
+    return pool
+
+
 class _BatchRun:
     """Shared, lazily executed engine call of one `query` / `query_many`."""
 
@@ -192,7 +204,7 @@ class _BatchRun:
         from . import _capi  # raises if the CUDA engine is missing: no fallback
         ctx = _capi.default_context()
         dev_tpl = jess._device_templates(ctx)
-        batch = MoleculeBatch(mols, serial=True)
+        batch = MoleculeBatch(mols, serial=True, pool=_staging_pool())
         rmsd, dist, maxdyn, ignore_chain, reorder, best_match = self.args
         # the engine searches in its own scan order; the ORDER of the records is the
         # reference's for the `reorder` flag the caller passed
@@ -213,11 +225,19 @@ class _BatchRun:
             first = np.ones(t.count, dtype=bool)
             first[1:] = (t.molecule[1:] != t.molecule[:-1]) | (t.template[1:] != t.template[:-1])
             keep = ~(first & single[t.template])
-        # iteration order per structure: template DESCENDING (reverse insertion), engine order within;
-        # one stable sort for the whole batch, the per-structure slices are views of it
+        # iteration order per structure: template DESCENDING (reverse insertion), engine order within.
+        # The table is sorted by (structure, template): only whole (structure, template) RUNS move.
         rows = np.arange(t.count, dtype=np.int64) if keep is None else np.nonzero(keep)[0]
         mol, tpl = t.molecule[rows], t.template[rows]
-        rows = rows[np.lexsort((-tpl.astype(np.int64), mol))]
+        if len(rows):
+            head = np.ones(len(rows), dtype=bool)
+            head[1:] = (mol[1:] != mol[:-1]) | (tpl[1:] != tpl[:-1])
+            start = np.nonzero(head)[0]
+            length = np.diff(np.append(start, len(rows)))
+            perm = np.lexsort((-tpl[start].astype(np.int64), mol[start]))          # runs, not records
+            start, length = start[perm], length[perm]
+            offs = np.cumsum(length) - length
+            rows = rows[np.repeat(start - offs, length) + np.arange(len(rows))]
         bounds = np.searchsorted(t.molecule[rows], np.arange(len(mols) + 1))
         self._slices = [rows[bounds[m]:bounds[m + 1]] for m in range(len(mols))]
 

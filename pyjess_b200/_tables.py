@@ -209,32 +209,44 @@ class MoleculeBatch:
     FIELDS = (("x", np.float64), ("y", np.float64), ("z", np.float64), ("name", np.uint32),
               ("resname", np.uint32), ("resseq", np.int32), ("chain", np.uint8))
 
-    def __init__(self, molecules: Sequence[Molecule], pinned: bool = False, serial: bool = False):
-        """`serial=True` also ships Atom.serial (only the reference hit order reads it)."""
+    def __init__(self, molecules: Sequence[Molecule], pinned: bool = False, serial: bool = False, pool=None):
+        """`serial=True` also ships Atom.serial (only the reference hit order reads it).
+        `pool`: a dict that keeps the staging arrays alive between short-lived batches of one
+        thread (no first-touch page faults on every query); the batch must not outlive the
+        next batch built from the same pool."""
+        self._pool = pool
         molecules = list(molecules)
         self.molecules = molecules
         self.n_molecules = len(molecules)
-        packs = [m._packed() for m in molecules]
-        counts = [p["n"] for p in packs]
+        counts = np.asarray([len(m._atoms) for m in molecules], dtype=np.int64)
         self.atom_offset = np.zeros(self.n_molecules + 1, dtype=np.int64)
-        np.cumsum(counts, out=self.atom_offset[1:])
-        total = int(self.atom_offset[-1])
+        total = int(counts.sum())
         self.n_atoms = total
         self._keep = []
         for field, dtype in self.FIELDS:
-            buf = self._alloc(max(total, 1), dtype, pinned)
-            if packs:
-                np.concatenate([p[field] for p in packs], out=buf[:total])
-            setattr(self, field, buf)
-        self.serial = None
-        if serial:
-            self.serial = self._alloc(max(total, 1), np.int32, pinned)
-            if molecules:
-                np.concatenate([np.ascontiguousarray(m._atoms["serial"], dtype=np.int32) for m in molecules],
-                               out=self.serial[:total])
+            setattr(self, field, self._alloc(max(total, 1), dtype, pinned))
+        self.serial = self._alloc(max(total, 1), np.int32, pinned) if serial else None
+        # one native pass over the molecules' record arrays (jb_molecules_pack, csrc/ingest.cu)
+        from . import _capi
+        lib = _capi.load_library()
+        recs = [np.ascontiguousarray(m._atoms) for m in molecules]
+        ptrs = np.asarray([r.ctypes.data for r in recs], dtype=np.uintp)
+        ptr = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
+        rc = lib.jb_molecules_pack(ptr(ptrs), ptr(counts), self.n_molecules, ptr(self.atom_offset), ptr(self.x),
+                                   ptr(self.y), ptr(self.z), ptr(self.name), ptr(self.resname), ptr(self.resseq),
+                                   ptr(self.chain), ptr(self.serial) if serial else None)
+        if rc != 0:
+            raise RuntimeError(f"jb_molecules_pack failed with status {rc}")
         self._struct = None
 
     def _alloc(self, n, dtype, pinned):
+        if self._pool is not None and not pinned:
+            key = (len(self._keep), np.dtype(dtype).str)
+            self._keep.append(key)
+            buf = self._pool.get(key)
+            if buf is None or len(buf) < n:
+                buf = self._pool[key] = np.zeros(max(n, 1 << 16) + n // 4, dtype=dtype)
+            return buf[:n]
         if pinned:
             import torch
             t = torch.empty(n * np.dtype(dtype).itemsize, dtype=torch.uint8, pin_memory=True)

@@ -177,3 +177,31 @@ extern "C" int64_t jb_format_atoms_pdb(const jb_atom_record *atoms, int64_t n, c
     }
     return pos;
 }
+
+// ---- packing: per-molecule _Atom arrays -> the SoA image of jb_molecule_batch -------------
+// What Molecule.__init__ + ResIndex_create consume in the reference (SURVEY 8b "bj_molecules_pack"):
+// reads the 59-byte records of every molecule once and writes the structure-of-arrays staging
+// buffers (pinned or pageable) that jb_molecules_upload / jb_query_host copy to HBM.
+extern "C" int jb_molecules_pack(const jb_atom_record *const *molecules, const int64_t *counts, int32_t n_molecules,
+                                 int64_t *atom_offset, double *x, double *y, double *z, uint32_t *name,
+                                 uint32_t *residue_name, int32_t *residue_number, uint8_t *chain_id2, int32_t *serial)
+{
+    if (n_molecules < 0 || !atom_offset || (n_molecules > 0 && (!molecules || !counts))) return JB_ERR_INVALID;
+    int64_t pos = 0;
+    atom_offset[0] = 0;
+    for (int32_t m = 0; m < n_molecules; m++) {
+        const jb_atom_record *a = molecules[m];
+        const int64_t n = counts[m];
+        if (n < 0 || (n > 0 && !a)) return JB_ERR_INVALID;
+        for (int64_t i = 0; i < n; i++, pos++) {
+            x[pos] = a[i].x[0]; y[pos] = a[i].x[1]; z[pos] = a[i].x[2];
+            memcpy(&name[pos], a[i].name, 4);
+            memcpy(&residue_name[pos], a[i].res_name, 4);
+            residue_number[pos] = a[i].res_seq;
+            chain_id2[pos] = a[i].chain_id2;
+            if (serial) serial[pos] = a[i].serial;
+        }
+        atom_offset[m + 1] = pos;
+    }
+    return JB_OK;
+}

@@ -226,3 +226,17 @@ def test_single_atom_templates_match_reference(name):
         assert np.abs(np.asarray(h.transformation) - np.asarray(g["transformation"])).max() <= 1e-6
         assert h.determinant == pytest.approx(g["determinant"], abs=1e-6)
         assert h.log_evalue == pytest.approx(g["log_evalue"], abs=1e-9)
+
+
+def test_thread_pool_recipe_of_the_reference_readme(lnb):
+    """README.md:155-162 of the reference: one Jess, a thread pool over molecules.  Engine
+    calls of concurrent threads are serialised per context; results must not mix."""
+    from multiprocessing.pool import ThreadPool
+    jess = Jess([load_template("template_01.qry"), load_template("1.3.3.tpl")])
+    mols = [lnb, load_molecule("1AMY.pdb"), load_molecule("pdb1a0p.ent")] * 6
+    expected = [[(h.template().id, round(h.rmsd, 9), tuple(a.serial for a in h.atoms(False)))
+                 for h in jess.query(m, 2.0, 4.0, 4.0)] for m in mols[:3]]
+    with ThreadPool(6) as pool:
+        got = pool.map(lambda m: [(h.template().id, round(h.rmsd, 9), tuple(a.serial for a in h.atoms(False)))
+                                  for h in jess.query(m, 2.0, 4.0, 4.0)], mols)
+    assert got == expected * 6 and sum(map(len, expected)) > 100
