@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py -- template x structure pairs/s of the query hot path on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3|cfg3dense|cfg4shard|cfg5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg3dense|cfg4shard|cfg5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...      # the reference's own CPU path (oracle/_ref)
 
@@ -107,6 +107,20 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def load_workload(name, scale=1.0, rank=0):
+    """Synthetic BASELINE configs 3-5 (pyjess_b200/synth.py) or, for `cfg2`, the reference's own
+    example set: 3 vendor templates x the 132 vendor structures at (2, 3, 3) -- 396 pairs, a
+    LATENCY datapoint (the structures come from tests/golden/cfg2_structures.npz, written by the
+    reference's parser; the same 132 structures on every rank)."""
+    if name == "cfg2":
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from _util import cfg2_molecules, load_template
+        tpl = [load_template(f"template_0{i}.qry") for i in (1, 2, 3)]
+        return tpl, list(cfg2_molecules()), (2.0, 3.0, 3.0), {}
+    from pyjess_b200 import synth
+    return synth.workload(name, scale=scale, rank=rank)
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own C implementation (oracle/_ref, built from
     the unmodified sources) on all host cores, on a bounded sample of the workload."""
@@ -115,7 +129,7 @@ def run_reference(args, rank, world):
     import oracle
     from pyjess_b200 import synth
     from pyjess_b200._tables import MoleculeBatch, TemplateTable, query_params
-    tpl, mols, params, kw = synth.workload(args.workload)
+    tpl, mols, params, kw = load_workload(args.workload)
     sample = mols[:args.cpu_structures]
     tt, mb = TemplateTable(tpl), MoleculeBatch(sample)
     qp = query_params(*params, **kw)
@@ -161,7 +175,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.cpu_structures <= 0:
-        full = {"cfg3": 1000, "cfg3dense": 1000, "cfg4shard": 300, "cfg5": 60}.get(args.workload, 100)
+        full = {"cfg2": 132, "cfg3": 1000, "cfg3dense": 1000, "cfg4shard": 300, "cfg5": 60}.get(args.workload, 100)
         args.cpu_structures = full if args.impl == "b200" else max(1, full // 3)
 
     rank = int(os.environ.get("RANK", "0"))
@@ -179,7 +193,7 @@ def main():
 
     # ---- inputs (synthetic, seeded; structures differ per rank, templates replicated);
     # generated before CUDA is initialised: the cfg 4 generator forks worker processes
-    tpl, mols, params, kw = synth.workload(args.workload, scale=args.scale, rank=rank)
+    tpl, mols, params, kw = load_workload(args.workload, scale=args.scale, rank=rank)
     qp = query_params(*params, **kw)
 
     if not torch.cuda.is_available():

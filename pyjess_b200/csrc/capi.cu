@@ -120,6 +120,7 @@ struct jb_context {
     DevBuf h_mol, h_tpl, h_atoms, h_rmsd, h_rot, h_c0, h_c1;   // hits as k_superpose appends them
     DevBuf f_mol, f_tpl, f_atoms, f_rmsd, f_rot, f_c0, f_c1;   // ... in canonical order (hits.cuh)
     DevBuf o_off, o_fill, o_grouped, o_order, o_tiles, o_runs, o_work;   // ordering workspace
+    DevBuf k_key, k_key2, k_iota, k_runid, k_scan;             // keyed hit ordering (hits.cuh)
     DevBuf h_pair, h_keys;                                     // reference-order mode: pair of each hit, rank vectors
     DevBuf q_ocnt, q_keyA, q_keyA2, q_keyB, q_keyB2, q_iota, q_perm, q_setpos, q_kdrank, q_coords, q_kdidx, q_cub;
     RunWork *host_work = nullptr;                              // pinned
@@ -209,7 +210,7 @@ extern "C" int jb_context_create(int device, void *stream, int64_t workspace_byt
     if (c->debug) for (int i = 0; i <= kMaxN; i++) CU(cudaEventCreate(&c->lev[i]));
     CU(cudaMallocHost(&c->host_ctr, sizeof(Counters)));
     CU(cudaMallocHost(&c->host_work, sizeof(RunWork)));
-    CU(c->o_work.ensure(sizeof(RunWork), c->stream));
+    CU(c->o_work.ensure(2 * sizeof(RunWork), c->stream));   // [0] tile work list, [1].n_runs = number of tie runs
     CU(c->ctr.ensure(sizeof(Counters), c->stream));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
@@ -227,7 +228,7 @@ extern "C" void jb_context_destroy(jb_context *c)
                        &c->tuples, &c->ctr, &c->h_mol, &c->h_tpl, &c->h_atoms, &c->h_rmsd, &c->h_rot, &c->h_c0,
                        &c->h_c1, &c->f_mol, &c->f_tpl, &c->f_atoms, &c->f_rmsd, &c->f_rot, &c->f_c0, &c->f_c1,
                        &c->o_off, &c->o_fill, &c->o_grouped, &c->o_order, &c->o_tiles, &c->o_runs, &c->o_work,
-                       &c->h_pair, &c->h_keys, &c->q_ocnt, &c->q_keyA, &c->q_keyA2, &c->q_keyB, &c->q_keyB2, &c->q_iota,
+                       &c->k_key, &c->k_key2, &c->k_iota, &c->k_runid, &c->k_scan, &c->h_pair, &c->h_keys, &c->q_ocnt, &c->q_keyA, &c->q_keyA2, &c->q_keyB, &c->q_keyB2, &c->q_iota,
                        &c->q_perm, &c->q_setpos, &c->q_kdrank, &c->q_coords, &c->q_kdidx, &c->q_cub };
     for (DevBuf *b : bufs) b->release();
     if (c->scratch_mol) {
@@ -528,6 +529,7 @@ static cudaError_t dispatch_expand_lv(int level, int g, int sm_count, cudaStream
     switch (level) {
         JB_LV_CASE(1) JB_LV_CASE(2) JB_LV_CASE(3) JB_LV_CASE(4)
         JB_LV_CASE(5) JB_LV_CASE(6) JB_LV_CASE(7) JB_LV_CASE(8)
+        JB_LV_CASE(9) JB_LV_CASE(10) JB_LV_CASE(11) JB_LV_CASE(12)
     default: return cudaErrorInvalidValue;
     }
 #undef JB_LV_CASE
@@ -874,27 +876,100 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
             }
             OA.off = c->o_off.as<unsigned>(); OA.fill = c->o_fill.as<unsigned>();
             OA.grouped = c->o_grouped.as<unsigned>(); OA.order = c->o_order.as<unsigned>();
+            OA.runid = nullptr;
             const unsigned hb = (unsigned)((nh + 255) / 256);
-            k_hit_hist<<<hb, 256, 0, st>>>(OA);
-            k_scan_tiles<<<n_tiles, kScanThreads, 0, st>>>(OA.off, pairs + 1, c->o_tiles.as<unsigned>());
-            k_scan_totals<<<1, kScanThreads, 0, st>>>(c->o_tiles.as<unsigned>(), n_tiles);
-            k_scan_add<<<n_tiles, kScanThreads, 0, st>>>(OA.off, pairs + 1, c->o_tiles.as<unsigned>());
-            k_hit_group<<<hb, 256, 0, st>>>(OA);
-            k_hit_rank<<<hb, 256, 0, st>>>(OA);
-            S.launches += 7;
+            // keyed path: one radix sort groups the hits by pair AND orders them by the first two key
+            // columns; the run machinery below then only resolves ties.  Needs the columns to fit
+            // their 20/21 bits (atom indices / ranks < 2^20) and the pair its 23 bits.
+            long long amax = 0;
+            for (int m = r.m0; m < r.m1; m++) amax = std::max(amax, mol->atom_off[m + 1] - mol->atom_off[m]);
+            const bool keyed = amax < (1ll << kKeyCol0Bits) && pairs <= (1ll << 23) && !getenv("JB_ORDER_COUNTING");
+            long long n_runs_bound = pairs;
+            const unsigned *d_n_runs = nullptr;
+            if (keyed) {
+                CU(c->k_key.ensure((size_t)nh * sizeof(u64), st));   CU(c->k_key2.ensure((size_t)nh * sizeof(u64), st));
+                CU(c->k_iota.ensure((size_t)nh * sizeof(unsigned), st));
+                CU(c->k_runid.ensure((size_t)(nh + 1) * sizeof(unsigned), st));
+                CU(c->o_off.ensure((size_t)(nh + 2) * sizeof(unsigned), st));
+                OA.off = c->o_off.as<unsigned>();
+                k_hit_key<<<hb, 256, 0, st>>>(OA, c->k_key.as<u64>(), c->k_iota.as<unsigned>());
+                int pair_bits = 1;
+                while ((1ll << pair_bits) < pairs) pair_bits++;
+                size_t tmp = 0;
+                const int end_bit = kKeyCol0Bits + kKeyCol1Bits + pair_bits;
+                CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->k_key.as<u64>(), c->k_key2.as<u64>(), c->k_iota.as<unsigned>(),
+                                                   OA.grouped, (int)nh, 0, end_bit, st));
+                CU(c->q_cub.ensure(tmp, st));
+                CU(cub::DeviceRadixSort::SortPairs(c->q_cub.p, tmp, c->k_key.as<u64>(), c->k_key2.as<u64>(),
+                                                   c->k_iota.as<unsigned>(), OA.grouped, (int)nh, 0, end_bit, st));
+                // runs of equal keys: flags -> exclusive scan -> run ids / offsets / count
+                unsigned *flag = c->k_runid.as<unsigned>();           // scanned in place, then overwritten by the ids
+                const int ft = (int)((nh + 1 + kScanTile - 1) / kScanTile);
+                CU(c->o_tiles.ensure((size_t)std::max(ft, n_tiles) * sizeof(unsigned), st));
+                CU(c->k_scan.ensure((size_t)(nh + 1) * sizeof(unsigned), st));
+                unsigned *scanned = c->k_scan.as<unsigned>();
+                k_run_flags<<<(unsigned)((nh + 1 + 255) / 256), 256, 0, st>>>(nh, c->k_key2.as<u64>(), scanned);
+                k_scan_tiles<<<ft, kScanThreads, 0, st>>>(scanned, nh + 1, c->o_tiles.as<unsigned>());
+                k_scan_totals<<<1, kScanThreads, 0, st>>>(c->o_tiles.as<unsigned>(), ft);
+                k_scan_add<<<ft, kScanThreads, 0, st>>>(scanned, nh + 1, c->o_tiles.as<unsigned>());
+                k_run_heads<<<hb, 256, 0, st>>>(nh, c->k_key2.as<u64>(), scanned, flag, OA.off, &c->o_work.as<RunWork>()[1].n_runs);
+                OA.runid = flag;
+                d_n_runs = &c->o_work.as<RunWork>()[1].n_runs;
+                n_runs_bound = nh;
+                k_hit_rank<<<hb, 256, 0, st>>>(OA);
+                S.launches += 7;   // + the radix sort passes (library kernels)
+            } else {
+                k_hit_hist<<<hb, 256, 0, st>>>(OA);
+                k_scan_tiles<<<n_tiles, kScanThreads, 0, st>>>(OA.off, pairs + 1, c->o_tiles.as<unsigned>());
+                k_scan_totals<<<1, kScanThreads, 0, st>>>(c->o_tiles.as<unsigned>(), n_tiles);
+                k_scan_add<<<n_tiles, kScanThreads, 0, st>>>(OA.off, pairs + 1, c->o_tiles.as<unsigned>());
+                k_hit_group<<<hb, 256, 0, st>>>(OA);
+                k_hit_rank<<<hb, 256, 0, st>>>(OA);
+                S.launches += 7;
+            }
             if (nh > (long long)kShortRun) {
                 // dense-hit pairs: segmented tiled bitonic sort of the long runs (hits.cuh)
-                const unsigned tile_cap = (unsigned)(nh / kTile + std::min<long long>(pairs, nh / kShortRun + 1) + 1);
+                const unsigned tile_cap = (unsigned)(nh / kTile + std::min<long long>(n_runs_bound, nh / kShortRun + 1) + 1);
                 CU(c->o_runs.ensure((size_t)tile_cap * sizeof(RunTile), st));
                 CU(cudaMemsetAsync(c->o_work.p, 0, sizeof(RunWork), st));
-                k_run_tiles<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(OA, pairs, c->o_runs.as<RunTile>(), tile_cap,
-                                                                             c->o_work.as<RunWork>());
+                k_run_tiles<<<(unsigned)((n_runs_bound + 255) / 256), 256, 0, st>>>(OA, n_runs_bound, d_n_runs, c->o_runs.as<RunTile>(),
+                                                                                    tile_cap, c->o_work.as<RunWork>());
                 CU(cudaMemcpyAsync(c->host_work, c->o_work.p, sizeof(RunWork), cudaMemcpyDeviceToHost, st));
                 CU(cudaStreamSynchronize(st));
                 const unsigned nt = c->host_work->n_tiles, max_npad = c->host_work->max_npad;
                 if (nt > tile_cap) return fail(JB_ERR_CAPACITY, "hit ordering: %u tiles exceed the work list (%u)", nt, tile_cap);
                 S.launches++;
-                if (nt > 0) {
+                const bool force_lsd = getenv("JB_ORDER_LSD") != nullptr;       // tests: take the dense path at any size
+                // ... worth it when a good share of the hits sits in long runs (n log^2 n per run otherwise)
+                const bool dense = nt > 0 && (long long)c->host_work->long_hits * 8 >= nh;
+                if ((dense || force_lsd) && keyed && !getenv("JB_ORDER_NO_LSD")) {
+                    // long tie runs: order the whole chunk by a multi-pass LSD radix sort (hits.cuh)
+                    int bits = 1;
+                    while ((1ll << bits) < amax + 1) bits++;                  // columns < amax (or all ones: padding)
+                    bits = std::min(bits + 1, (int)kKeyCol1Bits);
+                    const int per = 64 / bits;
+                    unsigned *perm = c->k_iota.as<unsigned>(), *perm2 = OA.grouped;
+                    k_iota<<<hb, 256, 0, st>>>(perm, nh);
+                    size_t tmp = 0;
+                    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->k_key.as<u64>(), c->k_key2.as<u64>(), perm, perm2,
+                                                       (int)nh, 0, 64, st));
+                    CU(c->q_cub.ensure(tmp, st));
+                    for (int hi = c->hit_stride; hi > 2;) {
+                        const int lo = std::max(2, hi - per);
+                        k_lsd_key<<<hb, 256, 0, st>>>(OA, perm, lo, hi, bits, 0, c->k_key.as<u64>());
+                        CU(cub::DeviceRadixSort::SortPairs(c->q_cub.p, tmp, c->k_key.as<u64>(), c->k_key2.as<u64>(), perm, perm2,
+                                                           (int)nh, 0, (hi - lo) * bits, st));
+                        std::swap(perm, perm2);
+                        S.launches += 1;
+                        hi = lo;
+                    }
+                    int pair_bits = 1;
+                    while ((1ll << pair_bits) < pairs) pair_bits++;
+                    k_lsd_key<<<hb, 256, 0, st>>>(OA, perm, 0, 0, bits, 1, c->k_key.as<u64>());
+                    CU(cub::DeviceRadixSort::SortPairs(c->q_cub.p, tmp, c->k_key.as<u64>(), c->k_key2.as<u64>(), perm, OA.order,
+                                                       (int)nh, 0, kKeyCol0Bits + kKeyCol1Bits + pair_bits, st));
+                    S.launches += 2;
+                } else if (nt > 0) {
                     const RunTile *rt = c->o_runs.as<RunTile>();
                     k_tile_sort<<<nt, kTileThreads, 0, st>>>(OA, rt);
                     S.launches++;

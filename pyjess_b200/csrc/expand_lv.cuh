@@ -30,7 +30,7 @@
 
 namespace jb {
 
-constexpr int kMaxLv = 8;        // levels 1..kMaxLv have a specialisation; deeper levels use k_expand
+constexpr int kMaxLv = 12;       // levels 1..kMaxLv have a specialisation; deeper levels use k_expand
 #ifndef JB_CHUNK
 #define JB_CHUNK 16
 #endif

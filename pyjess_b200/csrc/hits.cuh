@@ -8,12 +8,16 @@
 // so the order is established here with a counting sort over the (structure,
 // template) pairs of the chunk followed by a rank inside each -- usually tiny -- run:
 //
-//   k_hit_hist    count hits per pair                      (atomicAdd, one per hit)
-//   scan          exclusive prefix sum over the pairs      (k_scan_*: 3 small kernels)
-//   k_hit_group   slot = off[pair] + ticket  -> index list grouped by pair
-//   k_hit_rank    short runs: rank of every hit inside its run by lexicographic tuple compare
-//   k_run_* / k_tile_*  long runs (dense-hit pairs): segmented, tiled bitonic sort of the index lists
+//   k_hit_key     64-bit key (pair, first key column, second key column) per hit
+//   radix sort    cub::DeviceRadixSort over the keys: hits grouped by pair AND ordered by the first
+//                 two columns in one pass over the data (dense-hit workloads used to spend more
+//                 time in the segmented bitonic sort of whole pairs than in the search itself)
+//   k_run_heads   runs of EQUAL keys (ties on the first two columns) -> run ids and offsets (scan)
+//   k_hit_rank    ties: rank of every hit inside its (usually 1-element) run by full tuple compare
+//   k_run_* / k_tile_*  long tie runs: segmented, tiled bitonic sort of the index lists
 //   k_hit_gather  hit records -> final arrays in canonical order (coalesced writes)
+// (k_hit_hist / k_hit_group: the counting-sort grouping by pair, kept for structures whose atom
+//  indices do not fit the key's 20/21-bit columns.)
 #pragma once
 #include "kernels.cuh"
 
@@ -102,8 +106,9 @@ struct HitOrderArgs {
     const int *mol, *tpl, *atoms;
     unsigned *off;              // [pairs + 1] counts, then exclusive offsets
     unsigned *fill;             // [pairs] tickets
-    unsigned *grouped;          // [h1 - h0] hit indices grouped by pair
+    unsigned *grouped;          // [h1 - h0] hit indices grouped by run
     unsigned *order;            // [h1 - h0] hit indices in canonical order
+    const unsigned *runid;      // [h1 - h0] run of every GROUPED position (NULL: runs = pairs, off indexed by pair)
 };
 
 __device__ __forceinline__ long long hit_pair(const HitOrderArgs &A, long long i)
@@ -125,6 +130,64 @@ __global__ void __launch_bounds__(256) k_hit_group(HitOrderArgs A)
     A.grouped[A.off[p] + atomicAdd(&A.fill[p], 1u)] = (unsigned)(i - A.h0);
 }
 
+// ---- keyed path: (pair | column 0 | column 1) ------------------------------------------------
+constexpr int kKeyCol0Bits = 20, kKeyCol1Bits = 21;      // 23 bits remain for the pair of the chunk
+
+__global__ void __launch_bounds__(256) k_hit_key(HitOrderArgs A, u64 *key, unsigned *iota)
+{
+    const long long i = A.h0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.h1) return;
+    const int *row = A.atoms + i * A.stride;
+    const u64 c0 = (u64)((unsigned)row[0] & ((1u << kKeyCol0Bits) - 1));
+    const u64 c1 = A.stride > 1 ? (u64)((unsigned)row[1] & ((1u << kKeyCol1Bits) - 1)) : 0ull;
+    key[i - A.h0] = ((u64)hit_pair(A, i) << (kKeyCol0Bits + kKeyCol1Bits)) | (c0 << kKeyCol1Bits) | c1;
+    iota[i - A.h0] = (unsigned)(i - A.h0);
+}
+
+// Dense-hit fallback of the keyed path: when the first sort leaves LONG tie runs (thousands of hits
+// of one pair sharing their first two columns: symmetric side chains of large templates), the
+// whole chunk is ordered by a multi-pass LSD radix sort instead -- trailing columns first, `per`
+// columns of `bits` bits per 64-bit key, every pass stable, the (pair, c0, c1) pass last.
+__global__ void __launch_bounds__(256) k_lsd_key(HitOrderArgs A, const unsigned *perm, int lo, int hi, int bits, int final,
+                                                 u64 *key)
+{
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= A.h1 - A.h0) return;
+    const long long i = A.h0 + perm[j];
+    const int *row = A.atoms + i * A.stride;
+    u64 k = 0;
+    if (final) {
+        const u64 c0 = (u64)((unsigned)row[0] & ((1u << kKeyCol0Bits) - 1));
+        const u64 c1 = A.stride > 1 ? (u64)((unsigned)row[1] & ((1u << kKeyCol1Bits) - 1)) : 0ull;
+        k = ((u64)hit_pair(A, i) << (kKeyCol0Bits + kKeyCol1Bits)) | (c0 << kKeyCol1Bits) | c1;
+    } else {
+        const unsigned mask = (1u << bits) - 1;
+        for (int c = lo; c < hi; c++) k = (k << bits) | (u64)((unsigned)row[c] & mask);
+    }
+    key[j] = k;
+}
+
+// flag[j] = 1 where a new run of equal keys starts (j > 0); scanned in place afterwards
+__global__ void __launch_bounds__(256) k_run_flags(long long n, const u64 *skey, unsigned *flag)
+{
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > n) return;
+    flag[j] = (j > 0 && j < n && skey[j] != skey[j - 1]) ? 1u : 0u;
+}
+
+// after the exclusive scan of the flags: run id of every position, run offsets, run count
+__global__ void __launch_bounds__(256) k_run_heads(long long n, const u64 *skey, const unsigned *scanned, unsigned *runid,
+                                                   unsigned *off, unsigned *n_runs)
+{
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const bool head = j == 0 || skey[j] != skey[j - 1];
+    const unsigned r = scanned[j] + ((j > 0 && head) ? 1u : 0u);
+    runid[j] = r;
+    if (head) off[r] = (unsigned)j;
+    if (j == n - 1) { off[r + 1] = (unsigned)n; *n_runs = r + 1; }
+}
+
 constexpr unsigned kShortRun = 48;   // runs up to this length are ranked, longer ones sorted by a CTA
 
 // other < mine in lexicographic tuple order
@@ -139,11 +202,14 @@ __device__ __forceinline__ bool tuple_less(const int *other, const int *mine, in
 
 __global__ void __launch_bounds__(256) k_hit_rank(HitOrderArgs A)
 {
-    const long long i = A.h0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= A.h1) return;
-    const long long p = hit_pair(A, i);
+    const long long q = A.h0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= A.h1) return;
+    // keyed path: one thread per GROUPED position; counting-sort path: one thread per hit
+    const long long i = A.runid ? A.h0 + A.grouped[q - A.h0] : q;
+    const long long p = A.runid ? (long long)A.runid[q - A.h0] : hit_pair(A, i);
     const unsigned r0 = A.off[p], r1 = A.off[p + 1];
-    if (r1 - r0 > kShortRun) return;                          // k_hit_sort owns this run
+    if (r1 - r0 == 1) { A.order[r0] = (unsigned)(i - A.h0); return; }
+    if (r1 - r0 > kShortRun) return;                          // the tiled sort owns this run
     const int *mine = A.atoms + i * A.stride;
     unsigned rank = 0;
     for (unsigned r = r0; r < r1; r++) {
@@ -176,12 +242,15 @@ struct alignas(16) RunTile {
 struct RunWork {
     unsigned n_tiles;
     unsigned max_npad;
+    unsigned long_hits;      // hits inside runs longer than kShortRun
+    unsigned n_runs;         // keyed path: number of tie runs (written by k_run_heads)
 };
 
-__global__ void __launch_bounds__(256) k_run_tiles(HitOrderArgs A, long long n_pairs, RunTile *tiles, unsigned cap,
-                                                   RunWork *work)
+__global__ void __launch_bounds__(256) k_run_tiles(HitOrderArgs A, long long n_pairs, const unsigned *n_runs, RunTile *tiles,
+                                                   unsigned cap, RunWork *work)
 {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_runs) n_pairs = (long long)*n_runs;
     if (p >= n_pairs) return;
     const unsigned r0 = A.off[p], n = A.off[p + 1] - r0;
     if (n <= kShortRun) return;
@@ -190,6 +259,7 @@ __global__ void __launch_bounds__(256) k_run_tiles(HitOrderArgs A, long long n_p
     const unsigned nt = (n + kTile - 1) / kTile;
     const unsigned base = atomicAdd(&work->n_tiles, nt);
     atomicMax(&work->max_npad, npad);
+    atomicAdd(&work->long_hits, n);
     for (unsigned t = 0; t < nt; t++)
         if (base + t < cap) { RunTile e; e.r0 = r0; e.n = n; e.tile = t; e.npad = npad; tiles[base + t] = e; }
 }
