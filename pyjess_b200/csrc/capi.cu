@@ -129,6 +129,11 @@ struct jb_context {
     int hit_stride = 0;
     Counters *host_ctr = nullptr; // pinned
     struct jb_molecules *scratch_mol = nullptr;   // reused by jb_query_host (no per-call cudaMalloc)
+    struct jb_molecules *slice_mol[2] = { nullptr, nullptr };   // double-buffered staging of the pipelined jb_query_host
+    cudaStream_t copy_stream = nullptr;           // H2D of the next slice / D2H of the previous slice's hits
+    cudaEvent_t ev_up[2] = { nullptr, nullptr };
+    int pipeline_slices = 0;                      // JB_PIPELINE: 0 auto, 1 off, n >= 2 forced
+    long long last_hits = 0;                      // sizes the pinned result block of the next pipelined call
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
 };
 
@@ -165,6 +170,7 @@ struct jb_result {
     bool fetched = false;
     void *block = nullptr;    // page-locked host block holding the fetched arrays (from ctx->pin_pool)
     size_t block_bytes = 0;
+    size_t block_cap = 0;     // records the block is laid out for
     long long kept = 0;       // records after best_match selection
     int32_t *mol = nullptr, *tpl = nullptr, *atoms = nullptr;
     double *rmsd = nullptr, *rot = nullptr, *c0 = nullptr, *c1 = nullptr;
@@ -207,6 +213,7 @@ extern "C" int jb_context_create(int device, void *stream, int64_t workspace_byt
     }
     if (const char *g = getenv("JB_DEBUG")) c->debug = atoi(g);
     if (const char *g = getenv("JB_LEGACY")) c->legacy = atoi(g);
+    if (const char *g = getenv("JB_PIPELINE")) c->pipeline_slices = atoi(g);
     if (c->debug) for (int i = 0; i <= kMaxN; i++) CU(cudaEventCreate(&c->lev[i]));
     CU(cudaMallocHost(&c->host_ctr, sizeof(Counters)));
     CU(cudaMallocHost(&c->host_work, sizeof(RunWork)));
@@ -231,10 +238,15 @@ extern "C" void jb_context_destroy(jb_context *c)
                        &c->k_key, &c->k_key2, &c->k_iota, &c->k_runid, &c->k_scan, &c->h_pair, &c->h_keys, &c->q_ocnt, &c->q_keyA, &c->q_keyA2, &c->q_keyB, &c->q_keyB2, &c->q_iota,
                        &c->q_perm, &c->q_setpos, &c->q_kdrank, &c->q_coords, &c->q_kdidx, &c->q_cub };
     for (DevBuf *b : bufs) b->release();
-    if (c->scratch_mol) {
-        jb_molecules *m = c->scratch_mol;
-        for (DevBuf *b : m->all()) b->release();
-        delete m;
+    for (jb_molecules *m : { c->scratch_mol, c->slice_mol[0], c->slice_mol[1] })
+        if (m) {
+            for (DevBuf *b : m->all()) b->release();
+            delete m;
+        }
+    if (c->copy_stream) {
+        cudaStreamSynchronize(c->copy_stream);
+        cudaStreamDestroy(c->copy_stream);
+        for (int i = 0; i < 2; i++) if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]);
     }
     if (c->host_ctr) cudaFreeHost(c->host_ctr);
     if (c->host_work) cudaFreeHost(c->host_work);
@@ -402,33 +414,44 @@ extern "C" void jb_templates_free(jb_templates *t)
 extern "C" int jb_templates_spec_count(const jb_templates *t) { return t ? t->S : 0; }
 
 // ---- molecules --------------------------------------------------------------------------
-static int fill_molecules(jb_context *c, jb_molecules *m, const jb_molecule_batch *b)
+// Host -> device copies of structures [m0, m1) of `b` on stream `st` (no kernels, no sync)
+static int stage_molecules(jb_context *c, jb_molecules *m, const jb_molecule_batch *b, int m0, int m1, cudaStream_t st)
 {
-    const double t_0 = now_ms();
-    const int M = b->n_molecules;
-    if (M < 0) return fail(JB_ERR_INVALID, "negative molecule count");
+    const int M = m1 - m0;
+    if (M < 0 || m0 < 0 || m1 > b->n_molecules) return fail(JB_ERR_INVALID, "bad molecule range [%d, %d)", m0, m1);
     m->ctx = c;
     m->M = M;
-    m->atom_off.assign(b->atom_offset, b->atom_offset + M + 1);
+    m->atom_off.resize((size_t)M + 1);
+    const long long a0 = b->atom_offset[m0];
+    for (int i = 0; i <= M; i++) m->atom_off[i] = b->atom_offset[m0 + i] - a0;
     m->NA = M ? m->atom_off[M] : 0;
     for (int i = 0; i < M; i++)
         if (m->atom_off[i + 1] < m->atom_off[i] || m->atom_off[i + 1] - m->atom_off[i] > 0x7fffffffLL)
-            return fail(JB_ERR_INVALID, "molecule %d: bad atom offsets", i);
-    cudaStream_t st = c->stream;
+            return fail(JB_ERR_INVALID, "molecule %d: bad atom offsets", m0 + i);
     cudaError_t e = cudaSuccess;
 #define UP(buf, ptr, n) if (e == cudaSuccess) e = upload(buf, ptr, (size_t)(n), st)
     UP(m->d_off, m->atom_off.data(), M + 1);
-    UP(m->x, b->x, m->NA);
-    UP(m->y, b->y, m->NA);
-    UP(m->z, b->z, m->NA);
-    UP(m->name, b->name, m->NA);
-    UP(m->res, b->residue_name, m->NA);
-    UP(m->resseq, b->residue_number, m->NA);
-    UP(m->chain, b->chain_id2, m->NA);
+    UP(m->x, b->x + a0, m->NA);
+    UP(m->y, b->y + a0, m->NA);
+    UP(m->z, b->z + a0, m->NA);
+    UP(m->name, b->name + a0, m->NA);
+    UP(m->res, b->residue_name + a0, m->NA);
+    UP(m->resseq, b->residue_number + a0, m->NA);
+    UP(m->chain, b->chain_id2 + a0, m->NA);
     m->has_serial = b->serial != nullptr;
-    if (m->has_serial) UP(m->serial, b->serial, m->NA);
+    if (m->has_serial) UP(m->serial, b->serial + a0, m->NA);
 #undef UP
-    if (e == cudaSuccess) e = m->atoms.ensure(std::max<size_t>((size_t)m->NA, 1) * sizeof(AtomRec), st);
+    if (e != cudaSuccess)
+        return fail(e == cudaErrorMemoryAllocation ? JB_ERR_NOMEM : JB_ERR_CUDA, "molecule upload: %s", cudaGetErrorString(e));
+    return JB_OK;
+}
+
+// Derived device images of staged structures: 32-byte atom records, per-structure frame, x-sorted view
+static int prepare_molecules(jb_context *c, jb_molecules *m, cudaStream_t st)
+{
+    (void)c;
+    const int M = m->M;
+    cudaError_t e = m->atoms.ensure(std::max<size_t>((size_t)m->NA, 1) * sizeof(AtomRec), st);
     if (e == cudaSuccess && m->NA > 0) {
         k_pack_atoms<<<(unsigned)((m->NA + 255) / 256), 256, 0, st>>>(m->NA, m->x.as<double>(), m->y.as<double>(),
                                                                      m->z.as<double>(), m->resseq.as<int>(),
@@ -459,12 +482,22 @@ static int fill_molecules(jb_context *c, jb_molecules *m, const jb_molecule_batc
             e = cudaGetLastError();
         }
     }
-    // the caller's staging buffers must stay valid until the stream reaches the copies:
-    // synchronise so that they may be reused immediately.
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess)
         return fail(e == cudaErrorMemoryAllocation ? JB_ERR_NOMEM : JB_ERR_CUDA, "molecule upload: %s", cudaGetErrorString(e));
-    if (c->debug) fprintf(stderr, "[jb] upload %d structures, %lld atoms: %.2f ms\n", M, m->NA, now_ms() - t_0);
+    return JB_OK;
+}
+
+static int fill_molecules(jb_context *c, jb_molecules *m, const jb_molecule_batch *b)
+{
+    const double t_0 = now_ms();
+    if (b->n_molecules < 0) return fail(JB_ERR_INVALID, "negative molecule count");
+    int rc = stage_molecules(c, m, b, 0, b->n_molecules, c->stream);
+    if (rc == JB_OK) rc = prepare_molecules(c, m, c->stream);
+    if (rc != JB_OK) return rc;
+    // the caller's staging buffers must stay valid until the stream reaches the copies:
+    // synchronise so that they may be reused immediately.
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->debug) fprintf(stderr, "[jb] upload %d structures, %lld atoms: %.2f ms\n", m->M, m->NA, now_ms() - t_0);
     return JB_OK;
 }
 
@@ -638,13 +671,15 @@ static int grow_hits(jb_context *c, long long need, int stride)
     return JB_OK;
 }
 
+// `slice_base`: index of mol's first structure in the caller's batch (jb_query_host runs a batch
+// slice by slice); hits are appended after the res->count records already in the device buffers.
 static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecules *mol, const jb_query_params *q,
-                          jb_result *res)
+                          jb_result *res, int slice_base = 0)
 {
     CU(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     jb_stats &S = res->stats;
-    S.pairs = (int64_t)t->T * mol->M;
+    S.pairs += (int64_t)t->T * mol->M;
     if (t->T == 0 || mol->M == 0 || t->TA == 0) return JB_OK;
 
     TemplateTable TT;
@@ -696,7 +731,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         for (int m0 = mol->M; m0 > 0; m0 -= per) work.push_back({ std::max(0, m0 - per), m0 });
         // processed back to front (pop_back) => ascending structure order
     }
-    u64 hits_done = 0;
+    u64 hits_done = (u64)res->count;
     int attempts = 0;
     while (!work.empty()) {
         const Range r = work.back();
@@ -789,7 +824,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         HB.rmsd = c->h_rmsd.as<double>(); HB.rot = c->h_rot.as<double>(); HB.c0 = c->h_c0.as<double>();
         HB.c1 = c->h_c1.as<double>(); HB.cap = c->hit_cap; HB.stride = c->hit_stride;
         k_superpose<<<c->sm_count * 8, 128, 0, st>>>(c->tuples.as<int>(), &dc->tuples, tuple_cap, tuple_stride,
-                                                    c->recs.as<PairRec>(), TT, MT, r.m0, q->rmsd_threshold, q->all_tuples, HB,
+                                                    c->recs.as<PairRec>(), TT, MT, slice_base + r.m0, q->rmsd_threshold, q->all_tuples, HB,
                                                     dc);
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->evs[4], st));
@@ -866,7 +901,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
             CU(cudaMemsetAsync(c->o_off.p, 0, (size_t)(pairs + 1) * sizeof(unsigned), st));
             CU(cudaMemsetAsync(c->o_fill.p, 0, (size_t)pairs * sizeof(unsigned), st));
             HitOrderArgs OA;
-            OA.h0 = h0; OA.h1 = h1; OA.mol_base = r.m0; OA.n_templates = t->T; OA.stride = c->hit_stride;
+            OA.h0 = h0; OA.h1 = h1; OA.mol_base = slice_base + r.m0; OA.n_templates = t->T; OA.stride = c->hit_stride;
             OA.mol = HB.mol; OA.tpl = HB.tpl; OA.atoms = HB.atoms;
             if (q->hit_order != JB_ORDER_CANONICAL) {
                 // rank vectors of the reference's depth-first order replace the atom tuples as sort keys
@@ -1013,7 +1048,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
     CU(cudaEventSynchronize(c->ev1));
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    S.kernel_ms = ms;
+    S.kernel_ms += ms;
     S.hits = (int64_t)hits_done;
     res->count = (long long)hits_done;
     (void)attempts;
@@ -1042,6 +1077,85 @@ extern "C" int jb_query_run(jb_context *c, const jb_templates *t, const jb_molec
 
 static size_t align64(size_t v) { return (v + 63) & ~(size_t)63; }
 
+// One page-locked block for the seven hit arrays, laid out for `cap` records and recycled
+// through the context's pool.
+static int result_alloc_block(jb_result *r, size_t cap)
+{
+    jb_context *c = r->ctx;
+    const size_t stride = (size_t)r->stride;
+    const size_t o_mol = 0, o_tpl = o_mol + align64(cap * 4), o_atoms = o_tpl + align64(cap * 4),
+                 o_rmsd = o_atoms + align64(cap * stride * 4), o_rot = o_rmsd + align64(cap * 8),
+                 o_c0 = o_rot + align64(cap * 72), o_c1 = o_c0 + align64(cap * 24), total = o_c1 + align64(cap * 24) + 64;
+    if (r->block) {   // a smaller block from the pipelined path: back to the pool
+        if (c->pin_pool.size() < 4) c->pin_pool.emplace_back(r->block, r->block_bytes);
+        else cudaFreeHost(r->block);
+        r->block = nullptr;
+    }
+    for (size_t i = 0; i < c->pin_pool.size(); i++)
+        if (c->pin_pool[i].second >= total) {
+            r->block = c->pin_pool[i].first; r->block_bytes = c->pin_pool[i].second;
+            c->pin_pool.erase(c->pin_pool.begin() + i);
+            break;
+        }
+    if (!r->block) {
+        const size_t want = total + total / 4;
+        CU(cudaMallocHost(&r->block, want));
+        r->block_bytes = want;
+    }
+    char *base = static_cast<char *>(r->block);
+    r->mol = reinterpret_cast<int32_t *>(base + o_mol); r->tpl = reinterpret_cast<int32_t *>(base + o_tpl);
+    r->atoms = reinterpret_cast<int32_t *>(base + o_atoms); r->rmsd = reinterpret_cast<double *>(base + o_rmsd);
+    r->rot = reinterpret_cast<double *>(base + o_rot); r->c0 = reinterpret_cast<double *>(base + o_c0);
+    r->c1 = reinterpret_cast<double *>(base + o_c1);
+    r->block_cap = cap;
+    return JB_OK;
+}
+
+// device -> host copy of the ordered hit records [from, to) on stream `st` (no sync)
+static int result_copy_range(jb_result *r, size_t from, size_t to, cudaStream_t st)
+{
+    jb_context *c = r->ctx;
+    if (to <= from) return JB_OK;
+    const size_t n = to - from, stride = (size_t)r->stride;
+#define D2H(dst, buf, T, w) CU(cudaMemcpyAsync((dst) + from * (w), (buf).template as<T>() + from * (w), n * (w) * sizeof(T), cudaMemcpyDeviceToHost, st))
+    D2H(r->mol, c->f_mol, int, 1);
+    D2H(r->tpl, c->f_tpl, int, 1);
+    D2H(r->atoms, c->f_atoms, int, stride);
+    D2H(r->rmsd, c->f_rmsd, double, 1);
+    D2H(r->rot, c->f_rot, double, 9);
+    D2H(r->c0, c->f_c0, double, 3);
+    D2H(r->c1, c->f_c1, double, 3);
+#undef D2H
+    return JB_OK;
+}
+
+// keep the smallest RMSD per (molecule, template), compacting in place; ties -> first in the
+// record order (the reference keeps the first in ITS iteration order, _jess.pyx:2238)
+static void result_finalize(jb_result *r)
+{
+    const size_t n = (size_t)r->count, stride = (size_t)r->stride;
+    r->kept = (long long)n;
+    if (r->best_match && n) {
+        size_t w = 0;
+        for (size_t i = 0; i < n;) {
+            size_t j = i, best = i;
+            while (j < n && r->mol[j] == r->mol[i] && r->tpl[j] == r->tpl[i]) {
+                if (r->rmsd[j] < r->rmsd[best]) best = j;
+                j++;
+            }
+            r->mol[w] = r->mol[best]; r->tpl[w] = r->tpl[best]; r->rmsd[w] = r->rmsd[best];
+            memmove(&r->atoms[w * stride], &r->atoms[best * stride], stride * sizeof(int32_t));
+            memmove(&r->rot[w * 9], &r->rot[best * 9], 9 * sizeof(double));
+            memmove(&r->c0[w * 3], &r->c0[best * 3], 3 * sizeof(double));
+            memmove(&r->c1[w * 3], &r->c1[best * 3], 3 * sizeof(double));
+            w++;
+            i = j;
+        }
+        r->kept = (long long)w;
+    }
+    r->fetched = true;
+}
+
 extern "C" int jb_result_fetch(jb_result *r, jb_hits *out)
 {
     if (!r || !out) return fail(JB_ERR_INVALID, "jb_result_fetch: NULL argument");
@@ -1049,60 +1163,13 @@ extern "C" int jb_result_fetch(jb_result *r, jb_hits *out)
     CU(cudaSetDevice(c->device));
     if (!r->fetched) {
         const double t_0 = now_ms();
-        const size_t n = (size_t)r->count, stride = (size_t)r->stride;
-        // one page-locked block for the seven arrays, recycled through the context's pool
-        const size_t o_mol = 0, o_tpl = o_mol + align64(n * 4), o_atoms = o_tpl + align64(n * 4),
-                     o_rmsd = o_atoms + align64(n * stride * 4), o_rot = o_rmsd + align64(n * 8),
-                     o_c0 = o_rot + align64(n * 72), o_c1 = o_c0 + align64(n * 24), total = o_c1 + align64(n * 24) + 64;
-        for (size_t i = 0; i < c->pin_pool.size(); i++)
-            if (c->pin_pool[i].second >= total) {
-                r->block = c->pin_pool[i].first; r->block_bytes = c->pin_pool[i].second;
-                c->pin_pool.erase(c->pin_pool.begin() + i);
-                break;
-            }
-        if (!r->block) {
-            const size_t want = total + total / 4;
-            CU(cudaMallocHost(&r->block, want));
-            r->block_bytes = want;
-        }
-        char *base = static_cast<char *>(r->block);
-        r->mol = reinterpret_cast<int32_t *>(base + o_mol); r->tpl = reinterpret_cast<int32_t *>(base + o_tpl);
-        r->atoms = reinterpret_cast<int32_t *>(base + o_atoms); r->rmsd = reinterpret_cast<double *>(base + o_rmsd);
-        r->rot = reinterpret_cast<double *>(base + o_rot); r->c0 = reinterpret_cast<double *>(base + o_c0);
-        r->c1 = reinterpret_cast<double *>(base + o_c1);
-        if (n) {
-            cudaStream_t st = c->stream;
-            CU(cudaMemcpyAsync(r->mol, c->f_mol.p, n * sizeof(int), cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(r->tpl, c->f_tpl.p, n * sizeof(int), cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(r->atoms, c->f_atoms.p, n * stride * sizeof(int), cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(r->rmsd, c->f_rmsd.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(r->rot, c->f_rot.p, n * 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(r->c0, c->f_c0.p, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(r->c1, c->f_c1.p, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
-        }
-        r->kept = (long long)n;
-        if (r->best_match && n) {
-            // keep the smallest RMSD per (molecule, template), compacting in place; ties -> first
-            // in canonical order (the reference keeps the first in ITS iteration order, _jess.pyx:2238)
-            size_t w = 0;
-            for (size_t i = 0; i < n;) {
-                size_t j = i, best = i;
-                while (j < n && r->mol[j] == r->mol[i] && r->tpl[j] == r->tpl[i]) {
-                    if (r->rmsd[j] < r->rmsd[best]) best = j;
-                    j++;
-                }
-                r->mol[w] = r->mol[best]; r->tpl[w] = r->tpl[best]; r->rmsd[w] = r->rmsd[best];
-                memmove(&r->atoms[w * stride], &r->atoms[best * stride], stride * sizeof(int32_t));
-                memmove(&r->rot[w * 9], &r->rot[best * 9], 9 * sizeof(double));
-                memmove(&r->c0[w * 3], &r->c0[best * 3], 3 * sizeof(double));
-                memmove(&r->c1[w * 3], &r->c1[best * 3], 3 * sizeof(double));
-                w++;
-                i = j;
-            }
-            r->kept = (long long)w;
-        }
-        r->fetched = true;
+        const size_t n = (size_t)r->count;
+        int rc = result_alloc_block(r, n);
+        if (rc != JB_OK) return rc;
+        rc = result_copy_range(r, 0, n, c->stream);
+        if (rc != JB_OK) return rc;
+        CU(cudaStreamSynchronize(c->stream));
+        result_finalize(r);
         if (c->debug) fprintf(stderr, "[jb] fetch %zu hits: %.2f ms\n", n, now_ms() - t_0);
     }
     out->count = (int64_t)r->kept;
@@ -1130,16 +1197,101 @@ extern "C" void jb_result_free(jb_result *r)
     delete r;
 }
 
+// jb_query_host for large batches: the structures are processed in slices so that the host ->
+// device copy of slice k+1 (copy stream, double-buffered staging) and the device -> host copy of
+// slice k-1's hits overlap the kernels of slice k (compute stream).  Record order is unchanged:
+// slices are ascending runs of structures.
+static int query_host_pipelined(jb_context *c, const jb_templates *t, const jb_molecule_batch *b,
+                                const jb_query_params *q, int n_slices, jb_result **out, jb_hits *hits)
+{
+    if (!c->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < 2; i++)
+        if (!c->slice_mol[i]) c->slice_mol[i] = new jb_molecules();
+    // slice boundaries: equal shares of the atoms
+    const int M = b->n_molecules;
+    const long long NA = b->atom_offset[M];
+    std::vector<int> cut{ 0 };
+    for (int k = 1; k < n_slices; k++) {
+        const long long want = NA * k / n_slices;
+        int m = (int)(std::lower_bound(b->atom_offset, b->atom_offset + M + 1, want) - b->atom_offset);
+        m = std::min(std::max(m, cut.back() + 1), M - (n_slices - k));
+        cut.push_back(m);
+    }
+    cut.push_back(M);
+    jb_result *res = new jb_result();
+    res->ctx = c;
+    res->stride = std::max(t->nmax, 1);
+    res->best_match = q->all_tuples ? 0 : q->best_match;
+    res->n_templates = t->T;
+    int rc = result_alloc_block(res, (size_t)std::max<long long>(c->last_hits + c->last_hits / 8, 1 << 16));
+    bool direct = rc == JB_OK;                        // hits still fit the block laid out above
+    size_t copied = 0;
+    if (rc == JB_OK) rc = stage_molecules(c, c->slice_mol[0], b, cut[0], cut[1], c->copy_stream);
+    if (rc == JB_OK) CU(cudaEventRecord(c->ev_up[0], c->copy_stream));
+    for (int k = 0; k < n_slices && rc == JB_OK; k++) {
+        jb_molecules *cur = c->slice_mol[k & 1];
+        if (k + 1 < n_slices) {
+            rc = stage_molecules(c, c->slice_mol[(k + 1) & 1], b, cut[k + 1], cut[k + 2], c->copy_stream);
+            if (rc != JB_OK) break;
+            CU(cudaEventRecord(c->ev_up[(k + 1) & 1], c->copy_stream));
+        }
+        CU(cudaStreamWaitEvent(c->stream, c->ev_up[k & 1], 0));
+        rc = prepare_molecules(c, cur, c->stream);
+        if (rc == JB_OK) rc = query_run_impl(c, t, cur, q, res, cut[k]);       // returns with the slice's kernels done
+        if (rc != JB_OK) break;
+        if (direct && (size_t)res->count <= res->block_cap) {
+            rc = result_copy_range(res, copied, (size_t)res->count, c->copy_stream);
+            copied = (size_t)res->count;
+        } else direct = false;
+    }
+    if (rc == JB_OK) CU(cudaStreamSynchronize(c->copy_stream));
+    if (rc == JB_OK && !direct) {                     // more hits than expected: one plain fetch of everything
+        rc = result_alloc_block(res, (size_t)res->count);
+        if (rc == JB_OK) rc = result_copy_range(res, 0, (size_t)res->count, c->stream);
+        if (rc == JB_OK) CU(cudaStreamSynchronize(c->stream));
+    }
+    if (rc != JB_OK) {
+        cudaStreamSynchronize(c->copy_stream);
+        cudaStreamSynchronize(c->stream);
+        jb_result_free(res);
+        return rc;
+    }
+    res->stats.hits = (int64_t)res->count;
+    c->last_hits = res->count;
+    result_finalize(res);
+    *out = res;
+    return jb_result_fetch(res, hits);
+}
+
 extern "C" int jb_query_host(jb_context *c, const jb_templates *t, const jb_molecule_batch *b, const jb_query_params *q,
                              jb_result **out, jb_hits *hits)
 {
     if (!c || !b || !out || !hits) return fail(JB_ERR_INVALID, "jb_query_host: NULL argument");
     *out = nullptr;
+    if (!t || !q || t->ctx != c) return fail(JB_ERR_INVALID, "jb_query_host: bad templates/params");
+    if (q->ignore_chain < 0 || q->ignore_chain > 2) return fail(JB_ERR_INVALID, "invalid ignore_chain %d", q->ignore_chain);
+    if (q->reorder < 0 || q->reorder > 2) return fail(JB_ERR_INVALID, "invalid reorder %d", q->reorder);
+    if (q->hit_order < 0 || q->hit_order > 2) return fail(JB_ERR_INVALID, "invalid hit_order %d", q->hit_order);
     CU(cudaSetDevice(c->device));
+    if (b->n_molecules > 0 && t->T > 0 && t->TA > 0 && c->pipeline_slices != 1) {
+        const long long NA = b->atom_offset[b->n_molecules];
+        // auto: slicing costs launches and host syncs per slice (measured on cfg3: 4 slices +1.0 ms,
+        // 2 slices -0.25 ms), so only the copies worth hiding are pipelined: 2 slices for a large
+        // upload, 4 when the previous call on this context returned a large hit volume
+        const long long out_bytes = c->last_hits * (long long)(std::max(t->nmax, 1) * 4 + 136);
+        int n_slices = c->pipeline_slices > 1 ? c->pipeline_slices
+                       : out_bytes >= (256ll << 20) ? 4 : NA >= 1000000 ? 2 : 1;
+        n_slices = std::min(n_slices, b->n_molecules / 16);
+        if (n_slices >= 2) return query_host_pipelined(c, t, b, q, n_slices, out, hits);
+    }
     if (!c->scratch_mol) c->scratch_mol = new jb_molecules();
     int rc = fill_molecules(c, c->scratch_mol, b);      // grow-only device staging owned by the context
     if (rc != JB_OK) return rc;
     rc = jb_query_run(c, t, c->scratch_mol, q, out);
+    if (rc == JB_OK) c->last_hits = (*out)->count;
     if (rc == JB_OK) rc = jb_result_fetch(*out, hits);
     if (rc != JB_OK && *out) { jb_result_free(*out); *out = nullptr; }
     return rc;
