@@ -232,7 +232,7 @@ def format_atoms_pdb(records, xyz=None) -> str:
     got = lib.jb_format_atoms_pdb(records.ctypes.data, n, xp, buf, len(buf))
     if got < 0:
         _check(int(got))
-    return buf.raw[:got].decode("ascii", "replace") if got > (1 << 12) else buf.value.decode("ascii", "replace")
+    return C.string_at(buf, got).decode("ascii", "replace")
 
 
 _default = {}

@@ -466,6 +466,30 @@ static int prepare_molecules(jb_context *c, jb_molecules *m, cudaStream_t st)
     if (e == cudaSuccess && M > 0) {
         long long amax = 0;
         for (int i = 0; i < M; i++) amax = std::max(amax, m->atom_off[i + 1] - m->atom_off[i]);
+        if (amax > 16384 && m->NA < (1ll << 32)) {
+            // a very large structure in the batch: one device-wide radix sort (kernels.cuh, K0c)
+            const size_t n = (size_t)m->NA;
+            e = m->sort_scratch.ensure(n * (2 * sizeof(u64) + 2 * sizeof(unsigned)), st);
+            u64 *key = m->sort_scratch.as<u64>(), *key2 = key + n;
+            unsigned *idx = reinterpret_cast<unsigned *>(key2 + n), *idx2 = idx + n;
+            int mbits = 1;
+            while ((1ll << mbits) < M) mbits++;
+            size_t tmp = 0;
+            if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(nullptr, tmp, key, key2, idx, idx2, (int)n, 0, 32 + mbits, st);
+            if (e == cudaSuccess) e = c->q_cub.ensure(tmp, st);
+            if (e == cudaSuccess) {
+                k_sort_keys<<<M, kSortThreads, 0, st>>>(m->d_off.as<long long>(), m->atoms.as<AtomRec>(), m->ext.as<MolExt>(), key, idx);
+                e = cub::DeviceRadixSort::SortPairs(c->q_cub.p, tmp, key, key2, idx, idx2, (int)n, 0, 32 + mbits, st);
+            }
+            if (e == cudaSuccess) {
+                k_sorted_view<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((long long)n, key2, idx2, m->d_off.as<long long>(),
+                                                                           m->atoms.as<AtomRec>(), m->name.as<uint32_t>(),
+                                                                           m->res.as<uint32_t>(), m->ext.as<MolExt>(),
+                                                                           m->srec.as<float4>(), m->sname.as<uint32_t>(),
+                                                                           m->sres.as<uint32_t>());
+                e = cudaGetLastError();
+            }
+        } else {
         long long npad = 1;
         while (npad < amax) npad <<= 1;
         const int smem_keys = (int)std::min<long long>(npad, 16384);      // 8-byte keys: <= 128 KiB
@@ -480,6 +504,7 @@ static int prepare_molecules(jb_context *c, jb_molecules *m, cudaStream_t st)
                                                         m->sname.as<uint32_t>(), m->sres.as<uint32_t>(),
                                                         m->sort_scratch.as<u64>(), smem_keys);
             e = cudaGetLastError();
+        }
         }
     }
     if (e != cudaSuccess)

@@ -316,6 +316,56 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_atoms(const long long *at
     }
 }
 
+// ---- K0c: the same view for batches holding very large structures --------------------------
+// k_sort_atoms sorts one structure per CTA; beyond 16,384 atoms its keys leave shared memory and
+// a single CTA runs ~130 bitonic passes over global memory (5 ms for the 58,870-atom structure of
+// BASELINE config 2).  Such batches are sorted by ONE device-wide radix sort over the keys
+// (structure | orderable x): k_sort_keys (frame + keys), cub::DeviceRadixSort, k_sorted_view.
+__global__ void __launch_bounds__(kSortThreads) k_sort_keys(const long long *atom_off, const AtomRec *atoms, MolExt *ext,
+                                                            u64 *key, unsigned *idx)
+{
+    __shared__ double sh_ext[kSortThreads / 32];
+    const int m = blockIdx.x;
+    const long long a0 = atom_off[m], a1 = atom_off[m + 1];
+    const int na = (int)(a1 - a0);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    double ox = 0.0, oy = 0.0, oz = 0.0, e = 0.0;
+    if (na > 0) { const AtomRec o = atoms[a0]; ox = o.x; oy = o.y; oz = o.z; }
+    for (int i = tid; i < na; i += kSortThreads) {
+        const AtomRec ar = atoms[a0 + i];
+        e = fmax(e, fmax(fabs(__dsub_rn(ar.x, ox)), fmax(fabs(__dsub_rn(ar.y, oy)), fabs(__dsub_rn(ar.z, oz)))));
+        const float fx = __double2float_rn(__dsub_rn(ar.x, ox));
+        key[a0 + i] = ((u64)(unsigned)m << 32) | (u64)float_orderable(fx);
+        idx[a0 + i] = (unsigned)(a0 + i);
+    }
+    for (int o = 16; o > 0; o >>= 1) e = fmax(e, __shfl_xor_sync(0xffffffffu, e, o));
+    if (lane == 0) sh_ext[w] = e;
+    __syncthreads();
+    if (tid == 0) {
+        double v = 0.0;
+        for (int i = 0; i < kSortThreads / 32; i++) v = fmax(v, sh_ext[i]);
+        MolExt me; me.ox = ox; me.oy = oy; me.oz = oz; me.ext = v;
+        ext[m] = me;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_sorted_view(long long n, const u64 *skey, const unsigned *sidx,
+                                                     const long long *atom_off, const AtomRec *atoms, const uint32_t *name,
+                                                     const uint32_t *res, const MolExt *ext, float4 *srec, uint32_t *sname,
+                                                     uint32_t *sres)
+{
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int m = (int)(skey[j] >> 32);
+    const long long g = (long long)sidx[j];
+    const AtomRec ar = atoms[g];
+    const MolExt me = ext[m];
+    srec[j] = make_float4(__double2float_rn(__dsub_rn(ar.x, me.ox)), __double2float_rn(__dsub_rn(ar.y, me.oy)),
+                          __double2float_rn(__dsub_rn(ar.z, me.oz)), __int_as_float((int)(g - atom_off[m])));
+    sname[j] = name[g];
+    sres[j] = res[g];
+}
+
 // ---- K1: candidate lists ------------------------------------------------------
 // One CTA per structure, atoms visited in x-sorted order.  Warp w owns a contiguous
 // slice; pass 1 counts matches per (warp, spec) in shared memory, a scan over warps

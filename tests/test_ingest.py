@@ -77,3 +77,37 @@ def test_native_parser_rejects_mmcif_and_handles_empty():
     assert len(Molecule.loads(b"")) == 0
     assert len(Molecule.load(io.BytesIO(b"REMARK only\n"))) == 0
     assert len(Molecule.load(io.StringIO("ATOM      1  N   MET A   1      27.340  24.430   2.614\n"))) == 1
+
+
+def test_native_packing_matches_numpy_packing():
+    """jb_molecules_pack (csrc/ingest.cu) fills the SoA staging image exactly like slicing the
+    molecules' record arrays field by field (`Molecule._packed`)."""
+    from pyjess_b200._tables import MoleculeBatch
+    mols = [Molecule.load(os.path.join(DATA, f)) for f in FILES] + [Molecule([])]
+    for kw in ({}, {"serial": True}, {"serial": True, "pool": {}}):
+        b = MoleculeBatch(mols, **kw)
+        assert b.atom_offset.tolist() == np.cumsum([0] + [len(m) for m in mols]).tolist()
+        for field, key in (("x", "x"), ("y", "y"), ("z", "z"), ("name", "name"), ("resname", "resname"),
+                           ("resseq", "resseq"), ("chain", "chain")):
+            ref = np.concatenate([m._packed()[key] for m in mols])
+            assert np.array_equal(getattr(b, field)[:b.n_atoms], ref), field
+        if kw.get("serial"):
+            assert np.array_equal(b.serial[:b.n_atoms], np.concatenate([m._atoms["serial"] for m in mols]))
+        else:
+            assert b.serial is None
+
+
+def test_native_atom_formatter_matches_the_reference_sprintf():
+    """jb_format_atoms_pdb against the Python restatement of the reference's sprintf
+    (`_format_atom`, pinned to the reference's own Hit.dump text by tests/test_api_*.py)."""
+    from pyjess_b200 import _capi
+    from pyjess_b200._model import _format_atom
+    recs = Molecule.load(os.path.join(DATA, "1AMY.pdb"))._atoms[:300].copy()
+    recs["altLoc"][5] = 0
+    recs["occupancy"][7] = 0.005
+    recs["tempFactor"][9] = 99.995
+    recs["serial"][11] = -42
+    xyz = recs["x"] * 1.000001 + 0.0005
+    assert _capi.format_atoms_pdb(recs, xyz) == "".join(_format_atom(recs[k], xyz[k]) for k in range(len(recs)))
+    assert _capi.format_atoms_pdb(recs) == "".join(_format_atom(recs[k], recs["x"][k]) for k in range(len(recs)))
+    assert _capi.format_atoms_pdb(recs[:0]) == ""
