@@ -139,7 +139,7 @@ struct jb_context {
 
 struct jb_templates {
     jb_context *ctx = nullptr;
-    int T = 0, TA = 0, S = 0, nmax = 0;
+    int T = 0, TA = 0, S = 0, nmax = 0, nmin = 1 << 30;
     std::vector<int> atom_off;
     DevBuf d_atom_off, d_spec, d_resseq, d_chain, d_pos, d_weight, d_dist_off, d_dist, d_shell, d_vol;
     DevBuf s_code, s_noff, s_nraw, s_nup, s_roff, s_rup;
@@ -303,6 +303,7 @@ extern "C" int jb_templates_create(jb_context *c, const jb_template_table *tb, j
                         JB_MAX_TEMPLATE_ATOMS);
         }
         t->nmax = std::max(t->nmax, n);
+        t->nmin = std::min(t->nmin, n);
     }
     // de-duplicate atom specs: (mode, set of names it reads, set of residue names it reads)
     std::map<std::vector<uint32_t>, int> seen;
@@ -564,15 +565,16 @@ template <int G, bool STATS> static cudaError_t launch_expand(int grid, size_t s
 }
 
 // level-specialised kernel (expand_lv.cuh): levels 1..kMaxLv, G lanes per partial match
-template <int L, int G> static cudaError_t launch_expand_lv(int sm_count, cudaStream_t st, const ExpandArgs &a, int stats)
+template <int L, int G, bool ROOT = false>
+static cudaError_t launch_expand_lv(int sm_count, cudaStream_t st, const ExpandArgs &a, int stats)
 {
     constexpr size_t smem = expand_lv_smem<L, G>();
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_expand_lv<L, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_expand_lv<L, G, ROOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / smem));
-    k_expand_lv<L, G><<<sm_count * per_sm, kExpandThreads, smem, st>>>(a, stats);
+    k_expand_lv<L, G, ROOT><<<sm_count * per_sm, kExpandThreads, smem, st>>>(a, stats);
     return cudaGetLastError();
 }
 
@@ -648,7 +650,9 @@ static int build_reference_keys(jb_context *c, const jb_templates *t, const jb_m
         k_olist_ranks<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
             (long long)n, t->OS, c->q_keyB.as<u64>(), c->q_perm.as<unsigned>(), c->q_keyA2.as<u64>(), ooff, MT.atom_off,
             MT.atoms, c->q_setpos.as<unsigned>(), c->q_coords.as<double>(), c->q_kdidx.as<int>());
-        k_kd_order<<<(unsigned)((nl + 127) / 128), 128, 0, st>>>(nl, ooff, c->q_coords.as<double>(), c->q_kdidx.as<int>(),
+        // one thread per list, lists in memory order (a length-sorted schedule was measured 40 % slower:
+        // the threads of a warp then walk lists of different structures and lose their shared cache lines)
+        k_kd_order<<<(unsigned)((nl + 127) / 128), 128, 0, st>>>(nl, nullptr, ooff, c->q_coords.as<double>(), c->q_kdidx.as<int>(),
                                                                  c->q_perm.as<unsigned>(), c->q_kdrank.as<unsigned>());
         CU(cudaGetLastError());
         S.launches += 6;   // + the radix sort passes (library kernels)
@@ -822,6 +826,18 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
             // lanes per partial match: the configured G, widened at deep levels so that at
             // least two CTAs per SM fit their staging areas in shared memory
             int g = c->group;
+            // levels 0 + 1 fused: the roots are dealt out of the candidate lists by the level-1 kernel
+            // itself (needs every template to have >= 2 atoms: a single-atom root is a complete tuple)
+            const bool fused_root = t->nmin >= 2 && !c->legacy && !getenv("JB_NO_ROOT_FUSION");
+            if (l == 0 && fused_root) continue;
+            if (l == 1 && fused_root) {
+                A.in = nullptr; A.in_count = &dc->live_pairs; A.in_cap = pairs;
+                const int stats = c->debug != 0;
+                if (g <= 1) CU((launch_expand_lv<1, 1, true>(c->sm_count, st, A, stats)));
+                else if (g == 2) CU((launch_expand_lv<1, 2, true>(c->sm_count, st, A, stats)));
+                else CU((launch_expand_lv<1, 4, true>(c->sm_count, st, A, stats)));
+                continue;
+            }
             if (l >= 1 && l <= kMaxLv && !c->legacy) {
                 CU(dispatch_expand_lv(l, g, c->sm_count, st, A, c->debug != 0));
                 continue;
@@ -1308,7 +1324,8 @@ extern "C" int jb_query_host(jb_context *c, const jb_templates *t, const jb_mole
         // upload, 4 when the previous call on this context returned a large hit volume
         const long long out_bytes = c->last_hits * (long long)(std::max(t->nmax, 1) * 4 + 136);
         int n_slices = c->pipeline_slices > 1 ? c->pipeline_slices
-                       : out_bytes >= (256ll << 20) ? 4 : NA >= 1000000 ? 2 : 1;
+                       : out_bytes >= (256ll << 20) ? 4 : (NA >= 1000000 && q->hit_order == JB_ORDER_CANONICAL) ? 2 : 1;
+        // (the rank tables of the reference hit order are rebuilt per slice: not worth two slices)
         n_slices = std::min(n_slices, b->n_molecules / 16);
         if (n_slices >= 2) return query_host_pipelined(c, t, b, q, n_slices, out, hits);
     }

@@ -56,9 +56,13 @@ template <int L, int G> struct alignas(16) LvWarp {   // per-warp shared memory
 
 template <int L, int G> constexpr size_t expand_lv_smem() { return sizeof(LvWarp<L, G>) * kExpandWarps; }
 
-template <int L, int G>
+// ROOT (level 1 only): the level-0 launch and the level-1 frontier disappear -- every warp walks
+// its own live pairs (pair = warp id, + number of warps, ...) and deals the candidates of the first
+// scan atom straight into its batches, whatever pair they belong to.  A.in_count = live pairs.
+template <int L, int G, bool ROOT = false>
 __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_lv(const ExpandArgs A, const int stats)
 {
+    static_assert(!ROOT || L == 1, "root mode feeds level 1");
     constexpr int IPW = 32 / G;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int in_stride = L + 1, out_stride = L + 2;
@@ -151,17 +155,46 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_lv(const ExpandArg
         }
     };
 
-    for (long long base_item = ((long long)blockIdx.x * kExpandWarps + warp) * IPW; base_item < (long long)n_in;
+    long long my_pair = (long long)blockIdx.x * kExpandWarps + warp;      // ROOT: next pair of this warp
+    int root_j = 0, root_cnt = 0;
+    long long root_off = 0;
+    bool pair_loaded = false;
+    unsigned n_roots = 0;
+    for (long long base_item = ((long long)blockIdx.x * kExpandWarps + warp) * IPW; ROOT || base_item < (long long)n_in;
          base_item += total_warps * IPW) {
         const long long item = base_item + grp;
-        const bool valid = item < (long long)n_in;
+        bool valid = item < (long long)n_in;
+        int root_lp = 0, root_a = 0;
+        if (ROOT) {
+            int filled = 0;
+            valid = false;
+            while (filled < IPW && my_pair < (long long)n_in) {            // all conditions are warp uniform
+                if (!pair_loaded) {
+                    const PairRec *rec = A.recs + my_pair;
+                    const CandHead hd = A.head[(long long)rec->m * A.n_specs + rec->spec[0]];
+                    root_cnt = hd.cnt; root_off = hd.off; root_j = 0;
+                    pair_loaded = true;
+                }
+                const int take = min(root_cnt - root_j, IPW - filled);
+                if (grp >= filled && grp < filled + take) {
+                    valid = true;
+                    root_lp = (int)my_pair;
+                    root_a = __float_as_int(__ldg(&A.cand[root_off + root_j + (grp - filled)].w));
+                }
+                filled += take;
+                root_j += take;
+                if (root_j >= root_cnt) { my_pair += total_warps; pair_loaded = false; }
+            }
+            if (filled == 0) break;
+            if (valid && gl == 0) n_roots++;
+        }
         int cnt = 0;
         long long coff = 0, lidx = 0;
         float hx0 = 0.f, hinv = 0.f;
         float bx0 = -INF, by0 = -INF, bz0 = -INF, bx1 = INF, by1 = INF, bz1 = INF;
         if (valid) {
-            const int *it = A.in + item * in_stride;
-            const int lp = it[0];
+            const int *it = ROOT ? nullptr : A.in + item * in_stride;
+            const int lp = ROOT ? root_lp : it[0];
             const PairRec *rec = A.recs + lp;
             const int4 h0 = *reinterpret_cast<const int4 *>(rec);            // m, t, ta0, n
             const longlong2 h1 = *reinterpret_cast<const longlong2 *>(&rec->abase);
@@ -182,7 +215,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_lv(const ExpandArg
             for (int jj = 0; jj < (L + G - 1) / G; jj++) {
                 const int j = jj * G + gl;
                 if (j < L) {
-                    const int a = it[1 + j];
+                    const int a = ROOT ? root_a : it[1 + j];
                     const AtomRec ar = A.atoms[h1.x + a];
                     const ShellRec sh = A.shell[h1.y + (long long)rec->order[j] * n + k];
                     ChainRec c;
@@ -343,6 +376,11 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_lv(const ExpandArg
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) n_cand += __shfl_down_sync(FULL, n_cand, o);
     if (lane == 0 && n_cand) atomicAdd(&A.ctr->cand_tests, n_cand);
+    if (ROOT) {   // the roots are the partial matches with one atom: F_1 of the work counters
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n_roots += __shfl_down_sync(FULL, n_roots, o);
+        if (lane == 0 && n_roots) atomicAdd(&A.ctr->level[1], (u64)n_roots);
+    }
 }
 
 }  // namespace jb

@@ -169,11 +169,12 @@ __device__ void kd_qselect(int *idx, int n, int k, const double *u, int axis)
 // qselect the median position n/2 on the current axis, recurse on [0, n/2) and [n/2, n) with
 // the next axis.  The final index array is the left-to-right leaf order; KdTreeQuery_next
 // visits leaves right to left, so rank = count - 1 - leaf position.
-__global__ void __launch_bounds__(128) k_kd_order(long long n_lists, const unsigned *ooff, const double *coords,
-                                                  int *kd_idx, const unsigned *perm, unsigned *kd_rank)
+__global__ void __launch_bounds__(128) k_kd_order(long long n_lists, const unsigned *schedule, const unsigned *ooff,
+                                                  const double *coords, int *kd_idx, const unsigned *perm, unsigned *kd_rank)
 {
-    const long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (L >= n_lists) return;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_lists) return;
+    const long long L = schedule ? (long long)schedule[t] : t;
     const unsigned o0 = ooff[L], cnt = ooff[L + 1] - o0;
     if (cnt == 0) return;
     int *idx = kd_idx + o0;
