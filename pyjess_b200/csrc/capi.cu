@@ -883,7 +883,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
                         l == 0 ? hc.live_pairs : hc.level[l], hc.level[l + 1], ms);
             }
         }
-        S.launches += 4 + t->nmax;
+        S.launches += 4 + t->nmax - ((t->nmin >= 2 && !c->legacy && !getenv("JB_NO_ROOT_FUSION")) ? 1 : 0);
         {
             float ms[4] = { 0, 0, 0, 0 };
             for (int i = 0; i < 4; i++) CU(cudaEventElapsedTime(&ms[i], c->evs[i], c->evs[i + 1]));
