@@ -118,3 +118,32 @@ def test_every_hit_ordering_path_gives_the_same_records(engine, monkeypatch, env
     assert base.count == other.count > 1000
     for a, b in zip(base.arrays(), other.arrays()):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("hit_order", ["canonical", "reference"])
+def test_pipelined_host_path_gives_the_same_records(engine, monkeypatch, hit_order):
+    """jb_query_host in slices (H2D / kernels / D2H overlapped on a copy stream) against the
+    single-shot path: identical tables, for both record orders, incl. best_match."""
+    from pyjess_b200 import _capi, synth
+    from pyjess_b200._tables import query_params
+    tpl, mols, thr, kw = synth.workload("cfg3", scale=0.1)
+    tpl = tpl[:40]
+    monkeypatch.setenv("JB_PIPELINE", "3")
+    sliced = _capi.Context(0)            # reads JB_PIPELINE at creation
+    try:
+        for best in (False, True):
+            params = query_params(*thr, hit_order=hit_order, best_match=best, **kw)
+            tables = []
+            for ctx in (engine, sliced):
+                dev = _capi.DeviceTemplates(ctx, TemplateTable(tpl))
+                try:
+                    for _ in range(2):   # second call: the pinned block is sized from the first one
+                        table, stats = _capi.query_host(ctx, dev, MoleculeBatch(mols, serial=True), params)
+                    tables.append(table)
+                finally:
+                    dev.close()
+            assert tables[0].count == tables[1].count > 50
+            for a, b in zip(tables[0].arrays(), tables[1].arrays()):
+                assert np.array_equal(a, b)
+    finally:
+        sliced.close()
