@@ -41,7 +41,11 @@ constexpr int kQueueLv = 32 + 8 * kChunk;   // survivor queue: < 32 carried + 8 
 
 template <int L, int G> struct alignas(16) LvWarp {   // per-warp shared memory
     static constexpr int IPW = 32 / G;                // partial matches per batch
-    ChainRec chain[IPW * L];                          // placed atoms + shells towards the new atom
+    // placed atoms + shells towards the new atom, one array per field and [atom][partial match]: the drain's
+    // lanes read the records of DIFFERENT partial matches, which the 48-byte ChainRec layout served with
+    // 2- to 16-way bank conflicts depending on L (stride L x 12 words)
+    double cx[L][IPW], cy[L][IPW], cz[L][IPW], clo2[L][IPW], chi2[L][IPW];
+    int cres[L][IPW], cflag[L][IPW];
     float4 blo[IPW], bhi[IPW];                        // join box (outward rounded)
     long long cbase[IPW];                             // first record of the x range
     long long abase[IPW];                             // first atom of the structure
@@ -50,7 +54,7 @@ template <int L, int G> struct alignas(16) LvWarp {   // per-warp shared memory
     int cstart[IPW];                                  // first chunk of the partial match (exclusive scan)
     int2 queue[kQueueLv];                             // box survivors: (atom, partial match)
     unsigned char owner[kOwnerCap];                   // chunk -> partial match of the batch (short batches)
-    int chain_atom[IPW * L];
+    int chain_atom[L][IPW];
     int stage[kStageItems * (L + 2)];                 // accepted extensions awaiting the flush
 };
 
@@ -92,19 +96,18 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_lv(const ExpandArg
         const int2 mt = W.meta[g];
         if (ok) {
             const AtomRec p = A.atoms[W.abase[g] + a];
-            const ChainRec *ch = W.chain + g * L;
             // _Annulus_po (eff:Annulus.h:54-68): ((dx^2 + dy^2) + dz^2), centre - point
 #pragma unroll
             for (int j = 0; j < L; j++) {
-                const double t0 = __dsub_rn(ch[j].x, p.x), t1 = __dsub_rn(ch[j].y, p.y), t2 = __dsub_rn(ch[j].z, p.z);
+                const double t0 = __dsub_rn(W.cx[j][g], p.x), t1 = __dsub_rn(W.cy[j][g], p.y), t2 = __dsub_rn(W.cz[j][g], p.z);
                 const double s = __dadd_rn(__dadd_rn(__dmul_rn(t0, t0), __dmul_rn(t1, t1)), __dmul_rn(t2, t2));
-                if (s < ch[j].lo2 || s > ch[j].hi2) { ok = false; break; }
+                if (s < W.clo2[j][g] || s > W.chi2[j][g]) { ok = false; break; }
             }
             if (ok) {
 #pragma unroll
                 for (int j = 0; j < L; j++) {
-                    const int f = ch[j].flag;
-                    if (!pair_consistent(A.ignore_chain, (f & 0xff) == p.chain, (f & 0x100) != 0, ch[j].res == p.resseq,
+                    const int f = W.cflag[j][g];
+                    if (!pair_consistent(A.ignore_chain, (f & 0xff) == p.chain, (f & 0x100) != 0, W.cres[j][g] == p.resseq,
                                          (f & 0x200) != 0)) { ok = false; break; }
                 }
             }
@@ -126,7 +129,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_lv(const ExpandArg
                     int *dst = A.tuples + slot * A.tuple_stride;
                     dst[0] = mt.x;
 #pragma unroll
-                    for (int j = 0; j < L; j++) dst[1 + j] = W.chain_atom[g * L + j];
+                    for (int j = 0; j < L; j++) dst[1 + j] = W.chain_atom[j][g];
                     dst[1 + L] = a;
                 }
             }
@@ -136,7 +139,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_lv(const ExpandArg
                 int *dst = W.stage + (fill + __popc(nm & lt)) * out_stride;
                 dst[0] = mt.x;
 #pragma unroll
-                for (int j = 0; j < L; j++) dst[1 + j] = W.chain_atom[g * L + j];
+                for (int j = 0; j < L; j++) dst[1 + j] = W.chain_atom[j][g];
                 dst[1 + L] = a;
             }
             fill += __popc(nm);
@@ -218,11 +221,10 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_lv(const ExpandArg
                     const int a = ROOT ? root_a : it[1 + j];
                     const AtomRec ar = A.atoms[h1.x + a];
                     const ShellRec sh = A.shell[h1.y + (long long)rec->order[j] * n + k];
-                    ChainRec c;
-                    c.x = ar.x; c.y = ar.y; c.z = ar.z; c.lo2 = sh.lo2; c.hi2 = sh.hi2;
-                    c.res = ar.resseq; c.flag = ar.chain | (sh.flags << 8);
-                    W.chain[grp * L + j] = c;
-                    W.chain_atom[grp * L + j] = a;
+                    W.cx[j][grp] = ar.x; W.cy[j][grp] = ar.y; W.cz[j][grp] = ar.z;
+                    W.clo2[j][grp] = sh.lo2; W.chi2[j][grp] = sh.hi2;
+                    W.cres[j][grp] = ar.resseq; W.cflag[j][grp] = ar.chain | (sh.flags << 8);
+                    W.chain_atom[j][grp] = a;
                     const double dx = __dsub_rn(ar.x, me.ox), dy = __dsub_rn(ar.y, me.oy), dz = __dsub_rn(ar.z, me.oz);
                     const float rb = sh.rb;
                     bx0 = fmaxf(bx0, __fsub_rd(__fsub_rd(__double2float_rd(dx), rb), err));
