@@ -1,22 +1,31 @@
 // kernels.cuh -- sm_100a device code of the template-query engine.
 //
 // One kernel per stage of the reference hot path:
+//   k_pack_atoms, k_sort_atoms (or k_sort_keys + a device-wide radix sort + k_sorted_view
+//                     for batches with structures > 16,384 atoms): 32-byte atom records and
+//                     the x-sorted FP32 view, once per upload (stand in for the per-pair
+//                     k-d tree builds, eff:KdTree.c:145-186,343-423)
 //   k_classify        atoms x atom-specs -> per-(structure, spec) candidate
 //                     lists (replaces TessTemplate_candidates, ResIndex_*,
 //                     TessAtom_match: eff:TessTemplate.c:141-201,
 //                     eff:ResIndex.c:28-153, eff:TessAtom.c:238-449)
+//   k_xindex          32-bucket x index of every candidate list (the range query of
+//                     KdTreeQuery_next becomes a table look-up + a short scan)
 //   k_shells          squared annulus radii per ordered template-atom pair
 //                     (eff:Scanner.c:275-290, eff:Annulus.c:40-67)
-//   k_pairs           per (structure, template): liveness + scan order
+//   k_order, k_pairs  per (structure, template): liveness + scan order
 //                     (Scanner_reuse, eff:Scanner.c:106-183)
 //   k_expand<G>       level-synchronous frontier expansion, G lanes per
 //                     partial match (replaces Scanner_next + KdTreeQuery_next
 //                     + _Join_ipo/_Annulus_po + TessTemplate_check:
 //                     eff:Scanner.c:193-304, eff:KdTree.c:238-296,
-//                     eff:Annulus.h:54-68, eff:TessTemplate.c:78-119)
+//                     eff:Annulus.h:54-68, eff:TessTemplate.c:78-119); run-time level,
+//                     used beyond level 12 and for sets with single-atom templates --
+//                     the hot levels run k_expand_lv<L,G,ROOT> (expand_lv.cuh)
 //   k_superpose       batched FP64 superposition + RMSD filter + compaction
 //                     (vendor/jess/src/Super.c:139-538, eff:Jess.c:176-195,
 //                     src/pyjess/_jess.pyx:2238-2257)
+// hits.cuh orders the hit records, order.cuh rebuilds the reference's iteration order.
 //
 // Nothing here is a dense contraction: no tensor cores, no TMEM.  All FP64
 // decisions use explicit round-to-nearest intrinsics (and the TU is built
