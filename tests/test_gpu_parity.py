@@ -147,3 +147,38 @@ def test_pipelined_host_path_gives_the_same_records(engine, monkeypatch, hit_ord
                 assert np.array_equal(a, b)
     finally:
         sliced.close()
+
+
+@pytest.mark.parametrize("size", [2, 3, 4])
+def test_short_templates_match_oracle(engine, oracle_lib, size):
+    """Templates of 2-4 atoms: the fused level-0/1 kernel emits complete tuples (n == 2) or hands
+    level-2 items on; engine vs oracle: tuple set and work counters exact.  With 2 or 3 atoms the
+    covariance is rank deficient and the reference's rotation is 0/0 (vendor/jess/src/Super.c:
+    501-520 divides by sqrt of a zero eigenvalue): whether it comes out NaN -- and the hit is
+    dropped, _jess.pyx:2240-2251 -- depends on libm rounding noise, so for those sizes the HIT
+    sets are only required to agree on tuples whose rotation is finite on both sides."""
+    from _util import load_molecule, load_template
+    from pyjess_b200 import Template
+    from pyjess_b200._tables import query_params
+    full = [load_template(n) for n in ("template_01.qry", "template_02.qry", "1.3.3.tpl", "4.1.2.tpl")]
+    tpl = [Template(list(t)[k:k + size], id=f"{t.id}-{k}") for t in full for k in (0, 3)]
+    mols = [load_molecule("pdb1lnb.ent"), load_molecule("1AMY.pdb")]
+    for reorder in (1, 2):
+        params = query_params(2.0, 1.0, 1.0, reorder=reorder)
+        table, stats = run_engine(engine, tpl, mols, params)
+        ours, ostats = oracle_lib.query(TemplateTable(tpl), MoleculeBatch(mols), params, threads=4)
+        for key in ("pairs", "live_pairs", "candidate_atoms", "frontier_items", "frontier_ints", "candidate_tests",
+                    "tuples"):
+            assert stats[key] == ostats[key], key
+        every, _ = run_engine(engine, tpl, mols, query_params(2.0, 1.0, 1.0, reorder=reorder, all_tuples=True))
+        assert every.count == stats["tuples"] and set(table.keys()) <= set(every.keys()) >= set(ours.keys())
+        if size >= 4:
+            assert table.count == ours.count > 0
+            assert compare_tables(table, ours, params.rmsd_threshold, tpl, mols, []) == []
+            assert stats["nan_dropped"] == ostats["nan_dropped"]
+        else:
+            assert table.count + stats["nan_dropped"] == ours.count + ostats["nan_dropped"] > 0   # same RMSD filter
+            mine = {k: table.rmsd[i] for i, k in enumerate(table.keys())}
+            for i, k in enumerate(ours.keys()):
+                if k in mine:
+                    assert abs(mine[k] - ours.rmsd[i]) <= TOL
