@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_lv(const ExpandArg
             const int2 e = W.queue[q0 + lane];
             a = e.x; g = e.y;
         }
+        __syncwarp();   // the scan loop reuses these queue slots right after the drain (racecheck: WAR)
         const int2 mt = W.meta[g];
         if (ok) {
             const AtomRec p = A.atoms[W.abase[g] + a];

@@ -870,6 +870,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(const ExpandArgs A
             a = e.x; g = e.y;
             gm = meta[g];
         }
+        __syncwarp();   // the scan loop reuses these queue slots right after the drain (racecheck: WAR)
         if (ok && l > 0) {
             const AtomRec p = A.atoms[gm.abase + a];
             const ChainRec *ch = chain + g * lpad;
