@@ -944,7 +944,19 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
             HitOrderArgs OA;
             OA.h0 = h0; OA.h1 = h1; OA.mol_base = slice_base + r.m0; OA.n_templates = t->T; OA.stride = c->hit_stride;
             OA.mol = HB.mol; OA.tpl = HB.tpl; OA.atoms = HB.atoms;
-            if (q->hit_order != JB_ORDER_CANONICAL) {
+            bool ranked = q->hit_order != JB_ORDER_CANONICAL;
+            if (ranked && nh <= 1024) {
+                // sparse small result: with at most one hit per pair the order inside a pair is moot
+                int *flag = reinterpret_cast<int *>(&c->o_work.as<RunWork>()[1].max_npad);
+                CU(cudaMemsetAsync(flag, 0, sizeof(int), st));
+                k_hit_multi<<<1, 256, 0, st>>>(h0, (int)nh, HB.mol, HB.tpl, flag);
+                int multi = 1;
+                CU(cudaMemcpyAsync(&multi, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+                S.launches++;
+                ranked = multi != 0;
+            }
+            if (ranked) {
                 // rank vectors of the reference's depth-first order replace the atom tuples as sort keys
                 int rc = build_reference_keys(c, t, mol, q, r.m0, Mc, MT, CT, TT, h0, h1, S);
                 if (rc != JB_OK) return rc;

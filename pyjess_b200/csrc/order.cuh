@@ -196,6 +196,18 @@ __global__ void __launch_bounds__(128) k_kd_order(long long n_lists, const unsig
     for (unsigned q = 0; q < cnt; q++) kd_rank[perm[o0 + idx[q]]] = cnt - 1 - q;
 }
 
+// Small sparse results: does any (structure, template) pair own more than one hit?  If not, the
+// record order inside a pair is moot and the rank tables need not be built (a single small query
+// spends more time in them than in the search).  One CTA, n <= 1024 hits.
+__global__ void __launch_bounds__(256) k_hit_multi(long long h0, int n, const int *mol, const int *tpl, int *multi)
+{
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int m = mol[h0 + i], t = tpl[h0 + i];
+        for (int j = i + 1; j < n; j++)
+            if (mol[h0 + j] == m && tpl[h0 + j] == t) { *multi = 1; return; }
+    }
+}
+
 struct HitKeyArgs {
     long long h0, h1;
     int stride, n_specs, ref_reorder;      // ref_reorder: the reference ran with reorder=True
