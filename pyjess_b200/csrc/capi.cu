@@ -813,7 +813,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
             ExpandArgs A;
             A.level = l; A.n_specs = t->S; A.tuple_stride = tuple_stride; A.ignore_chain = q->ignore_chain;
             A.recs = c->recs.as<PairRec>(); A.shell = TT.shell; A.atoms = MT.atoms; A.ext = MT.ext;
-            A.head = CT.head; A.xtab = CT.xtab; A.cand = CT.rec;
+            A.head = CT.head; A.xtab = CT.xtab; A.cand = CT.rec; A.cand_cap = CT.cap;
             A.in = l == 0 ? nullptr : c->fr[(l - 1) & 1].as<int>();
             A.in_count = l == 0 ? &dc->live_pairs : &dc->level[l];
             A.in_cap = l == 0 ? pairs : fr_ints[(l - 1) & 1] / (l + 1);

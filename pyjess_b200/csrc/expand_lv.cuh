@@ -149,9 +149,10 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_lv(const ExpandArg
                 u64 ob = 0;
                 if (lane == 0) ob = atomicAdd(A.out_count, (u64)fill);
                 ob = __shfl_sync(FULL, ob, 0);
-                if ((long long)ob + fill <= A.out_cap) {
+                if ((long long)ob < A.out_cap) {   // on overflow write the part that fits: every slot below
+                    const int fit = (int)min((long long)fill, A.out_cap - (long long)ob);   // the capacity holds a real item
                     int *dst = A.out + (long long)ob * out_stride;
-                    for (int i = lane; i < fill * out_stride; i += 32) dst[i] = W.stage[i];
+                    for (int i = lane; i < fit * out_stride; i += 32) dst[i] = W.stage[i];
                 }
                 fill = 0;
                 __syncwarp();
@@ -177,6 +178,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_lv(const ExpandArg
                     const PairRec *rec = A.recs + my_pair;
                     const CandHead hd = A.head[(long long)rec->m * A.n_specs + rec->spec[0]];
                     root_cnt = hd.cnt; root_off = hd.off; root_j = 0;
+                    if (root_off + root_cnt > A.cand_cap) root_cnt = (int)max(0ll, A.cand_cap - root_off);
                     pair_loaded = true;
                 }
                 const int take = min(root_cnt - root_j, IPW - filled);
@@ -208,6 +210,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_lv(const ExpandArg
             const CandHead hd = A.head[lidx];
             cnt = hd.cnt;
             coff = hd.off;
+            if (coff + cnt > A.cand_cap) cnt = (int)max(0ll, A.cand_cap - coff);   // overflowing chunk: stay in bounds
             hx0 = hd.x0; hinv = hd.inv_w;
             if (gl == 0) {
                 W.meta[grp] = make_int2(lp, (L + 1 == n) ? 1 : 0);
@@ -371,9 +374,10 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_lv(const ExpandArg
         u64 ob = 0;
         if (lane == 0) ob = atomicAdd(A.out_count, (u64)fill);
         ob = __shfl_sync(FULL, ob, 0);
-        if ((long long)ob + fill <= A.out_cap) {
+        if ((long long)ob < A.out_cap) {
+            const int fit = (int)min((long long)fill, A.out_cap - (long long)ob);
             int *dst = A.out + (long long)ob * out_stride;
-            for (int i = lane; i < fill * out_stride; i += 32) dst[i] = W.stage[i];
+            for (int i = lane; i < fit * out_stride; i += 32) dst[i] = W.stage[i];
         }
     }
 #pragma unroll

@@ -768,6 +768,7 @@ struct ExpandArgs {
     const CandHead *head;
     const unsigned short *xtab;  // x-bucket index of the lists (k_xindex)
     const float4 *cand;
+    long long cand_cap;          // records allocated: lists are clamped to it while a chunk overflows (then re-run)
     const int *in;               // items [lp, a_0..a_{l-1}], stride l+1 (unused for l==0)
     const u64 *in_count;         // items available (may exceed in_cap after an overflow)
     long long in_cap;
@@ -922,9 +923,10 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(const ExpandArgs A
                 u64 ob = 0;
                 if (lane == 0) ob = atomicAdd(A.out_count, (u64)fill);
                 ob = __shfl_sync(FULL, ob, 0);
-                if ((long long)ob + fill <= A.out_cap) {
+                if ((long long)ob < A.out_cap) {   // on overflow write the part that fits: every slot below
+                    const int fit = (int)min((long long)fill, A.out_cap - (long long)ob);   // the capacity holds a real item
                     int *dst = A.out + (long long)ob * out_stride;
-                    for (int i = lane; i < fill * out_stride; i += 32) dst[i] = stage[i];
+                    for (int i = lane; i < fit * out_stride; i += 32) dst[i] = stage[i];
                 }
                 fill = 0;
                 __syncwarp();
@@ -949,6 +951,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(const ExpandArgs A
             const CandHead hd = A.head[(long long)h0.x * A.n_specs + rec->spec[l]];
             cnt = hd.cnt;
             coff = hd.off;
+            if (coff + cnt > A.cand_cap) cnt = (int)max(0ll, A.cand_cap - coff);   // overflowing chunk: stay in bounds
             if (gl == 0) {
                 GroupMeta gm; gm.abase = h1.x; gm.lp = lp; gm.complete = (l + 1 == n) ? 1 : 0;
                 meta[grp] = gm;
@@ -1045,9 +1048,10 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(const ExpandArgs A
         u64 ob = 0;
         if (lane == 0) ob = atomicAdd(A.out_count, (u64)fill);
         ob = __shfl_sync(FULL, ob, 0);
-        if ((long long)ob + fill <= A.out_cap) {
+        if ((long long)ob < A.out_cap) {
+            const int fit = (int)min((long long)fill, A.out_cap - (long long)ob);
             int *dst = A.out + (long long)ob * out_stride;
-            for (int i = lane; i < fill * out_stride; i += 32) dst[i] = stage[i];
+            for (int i = lane; i < fit * out_stride; i += 32) dst[i] = stage[i];
         }
     }
     if (lane == 0) {   // statistics: lane 0 carries the warp totals

@@ -182,3 +182,31 @@ def test_short_templates_match_oracle(engine, oracle_lib, size):
             for i, k in enumerate(ours.keys()):
                 if k in mine:
                     assert abs(mine[k] - ours.rmsd[i]) <= TOL
+
+
+def test_small_workspace_splits_chunks_and_fails_loudly(engine):
+    """The frontier workspace is bounded (`workspace_bytes`): an overflowing chunk is re-run with
+    larger buffers or split into smaller runs of structures -- same table -- and a single
+    structure that cannot fit raises JB_ERR_CAPACITY instead of truncating."""
+    from pyjess_b200 import _capi, synth
+    from pyjess_b200._tables import query_params
+    tpl, mols, thr, kw = synth.workload("cfg3dense", scale=0.05)
+    tpl, mols = tpl[:5], mols[:24]
+    params = query_params(*thr, **kw)
+    base, _ = run_engine(engine, tpl, mols, params)
+    small = _capi.Context(0, workspace_bytes=1 << 20)
+    try:
+        table, stats = run_engine(small, tpl, mols, params)
+        assert stats["retries"] > 0 and stats["chunks"] > 1
+        assert base.count == table.count > 1000
+        for a, b in zip(base.arrays(), table.arrays()):
+            assert np.array_equal(a, b)
+    finally:
+        small.close()
+    tiny = _capi.Context(0, workspace_bytes=1 << 12)
+    try:
+        with pytest.raises(_capi.EngineError) as err:
+            run_engine(tiny, tpl, mols, params)
+        assert err.value.status == -4
+    finally:
+        tiny.close()
