@@ -771,7 +771,9 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         CU(c->recs.ensure((size_t)pairs * sizeof(PairRec), st));
         if (c->crec.bytes == 0) {
             const long long chunk_atoms = mol->atom_off[r.m1] - mol->atom_off[r.m0];
-            CU(c->crec.ensure((size_t)std::max<long long>(chunk_atoms * 4, 1 << 20) * sizeof(float4), st));
+            long long init_records = std::max<long long>(chunk_atoms * 4, 1 << 20);
+            if (const char *g = getenv("JB_TEST_CREC")) init_records = std::max(64, atoi(g));   // tests: force the retry
+            CU(c->crec.ensure((size_t)init_records * sizeof(float4), st));
         }
         MolTable MT;
         MT.n_molecules = Mc;

@@ -210,3 +210,42 @@ def test_small_workspace_splits_chunks_and_fails_loudly(engine):
         assert err.value.status == -4
     finally:
         tiny.close()
+
+
+def test_candidate_record_overflow_is_retried(engine, oracle_lib, monkeypatch):
+    """Residue-independent match modes (100-107: most atoms are candidates of several specs) against
+    the oracle, and the candidate-record buffer overflowing on the first attempt (forced small with
+    JB_TEST_CREC): the chunk is re-run with a larger buffer, same table."""
+    from pyjess_b200 import Template, TemplateAtom, _capi, synth
+    from pyjess_b200._tables import query_params
+    _, mols, _, _ = synth.workload("cfg3", scale=0.03)
+    mols = mols[:12]
+    src = mols[0]._atoms
+    bb = [int(np.nonzero((src["resSeq"] == 5) & (src["name"] == n))[0][0]) for n in (b"_N__", b"_CA_", b"_C__", b"_O__")]
+    # modes that accept N / CA / C / O respectively (mainchain = CA, N, O; eff:TessAtom.c:269-276)
+    sets = [[(104, "N"), (105, "CA"), (106, "C"), (102, "O")], [(107, "N"), (100, "CA"), (103, "C"), (104, "O")],
+            [(102, "N"), (107, "CA"), (103, "CA"), (105, "O")]]
+    tpl = []
+    for k, modes in enumerate(sets):
+        atoms = []
+        for (mode, name), a in zip(modes, bb):
+            x, y, z = (float(v) for v in src["x"][a])
+            atoms.append(TemplateAtom(chain_id="A", residue_number=5, x=x, y=y, z=z, residue_names=["ALA"],
+                                      atom_names=[name], distance_weight=0.0, match_mode=mode))
+        tpl.append(Template(atoms, id=f"any-{k}"))
+    params = query_params(0.5, 0.3, 0.3)
+    base, bstats = run_engine(engine, tpl, mols, params)
+    ours, ostats = oracle_lib.query(TemplateTable(tpl), MoleculeBatch(mols), params, threads=8)
+    assert base.count == ours.count > 1000
+    assert compare_tables(base, ours, params.rmsd_threshold, tpl, mols, []) == []
+    for key in COUNTERS:
+        assert bstats[key] == ostats[key], key
+    monkeypatch.setenv("JB_TEST_CREC", "4096")
+    fresh = _capi.Context(0)             # its candidate buffer starts at 4,096 records
+    try:
+        table, stats = run_engine(fresh, tpl, mols, params)
+    finally:
+        fresh.close()
+    assert stats["retries"] > 0 and stats["candidate_records"] > 4096
+    for a, b in zip(base.arrays(), table.arrays()):
+        assert np.array_equal(a, b)
