@@ -8,6 +8,17 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def pytest_sessionstart(session):
+    """The engine library is a build artefact (git-ignored): compile it when it is missing or older
+    than its sources, so that a fresh checkout can run the suite (host-side entry points such as the
+    PDB parser are used by CPU tests too).  A failure here is reported by the tests that need it."""
+    try:
+        from pyjess_b200 import _build
+        _build.build()
+    except Exception as err:  # pragma: no cover
+        print(f"[conftest] could not build libjess_b200.so: {err}", file=sys.stderr)
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     config.addinivalue_line("markers", "slow: long-running CPU test")
