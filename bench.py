@@ -245,6 +245,8 @@ def main():
 
     import torch
     import torch.distributed as dist
+    from pyjess_b200 import _build
+    _build.build()                         # no-op unless the (git-ignored) library is missing or stale; lock-protected
     from pyjess_b200 import _capi, synth
     from pyjess_b200._tables import MoleculeBatch, TemplateTable, query_params
 
