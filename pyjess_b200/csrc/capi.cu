@@ -112,6 +112,7 @@ struct jb_context {
     int sm_count = 148;
     size_t ws_limit = 0;          // bytes the frontier buffers may use in total
     int group = 2;                // lanes per partial match (JB_GROUP)
+    int group_lv[kMaxN + 1] = {};  // per-level override (JB_GROUPS="g1,g2,..." for levels 1, 2, ...); 0: default
     int debug = 0;                // JB_DEBUG: per-level counts and times on stderr
     int legacy = 0;               // JB_LEGACY: run-time-level k_expand at every level (A/B comparisons)
     cudaEvent_t lev[kMaxN + 1] = {};
@@ -210,6 +211,15 @@ extern "C" int jb_context_create(int device, void *stream, int64_t workspace_byt
     if (const char *g = getenv("JB_GROUP")) {
         int v = atoi(g);
         if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) c->group = v;
+    }
+    c->group_lv[1] = 1;   // level 1 stages a single atom per partial match: one lane each (measured -3 % per step)
+    if (const char *g = getenv("JB_GROUPS")) {
+        int l = 1;
+        for (const char *p = g; *p && l <= kMaxN; l++) {
+            c->group_lv[l] = atoi(p);
+            while (*p && *p != ',') p++;
+            if (*p == ',') p++;
+        }
     }
     if (const char *g = getenv("JB_DEBUG")) c->debug = atoi(g);
     if (const char *g = getenv("JB_LEGACY")) c->legacy = atoi(g);
@@ -827,7 +837,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
             if (c->debug) CU(cudaEventRecord(c->lev[l], st));
             // lanes per partial match: the configured G, widened at deep levels so that at
             // least two CTAs per SM fit their staging areas in shared memory
-            int g = c->group;
+            int g = (l <= kMaxN && c->group_lv[l] > 0) ? c->group_lv[l] : c->group;
             // levels 0 + 1 fused: the roots are dealt out of the candidate lists by the level-1 kernel
             // itself (needs every template to have >= 2 atoms: a single-atom root is a complete tuple)
             const bool fused_root = t->nmin >= 2 && !c->legacy && !getenv("JB_NO_ROOT_FUSION");
