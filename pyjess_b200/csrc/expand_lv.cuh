@@ -34,10 +34,20 @@ constexpr int kMaxLv = 12;       // levels 1..kMaxLv have a specialisation; deep
 #ifndef JB_CHUNK
 #define JB_CHUNK 16
 #endif
-constexpr int kChunk = JB_CHUNK; // records per scan chunk, read by a QUAD of lanes (64-byte pieces)
+#ifndef JB_CHUNK_L1
+#define JB_CHUNK_L1 JB_CHUNK
+#endif
+#ifndef JB_CHUNK_DEEP
+#define JB_CHUNK_DEEP JB_CHUNK
+#endif
+#ifndef JB_DEEP_FROM
+#define JB_DEEP_FROM 99
+#endif
+// records per scan chunk, read by a QUAD of lanes (64-byte pieces); per level: the single-shell box of
+// level 1 leaves long x ranges, the join boxes of deep levels short ones
+template <int L> struct ChunkOf { static constexpr int value = L == 1 ? JB_CHUNK_L1 : (L >= JB_DEEP_FROM ? JB_CHUNK_DEEP : JB_CHUNK); };
 constexpr int kOwnerCap = 128;   // batches of up to this many chunks get a direct chunk -> owner table
 constexpr int kQuad = 4;         // lanes per chunk: one LDG.128 of a quad covers 64 contiguous bytes
-constexpr int kQueueLv = 32 + 8 * kChunk;   // survivor queue: < 32 carried + 8 chunks new per scan iteration
 
 template <int L, int G> struct alignas(16) LvWarp {   // per-warp shared memory
     static constexpr int IPW = 32 / G;                // partial matches per batch
@@ -52,7 +62,7 @@ template <int L, int G> struct alignas(16) LvWarp {   // per-warp shared memory
     int2 meta[IPW];                                   // pair index, "this level completes the template"
     int clen[IPW];                                    // records in the x range
     int cstart[IPW];                                  // first chunk of the partial match (exclusive scan)
-    int2 queue[kQueueLv];                             // box survivors: (atom, partial match)
+    int2 queue[32 + 8 * ChunkOf<L>::value];               // box survivors (atom, partial match): < 32 carried + 8 chunks new
     unsigned char owner[kOwnerCap];                   // chunk -> partial match of the batch (short batches)
     int chain_atom[L][IPW];
     int stage[kStageItems * (L + 2)];                 // accepted extensions awaiting the flush
@@ -70,6 +80,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_lv(const ExpandArg
     constexpr int IPW = 32 / G;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int in_stride = L + 1, out_stride = L + 2;
+    constexpr int kChunk = ChunkOf<L>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LvWarp<L, G> &W = reinterpret_cast<LvWarp<L, G> *>(smem_raw)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
