@@ -368,7 +368,8 @@ class Query:
     # vectorised access for heavy consumers (no Hit objects)
     def hit_table(self):
         """(HitTable, row indices of this structure) of the underlying batch."""
-        return self._run.table, self._run.indices(self._index)
+        rows = self._run.indices(self._index)        # runs the batch on first use: fetch it before the table
+        return self._run.table, rows
 
     @property
     def stats(self):

@@ -12,12 +12,13 @@ passes the invalid value ``"all"`` there, cli.py:248, and fails).
 from __future__ import annotations
 
 import argparse
+import io
 import sys
 import typing
 import warnings
 from pathlib import Path
 
-from . import __version__
+from . import __version__, sites
 from ._jess import Jess
 from ._model import Molecule, Template
 
@@ -62,6 +63,10 @@ def argument_parser(prog: str = "pyjess_b200") -> argparse.ArgumentParser:
                             "order of the original Jess.")
     group.add_argument("-b", "--best-match", action="store_true",
                        help="Return only the best match for each template/query pair.")
+    group.add_argument("--best-sites", choices=("all", "best"), default=None,
+                       help="Post-filter of the reference's vendor/jess/filter_output.py: keep the lowest log(E) hit "
+                            "per distinct list of matched residues of every template/query pair and drop self "
+                            "matches ('all'), or only the best of those per pair ('best'). Applied per batch.")
     return parser
 
 
@@ -88,10 +93,18 @@ def main(argv: typing.Optional[typing.List[str]] = None, stdout: typing.TextIO =
             queries = jess.query_many(mols, args.rmsd, args.distance_cutoff, args.maximum_distance,
                                       max_candidates=args.max_candidates, ignore_chain=ignore_chain,
                                       reorder=args.reorder, best_match=args.best_match)
+            if args.best_sites is not None and args.max_candidates is None:
+                sites.write_hits(sites.best_sites(queries, all_instances=args.best_sites == "all"), stdout,
+                                 transform=args.transform)
+                continue
+            text = io.StringIO() if args.best_sites is not None else stdout
             for query in queries:
                 for hit in query:
-                    hit.dump(stdout, format="pdb", transform=args.transform)
-                    stdout.write("\n")
+                    hit.dump(text, format="pdb", transform=args.transform)
+                    text.write("\n")
+            if args.best_sites is not None:    # max_candidates: the replayed stream is filtered as text
+                text.seek(0)
+                sites.filter_text(text, stdout, all_instances=args.best_sites == "all")
     except Exception as err:  # same contract as the reference CLI: message on stderr, errno or 1
         print("Error: {}".format(err), file=stderr)
         return getattr(err, "errno", None) or 1

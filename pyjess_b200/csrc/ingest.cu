@@ -9,6 +9,7 @@
 // C atoi/atof PREFIX parsing from the field's first column, fields beyond the end of the
 // line keep their zero value, tokens copied with blanks/NULs turned into '_'.
 #include <cctype>
+#include <cmath>
 #include <cstdio>
 #include <cstdint>
 #include <cstdlib>
@@ -156,26 +157,94 @@ static inline void decode_token(char *d, const char *s, int n)
     d[n] = 0;
 }
 
+// "%<width>i": right-justified decimal, wider when it does not fit (like printf)
+static inline char *put_int(char *p, int32_t v, int width)
+{
+    char tmp[12];
+    int n = 0;
+    uint32_t u = v < 0 ? 0u - (uint32_t)v : (uint32_t)v;
+    do { tmp[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+    if (v < 0) tmp[n++] = '-';
+    for (int i = n; i < width; i++) *p++ = ' ';
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+
+// "%<width>.<prec>f" without the printf machinery.  printf rounds the EXACT binary value half-to-even;
+// |v| * 10^prec is computed here with one rounding (<= 2^-23 below 2^30), so the integer nearest to it is
+// the right one unless the product sits within 1e-6 of a half: those (exact ties such as k/16, and the
+// neighbours no double product can tell apart), non-finite and huge values go through snprintf.
+static inline char *put_fixed(char *p, double v, int width, int prec)
+{
+    const double scale = prec == 3 ? 1000.0 : 100.0;
+    const double r = fabs(v) * scale;
+    if (!(r < 1073741824.0)) return p + snprintf(p, 400, "%*.*f", width, prec, v);
+    const double f = floor(r), frac = r - f;
+    if (fabs(frac - 0.5) < 1e-6) return p + snprintf(p, 400, "%*.*f", width, prec, v);
+    uint64_t m = (uint64_t)f + (frac > 0.5 ? 1u : 0u);
+    char tmp[24];
+    int n = 0;
+    for (int i = 0; i < prec; i++) { tmp[n++] = (char)('0' + m % 10); m /= 10; }
+    tmp[n++] = '.';
+    do { tmp[n++] = (char)('0' + m % 10); m /= 10; } while (m);
+    if (signbit(v)) tmp[n++] = '-';
+    for (int i = n; i < width; i++) *p++ = ' ';
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+
 extern "C" int64_t jb_format_atoms_pdb(const jb_atom_record *atoms, int64_t n, const double *xyz, char *out,
                                        int64_t capacity)
 {
     if (!atoms || !out || n < 0) return JB_ERR_INVALID;
-    int64_t pos = 0;
+    // "ATOM  %5i%5s%c%-3s%c%c%4i%-4c%8.3f%8.3f%8.3f%6.2f%6.2f          %2s\n" (_jess.pyx:1273-1291), field by field;
+    // a line is 79 bytes; a double printed with %f takes up to 317, so the field-by-field path wants 2 KiB of room
+    char *p = out;
     char name[5], res[4], elem[3];
     for (int64_t k = 0; k < n; k++) {
         const jb_atom_record *a = &atoms[k];
-        if (capacity - pos < 96) return JB_ERR_CAPACITY;
+        if (capacity - (p - out) < 2048) {
+            if (capacity - (p - out) < 96) return JB_ERR_CAPACITY;
+            // short of room for the worst case: let snprintf bound the line
+            decode_token(name, a->name, 4);
+            decode_token(res, a->res_name, 3);
+            decode_token(elem, a->element, 2);
+            const double *x = xyz ? xyz + 3 * k : a->x;
+            const int64_t room = capacity - (p - out);
+            const int w = snprintf(p, (size_t)room,
+                                   "ATOM  %5i%5s%c%-3s%c%c%4i%-4c%8.3f%8.3f%8.3f%6.2f%6.2f          %2s\n", a->serial, name,
+                                   a->alt_loc ? a->alt_loc : ' ', res, a->chain_id1 ? a->chain_id1 : ' ',
+                                   a->chain_id2 ? a->chain_id2 : ' ', a->res_seq, a->i_code ? a->i_code : ' ', x[0], x[1],
+                                   x[2], (double)a->occupancy, (double)a->temp_factor, elem);
+            if (w < 0 || w >= room) return JB_ERR_CAPACITY;
+            p += w;
+            continue;
+        }
         decode_token(name, a->name, 4);
         decode_token(res, a->res_name, 3);
         decode_token(elem, a->element, 2);
         const double *x = xyz ? xyz + 3 * k : a->x;
-        pos += snprintf(out + pos, (size_t)(capacity - pos),
-                        "ATOM  %5i%5s%c%-3s%c%c%4i%-4c%8.3f%8.3f%8.3f%6.2f%6.2f          %2s\n", a->serial, name,
-                        a->alt_loc ? a->alt_loc : ' ', res, a->chain_id1 ? a->chain_id1 : ' ',
-                        a->chain_id2 ? a->chain_id2 : ' ', a->res_seq, a->i_code ? a->i_code : ' ', x[0], x[1], x[2],
-                        (double)a->occupancy, (double)a->temp_factor, elem);
+        memcpy(p, "ATOM  ", 6); p += 6;
+        p = put_int(p, a->serial, 5);
+        *p++ = ' ';
+        memcpy(p, name, 4); p += 4;
+        *p++ = a->alt_loc ? (char)a->alt_loc : ' ';
+        memcpy(p, res, 3); p += 3;
+        *p++ = a->chain_id1 ? (char)a->chain_id1 : ' ';
+        *p++ = a->chain_id2 ? (char)a->chain_id2 : ' ';
+        p = put_int(p, a->res_seq, 4);
+        *p++ = a->i_code ? (char)a->i_code : ' ';
+        memcpy(p, "   ", 3); p += 3;
+        p = put_fixed(p, x[0], 8, 3);
+        p = put_fixed(p, x[1], 8, 3);
+        p = put_fixed(p, x[2], 8, 3);
+        p = put_fixed(p, (double)a->occupancy, 6, 2);
+        p = put_fixed(p, (double)a->temp_factor, 6, 2);
+        memcpy(p, "          ", 10); p += 10;
+        memcpy(p, elem, 2); p += 2;
+        *p++ = '\n';
     }
-    return pos;
+    return p - out;
 }
 
 // ---- packing: per-molecule _Atom arrays -> the SoA image of jb_molecule_batch -------------

@@ -240,3 +240,41 @@ def test_thread_pool_recipe_of_the_reference_readme(lnb):
         got = pool.map(lambda m: [(h.template().id, round(h.rmsd, 9), tuple(a.serial for a in h.atoms(False)))
                                   for h in jess.query(m, 2.0, 4.0, 4.0)], mols)
     assert got == expected * 6 and sum(map(len, expected)) > 100
+
+
+def _all_hits_text(queries):
+    import io
+    buf = io.StringIO()
+    for query in queries:
+        for hit in query:
+            hit.dump(buf)
+            buf.write("\n")
+    buf.seek(0)
+    return buf
+
+
+@pytest.mark.parametrize("all_instances", [True, False])
+@pytest.mark.parametrize("workload", ["cfg2", "cfg3dense"])
+def test_best_sites_equals_the_filter_script_on_the_dumped_hits(workload, all_instances):
+    """`sites.best_sites` on the engine's hit table == `sites.filter_text` (pinned
+    byte for byte to vendor/jess/filter_output.py by tests/test_sites.py) on the text of ALL
+    hits.  cfg3dense: thousands of hits, several per site, self matches (a template renamed
+    to the id of a structure)."""
+    import io
+    from pyjess_b200 import sites, synth
+    if workload == "cfg2":
+        from _util import cfg2_molecules
+        templates = [Template.load(os.path.join(DATA, f"template_0{i}.qry"), id=f"template_0{i}") for i in (1, 2, 3)]
+        mols, thr = cfg2_molecules(), (2.0, 3.0, 3.0)
+    else:
+        templates, mols, thr, _ = synth.workload("cfg3dense", scale=0.04)
+        templates = [Template(list(t), id=mols[0].id if i == 1 else t.id) for i, t in enumerate(templates)]
+    jess = Jess(templates)
+    want = io.StringIO()
+    n_want = sites.filter_text(_all_hits_text(jess.query_many(mols, *thr)), want, all_instances=all_instances)
+    hits = sites.best_sites(jess.query_many(mols, *thr), all_instances=all_instances)
+    got = io.StringIO()
+    sites.write_hits(hits, got)
+    assert len(hits) == n_want and n_want > 0
+    assert got.getvalue() == want.getvalue()
+    assert all(h.template().id != h.molecule().id for h in hits)

@@ -45,3 +45,17 @@ def test_cli_reports_errors_like_the_reference(engine, monkeypatch, tmp_path):
     rc = main(["-T", "tests/golden/cli_templates.txt", "-Q", str(missing), "-R", "2", "-D", "3", "-M", "3"],
               stdout=out, stderr=err)
     assert rc != 0 and err.getvalue().startswith("Error: ")
+
+
+@pytest.mark.parametrize("golden", sorted(CASES))
+@pytest.mark.parametrize("mode", ["all", "best"])
+def test_cli_best_sites_matches_filter_output_script(engine, monkeypatch, golden, mode):
+    """`--best-sites`: the text vendor/jess/filter_output.py writes when fed the reference
+    command line's output (goldens: tests/golden/make_golden_sites.py)."""
+    monkeypatch.chdir(ROOT)
+    out, err = io.StringIO(), io.StringIO()
+    rc = main(LISTS + CASES[golden] + ["--best-sites", mode], stdout=out, stderr=err)
+    assert rc == 0, err.getvalue()
+    with open(os.path.join(GOLD, "sites_" + golden.replace(".txt", "") + "_" + mode + ".txt")) as f:
+        want = f.read()
+    assert out.getvalue() == want

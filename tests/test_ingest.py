@@ -111,3 +111,46 @@ def test_native_atom_formatter_matches_the_reference_sprintf():
     assert _capi.format_atoms_pdb(recs, xyz) == "".join(_format_atom(recs[k], xyz[k]) for k in range(len(recs)))
     assert _capi.format_atoms_pdb(recs) == "".join(_format_atom(recs[k], recs["x"][k]) for k in range(len(recs)))
     assert _capi.format_atoms_pdb(recs[:0]) == ""
+
+
+def test_native_atom_formatter_rounding_and_overflow_cases():
+    """The field-by-field fixed-point writer of jb_format_atoms_pdb against printf's exact
+    half-to-even rounding (Python's % operator, as `_format_atom`): exact decimal ties (k/16
+    and k/8), products next to a tie, negative zero, values overflowing their fields,
+    non-finite numbers, and a large random block."""
+    from pyjess_b200 import _capi
+    from pyjess_b200._model import ATOM_DTYPE, _format_atom
+    rng = np.random.default_rng(7)
+    special = np.array([0.0625, 0.1875, -0.0625, 2.5e-4, 0.0005, 0.0015, 0.0025, -0.0005, 1.0005, 2.0015, 1234.5675,
+                        -1234.5675, 0.125, 0.375, 8.3125, -0.0, -1e-9, 1e-9, 0.9995, 9999.9995, -999.9995, 99999.9999,
+                        1e7, -1e7, 1e9, 1.5e9, 1e15, 1e22, 1e300, -1e300, np.nan, np.inf, -np.inf, 5e-324,
+                        0.4999999999, 0.0004999999999, 0.00050000000001, 123.4565, 123.45650000000001, 123.45649999999999])
+    special = np.concatenate([special, rng.integers(-40000, 40000, 400) / 16.0, rng.integers(-40000, 40000, 400) / 8.0,
+                              np.nextafter(rng.integers(1, 90000, 300) / 2000.0, 1e9),
+                              np.nextafter(rng.integers(1, 90000, 300) / 2000.0, -1e9)])
+    n = len(special) + 20000
+    recs = np.zeros(n, dtype=ATOM_DTYPE)
+    recs["name"], recs["resName"], recs["element"] = b"_CA_", b"SER", b"_C"
+    recs["chainID1"], recs["chainID2"], recs["altLoc"], recs["iCode"] = 0x20, 0x41, 0x20, 0x20
+    recs["serial"] = rng.integers(-200000, 2000000, n)
+    recs["serial"][:4] = (0, -2147483648, 2147483647, 99999)
+    recs["resSeq"] = rng.integers(-2000, 20000, n)
+    xyz = rng.uniform(-500, 500, (n, 3))
+    xyz[len(special):len(special) + 5000] = np.round(xyz[len(special):len(special) + 5000], 3)   # PDB precision
+    xyz[:len(special), 0] = special
+    xyz[:len(special), 1] = special[::-1]
+    recs["x"] = xyz
+    recs["occupancy"] = rng.uniform(0, 1, n).astype(np.float32)
+    recs["tempFactor"] = rng.uniform(0, 120, n).astype(np.float32)
+    with np.errstate(over="ignore"):
+        recs["occupancy"][:len(special)] = special.astype(np.float32)
+    recs["tempFactor"][:200] = (rng.integers(0, 8000, 200) / 8.0 + 0.005).astype(np.float32)
+    got = _capi.format_atoms_pdb(recs)
+    want = "".join(_format_atom(recs[k], recs["x"][k]) for k in range(n))
+    if got != want:
+        g, w = got.splitlines(), want.splitlines()
+        bad = [k for k in range(min(len(g), len(w))) if g[k] != w[k]][:3]
+        raise AssertionError("\n".join(f"{k}: {g[k]!r} != {w[k]!r}" for k in bad) or "line counts differ")
+    # a block that ends inside the 2 KiB reserve of the output buffer goes through the bounded path
+    small = recs[len(special):len(special) + 3]
+    assert _capi.format_atoms_pdb(small) == "".join(_format_atom(small[k], small["x"][k]) for k in range(3))
