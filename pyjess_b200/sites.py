@@ -90,18 +90,24 @@ def _printed(values: np.ndarray, fmt: str) -> np.ndarray:
     return np.char.mod(fmt, values).astype(np.float64)
 
 
-def _residue_ids(records: np.ndarray, names: dict) -> np.ndarray:
+def _left_justified(cols: np.ndarray) -> np.ndarray:
+    """`str.strip` on fixed-width byte columns, as far as equality goes: '_'/NUL are blanks in the
+    dumped text, leading blanks are shifted out, trailing ones are padding either way."""
+    cols = np.where((cols == 0) | (cols == 0x5F), 0x20, cols).astype(np.int64)
+    for _ in range(cols.shape[1] - 1):
+        lead = cols[:, 0] == 0x20
+        cols = np.where(lead[:, None], np.concatenate([cols[:, 1:], np.full((len(cols), 1), 0x20)], axis=1), cols)
+    return cols
+
+
+def _residue_ids(records: np.ndarray) -> np.ndarray:
     """One integer per atom, equal exactly when the script's ``resname_chain_resid`` strings
-    are: columns 18-20, 21-22 and 23-26 of the dumped line, each stripped (:63-66)."""
-    raw = np.empty(len(records), dtype=[("r", "S4"), ("c1", "u1"), ("c2", "u1"), ("s", "<i4")])
-    raw["r"], raw["c1"], raw["c2"], raw["s"] = records["resName"], records["chainID1"], records["chainID2"], records["resSeq"]
-    uniq, inverse = np.unique(raw, return_inverse=True)
-    ids = np.empty(len(uniq), dtype=np.int64)
-    for j, u in enumerate(uniq):
-        resname = bytes(u["r"])[:3].replace(b"_", b" ").replace(b"\0", b" ").strip()
-        chain = bytes([int(u["c1"]) or 32, int(u["c2"]) or 32]).strip()
-        ids[j] = names.setdefault((resname, chain, int(u["s"])), len(names))
-    return ids[inverse.reshape(-1)]
+    are: columns 18-20, 21-22 and 23-26 of the dumped line, each stripped (:63-66).  Injective
+    over the residue numbers that fit the fixed columns (`_fixed_columns`): 5 bytes + 14 bits."""
+    name = _left_justified(np.frombuffer(np.ascontiguousarray(records["resName"]).tobytes(), dtype=np.uint8).reshape(-1, 4)[:, :3])
+    chain = _left_justified(np.stack([records["chainID1"], records["chainID2"]], axis=1))
+    key = (name[:, 0] << 48) | (name[:, 1] << 40) | (name[:, 2] << 32) | (chain[:, 0] << 24) | (chain[:, 1] << 16)
+    return key | (records["resSeq"].astype(np.int64) + 1024)
 
 
 def _fixed_columns(records: np.ndarray) -> bool:
@@ -123,10 +129,10 @@ def best_sites(queries, all_instances: bool = True) -> list:
     if isinstance(queries, Query):
         queries = [queries]
     queries = list(queries)
-    sites, scores, selfs, owners = [], [], [], []
-    names: dict = {}
-    residue_names: dict = {}             # shared: structures with equal ids fall into one flush unit
-    pair_of_row = []
+    sites, log_es, selfs, owners, pair_of_row = [], [], [], [], []
+    mol_names: dict = {}
+    tpl_names: dict = {}
+    per_jess: dict = {}        # id(jess) -> (dim[t], name id[t]) of its templates
     for q, query in enumerate(queries):
         if not isinstance(query, Query):
             raise TypeError(f"best_sites expects Query objects, found {type(query).__name__}")
@@ -140,29 +146,23 @@ def best_sites(queries, all_instances: bool = True) -> list:
             raise RuntimeError("cannot filter hits where `molecule.id` is `None`")
         if not _fixed_columns(mol._atoms):
             raise ValueError("serial or residue numbers overflow the fixed PDB columns the filter reads")
-        templates = query.jess._templates
+        if id(query.jess) not in per_jess:
+            templates = query.jess._templates
+            if any(t.id is None for t in templates):
+                raise RuntimeError("cannot filter hits where `template.id` is `None`")
+            per_jess[id(query.jess)] = (np.asarray([float(t._dim) for t in templates], dtype=np.float64),
+                                        np.asarray([tpl_names.setdefault(t.id, len(tpl_names)) for t in templates],
+                                                   dtype=np.int64))
+        dim, tpl_name = per_jess[id(query.jess)]
         tpl = table.template[rows].astype(np.int64)
-        res = _residue_ids(mol._atoms, residue_names)
+        res = _residue_ids(mol._atoms)
         atoms = table.atoms[rows].astype(np.int64)
         sites.append(np.where(atoms >= 0, res[np.maximum(atoms, 0)], -1))
         # Hit.log_evalue (TessTemplate_logE) evaluated in the same order of operations
-        used = np.unique(tpl)
-        dim = np.zeros(len(templates), dtype=np.float64)
-        pair = np.zeros(len(templates), dtype=np.int64)
-        same = np.zeros(len(templates), dtype=bool)
-        for t in used:
-            template = templates[t]
-            if template.id is None:
-                raise RuntimeError("cannot filter hits where `template.id` is `None`")
-            dim[t] = float(template._dim)
-            pair[t] = names.setdefault((mol.id, template.id), len(names))
-            # Match.from_remark splits the REMARK line on blanks: names are compared as printed
-            same[t] = template.id == mol.id
-        rmsd = table.rmsd[rows]
-        log_e = -8.5 + 2.5 * rmsd + -0.7 * dim[tpl] + math.log(float(len(mol)))
-        scores.append(_printed(log_e, "%4.2f"))
-        selfs.append(same[tpl])
-        pair_of_row.append(pair[tpl])
+        log_es.append(-8.5 + 2.5 * table.rmsd[rows] + -0.7 * dim[tpl] + math.log(float(len(mol))))
+        # Match.from_remark splits the REMARK line on blanks: names are compared as printed
+        selfs.append(tpl_name[tpl] == tpl_names.get(mol.id, -1))
+        pair_of_row.append(mol_names.setdefault(mol.id, len(mol_names)) * (1 << 32) + tpl_name[tpl])
         owners.append((q, rows))
     if not sites:
         return []
@@ -172,14 +172,11 @@ def best_sites(queries, all_instances: bool = True) -> list:
     # flush units: runs of CONSECUTIVE hits with the same (target, template) names
     block = np.zeros(len(pair_of_row), dtype=np.int64)
     block[1:] = np.cumsum(pair_of_row[1:] != pair_of_row[:-1])
-    chosen = select_sites(block, np.concatenate(sites), np.concatenate(scores), np.concatenate(selfs), all_instances)
+    chosen = select_sites(block, np.concatenate(sites), _printed(np.concatenate(log_es), "%4.2f"), np.concatenate(selfs), all_instances)
     starts = np.cumsum([0] + [len(rows) for _, rows in owners])
-    hits = []
-    for i in chosen:
-        o = int(np.searchsorted(starts, i, side="right")) - 1
-        q, rows = owners[o]
-        hits.append(queries[q]._make_hit(int(rows[i - starts[o]])))
-    return hits
+    owner = np.searchsorted(starts, chosen, side="right") - 1
+    all_rows = np.concatenate([rows for _, rows in owners])[chosen]
+    return [queries[owners[o][0]]._make_hit(r) for o, r in zip(owner.tolist(), all_rows.tolist())]
 
 
 def filter_text(lines: typing.Iterable[str], out: typing.TextIO, all_instances: bool = True) -> int:

@@ -100,3 +100,63 @@ def test_select_sites_empty_and_shapes():
     # [a, a, b] and [a, b, b] are the same residue list; [b, a] is another one
     got = select_sites([0, 0, 0], [[1, 1, 2], [1, 2, 2], [2, 1, -1]], [0.5, 0.25, 0.1], [False] * 3)
     assert got.tolist() == [1, 2]
+
+
+def _fake_queries(n_hits, seed):
+    """`Query` objects over a hand-made hit table (the host layer only: no engine call)."""
+    import types
+    from pyjess_b200 import Template, synth
+    from pyjess_b200._jess import Jess, Query, _BatchRun
+    tpl, mols, thr, _ = synth.workload("cfg3", scale=0.012)
+    tpl = [Template(list(t), id=mols[1].id if i == 2 else t.id) for i, t in enumerate(tpl)]      # a self match
+    jess = Jess.__new__(Jess)
+    jess._templates = tpl
+    rng = np.random.default_rng(seed)
+    mol = np.sort(rng.integers(0, len(mols), n_hits))
+    t = rng.integers(0, len(tpl), n_hits)
+    order = np.lexsort((-t, mol))                      # iteration order: templates descending per structure
+    mol, t = mol[order], t[order]
+    atoms = np.full((n_hits, 18), -1, dtype=np.int32)
+    for i in range(n_hits):
+        n = len(tpl[t[i]])
+        atoms[i, :n] = rng.integers(0, 60) + rng.integers(0, 24, n)        # few residues: many repeated sites
+    rot = np.tile(np.eye(3), (n_hits, 1, 1))
+    table = types.SimpleNamespace(count=n_hits, molecule=mol.astype(np.int32), template=t.astype(np.int32),
+                                  atoms=atoms, rmsd=rng.integers(0, 40, n_hits) / 20.0, rotation=rot,
+                                  centre0=np.zeros((n_hits, 3)), centre1=np.zeros((n_hits, 3)))
+    run = _BatchRun(jess, mols, (2.0, 1.5, 1.5, None, True, False), False)
+    run.done, run.table = True, table
+    bounds = np.searchsorted(mol, np.arange(len(mols) + 1))
+    run._slices = [np.arange(bounds[m], bounds[m + 1]) for m in range(len(mols))]
+    return [Query(jess, m, 2.0, False, None, None, run, i) for i, m in enumerate(mols)]
+
+
+@pytest.mark.parametrize("flag", [True, False])
+def test_best_sites_over_a_hit_table_equals_the_text_route(flag):
+    """`best_sites` (arrays of the hit table) == `filter_text` (pinned to the script above) on
+    the dump of every hit, `Hit.dump` text included."""
+    from pyjess_b200 import sites
+    text = io.StringIO()
+    for query in _fake_queries(3000, 5):
+        for hit in query:
+            hit.dump(text)
+            text.write("\n")
+    text.seek(0)
+    want = io.StringIO()
+    n = sites.filter_text(text, want, all_instances=flag)
+    hits = sites.best_sites(_fake_queries(3000, 5), all_instances=flag)
+    got = io.StringIO()
+    sites.write_hits(hits, got)
+    assert 0 < n == len(hits) < 3000
+    assert got.getvalue() == want.getvalue()
+
+
+def test_best_sites_rejects_what_it_cannot_filter():
+    from pyjess_b200 import sites
+    queries = _fake_queries(50, 1)
+    next(q for q in queries if len(q.hit_table()[1]))._pos = 1
+    with pytest.raises(RuntimeError):
+        sites.best_sites(queries)
+    with pytest.raises(TypeError):
+        sites.best_sites([object()])
+    assert sites.best_sites([]) == []
