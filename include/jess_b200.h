@@ -191,6 +191,14 @@ int jb_context_create(int device, void *stream, int64_t workspace_bytes,
                       jb_context **out);
 void jb_context_destroy(jb_context *ctx);
 int jb_context_synchronize(jb_context *ctx);
+/* The context's device buffers (candidate lists, frontiers, hit tables, ordering workspace,
+ * staging of jb_query_host) only grow, to the largest workload and hit volume seen -- the
+ * counterpart of the reference's per-query malloc/free (Scanner_create .. JessQuery_free,
+ * eff:Jess.c:119-167).  jb_context_trim waits for the stream and frees them all; they are
+ * re-allocated on demand.  Runs whose hits were not fetched yet are discarded (their
+ * jb_result_fetch fails with JB_ERR_INVALID).  jb_query_run / jb_query_host /
+ * jb_molecules_upload do this themselves, once, before they report JB_ERR_NOMEM.          */
+int jb_context_trim(jb_context *ctx);
 
 /* ---- templates: replaces Jess_create + Jess_addTemplate (jess.pxd:18-21,
  * eff:Jess.c:79-117) and TessTemplate_copy (eff:TessTemplate.c:388-460).

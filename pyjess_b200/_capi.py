@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("JB_LIB_PATH") or os.path.join(HERE, "libjess_b200.so"
 
 EXPORTS = [
     "jb_abi_version", "jb_last_error", "jb_device_count",
-    "jb_context_create", "jb_context_destroy", "jb_context_synchronize",
+    "jb_context_create", "jb_context_destroy", "jb_context_synchronize", "jb_context_trim",
     "jb_templates_create", "jb_templates_free", "jb_templates_spec_count",
     "jb_molecules_upload", "jb_molecules_free",
     "jb_query_run", "jb_result_fetch", "jb_result_stats", "jb_result_free", "jb_query_host",
@@ -56,6 +56,7 @@ def load_library():
                 "jb_context_create": (i32, [i32, vp, i64, P(vp)]),
                 "jb_context_destroy": (None, [vp]),
                 "jb_context_synchronize": (i32, [vp]),
+                "jb_context_trim": (i32, [vp]),
                 "jb_templates_create": (i32, [vp, P(jb_template_table), P(vp)]),
                 "jb_templates_free": (None, [vp]),
                 "jb_templates_spec_count": (i32, [vp]),
@@ -108,6 +109,11 @@ class Context:
 
     def synchronize(self):
         _check(self.lib.jb_context_synchronize(self._h))
+
+    def trim(self):
+        """Give the context's grow-only device buffers back (`jb_context_trim`)."""
+        with self.lock:
+            _check(self.lib.jb_context_trim(self._h))
 
 
 class DeviceTemplates:

@@ -470,8 +470,9 @@ class Molecule:
     @classmethod
     def load(cls, file, format: str = "detect", *, id=None, date=None, name=None,
              ignore_endmdl: bool = False, use_author: bool = False, skip_hetatm: bool = False):
-        """Read a PDB file (``PDBMoleculeParser.load``, src/pyjess/_io.py:68-103).
-        mmCIF input is outside the query hot path and not supported."""
+        """Read a PDB file (``PDBMoleculeParser.load``, src/pyjess/_io.py:68-103: the native
+        one-pass parser) or an mmCIF file (``CIFMoleculeParser``, _io.py:105-245: `_cif`, no
+        gemmi needed); ``format="detect"`` as src/pyjess/_jess.pyx:407-441."""
         try:
             handle = open(file, "rb")
             close = True
@@ -484,6 +485,12 @@ class Molecule:
                 handle.close()
         if isinstance(data, str):
             data = data.encode("utf-8")
+        if format not in ("pdb", "cif", "detect"):
+            raise ValueError(f"invalid value for `format` argument: {format!r}")
+        from . import _cif
+        if format == "cif" or (format == "detect" and _cif.looks_like_cif(data)):
+            return _cif.load_molecule(data.decode("utf-8"), cls, id=id, date=date, name=name, use_author=use_author,
+                                      skip_hetatm=skip_hetatm, ignore_endmdl=ignore_endmdl)
         return cls._parse_pdb(data, id=id, date=date, name=name,
                               ignore_endmdl=ignore_endmdl, skip_hetatm=skip_hetatm, format=format)
 
@@ -496,8 +503,6 @@ class Molecule:
     def _parse_pdb(cls, data: bytes, *, id, date, name, ignore_endmdl, skip_hetatm, format):
         """One pass of the engine library's native parser (`jb_pdb_parse`, csrc/ingest.cu)
         over the file image; only the optional HEADER line is decoded in Python."""
-        if format not in ("pdb", "detect"):
-            raise ValueError(f"unsupported format on the B200 path: {format!r} (PDB only)")
         from . import _capi
         data = bytes(data)
         cap = data.count(b"ATOM") + data.count(b"HETATM")

@@ -128,6 +128,7 @@ struct jb_context {
     std::vector<std::pair<void *, size_t>> pin_pool;           // page-locked result blocks, recycled
     long long hit_cap = 0;
     int hit_stride = 0;
+    long long trim_epoch = 0;     // bumped by jb_context_trim: un-fetched results of earlier runs are gone
     Counters *host_ctr = nullptr; // pinned
     struct jb_molecules *scratch_mol = nullptr;   // reused by jb_query_host (no per-call cudaMalloc)
     struct jb_molecules *slice_mol[2] = { nullptr, nullptr };   // double-buffered staging of the pipelined jb_query_host
@@ -169,6 +170,7 @@ struct jb_result {
     int n_templates = 0;
     jb_stats stats{};
     bool fetched = false;
+    long long trim_epoch = 0;
     void *block = nullptr;    // page-locked host block holding the fetched arrays (from ctx->pin_pool)
     size_t block_bytes = 0;
     size_t block_cap = 0;     // records the block is laid out for
@@ -176,6 +178,8 @@ struct jb_result {
     int32_t *mol = nullptr, *tpl = nullptr, *atoms = nullptr;
     double *rmsd = nullptr, *rot = nullptr, *c0 = nullptr, *c1 = nullptr;
 };
+
+static void context_trim(jb_context *c);
 
 // ---- library -----------------------------------------------------------------------
 extern "C" int jb_abi_version(void) { return JB_ABI_VERSION; }
@@ -236,17 +240,50 @@ extern "C" int jb_context_create(int device, void *stream, int64_t workspace_byt
     return JB_OK;
 }
 
+// Every grow-only device buffer of the context except the two small ones allocated at creation (counters,
+// ordering work list).  They only ever grow to the largest workload seen; jb_context_trim gives the memory back.
+static std::vector<DevBuf *> context_buffers(jb_context *c)
+{
+    return { &c->crec, &c->chead, &c->cxtab, &c->recs, &c->ordbuf, &c->fr[0], &c->fr[1],
+             &c->tuples, &c->h_mol, &c->h_tpl, &c->h_atoms, &c->h_rmsd, &c->h_rot, &c->h_c0,
+             &c->h_c1, &c->f_mol, &c->f_tpl, &c->f_atoms, &c->f_rmsd, &c->f_rot, &c->f_c0, &c->f_c1,
+             &c->o_off, &c->o_fill, &c->o_grouped, &c->o_order, &c->o_tiles, &c->o_runs,
+             &c->k_key, &c->k_key2, &c->k_iota, &c->k_runid, &c->k_scan, &c->h_pair, &c->h_keys, &c->q_ocnt, &c->q_keyA,
+             &c->q_keyA2, &c->q_keyB, &c->q_keyB2, &c->q_iota, &c->q_perm, &c->q_setpos, &c->q_kdrank, &c->q_coords,
+             &c->q_kdidx, &c->q_cub };
+}
+
+static void context_trim(jb_context *c)
+{
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    cudaGetLastError();                               // a failed cudaMalloc leaves its (non-sticky) error behind
+    for (DevBuf *b : context_buffers(c)) b->release();
+    for (jb_molecules *m : { c->scratch_mol, c->slice_mol[0], c->slice_mol[1] })
+        if (m) for (DevBuf *b : m->all()) b->release();
+    for (auto &blk : c->pin_pool) cudaFreeHost(blk.first);
+    c->pin_pool.clear();
+    c->hit_cap = 0;
+    c->hit_stride = 0;
+    c->trim_epoch++;                                  // results not fetched yet lived in these buffers
+}
+
+extern "C" int jb_context_trim(jb_context *c)
+{
+    if (!c) return fail(JB_ERR_INVALID, "jb_context_trim: NULL context");
+    context_trim(c);
+    return JB_OK;
+}
+
 extern "C" void jb_context_destroy(jb_context *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = { &c->crec, &c->chead, &c->cxtab, &c->recs, &c->ordbuf, &c->fr[0], &c->fr[1],
-                       &c->tuples, &c->ctr, &c->h_mol, &c->h_tpl, &c->h_atoms, &c->h_rmsd, &c->h_rot, &c->h_c0,
-                       &c->h_c1, &c->f_mol, &c->f_tpl, &c->f_atoms, &c->f_rmsd, &c->f_rot, &c->f_c0, &c->f_c1,
-                       &c->o_off, &c->o_fill, &c->o_grouped, &c->o_order, &c->o_tiles, &c->o_runs, &c->o_work,
-                       &c->k_key, &c->k_key2, &c->k_iota, &c->k_runid, &c->k_scan, &c->h_pair, &c->h_keys, &c->q_ocnt, &c->q_keyA, &c->q_keyA2, &c->q_keyB, &c->q_keyB2, &c->q_iota,
-                       &c->q_perm, &c->q_setpos, &c->q_kdrank, &c->q_coords, &c->q_kdidx, &c->q_cub };
+    std::vector<DevBuf *> bufs = context_buffers(c);
+    bufs.push_back(&c->ctr);
+    bufs.push_back(&c->o_work);
     for (DevBuf *b : bufs) b->release();
     for (jb_molecules *m : { c->scratch_mol, c->slice_mol[0], c->slice_mol[1] })
         if (m) {
@@ -544,7 +581,11 @@ extern "C" int jb_molecules_upload(jb_context *c, const jb_molecule_batch *b, jb
     CU(cudaSetDevice(c->device));
     jb_molecules *m = new jb_molecules();
     m->ctx = c;
-    const int rc = fill_molecules(c, m, b);
+    int rc = fill_molecules(c, m, b);
+    if (rc == JB_ERR_NOMEM) {                         // the context's idle buffers may hold the memory (see jb_query_run)
+        context_trim(c);
+        rc = fill_molecules(c, m, b);
+    }
     if (rc != JB_OK) { jb_molecules_free(m); return rc; }
     *out = m;
     return JB_OK;
@@ -1120,8 +1161,24 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
     return JB_OK;
 }
 
+static int query_run_once(jb_context *c, const jb_templates *t, const jb_molecules *mol, const jb_query_params *q,
+                          jb_result **out);
+
+// Out of device memory: the grow-only buffers of the context may still be sized for an earlier, larger
+// workload (or hit volume) -- give them back and try once more before reporting JB_ERR_NOMEM.
 extern "C" int jb_query_run(jb_context *c, const jb_templates *t, const jb_molecules *mol, const jb_query_params *q,
                             jb_result **out)
+{
+    int rc = query_run_once(c, t, mol, q, out);
+    if (rc == JB_ERR_NOMEM && c) {
+        context_trim(c);
+        rc = query_run_once(c, t, mol, q, out);
+    }
+    return rc;
+}
+
+static int query_run_once(jb_context *c, const jb_templates *t, const jb_molecules *mol, const jb_query_params *q,
+                          jb_result **out)
 {
     if (!c || !t || !mol || !q || !out) return fail(JB_ERR_INVALID, "jb_query_run: NULL argument");
     *out = nullptr;
@@ -1134,6 +1191,7 @@ extern "C" int jb_query_run(jb_context *c, const jb_templates *t, const jb_molec
     res->stride = std::max(t->nmax, 1);
     res->best_match = q->all_tuples ? 0 : q->best_match;
     res->n_templates = t->T;
+    res->trim_epoch = c->trim_epoch;
     const int rc = query_run_impl(c, t, mol, q, res);
     if (rc != JB_OK) { delete res; return rc; }
     *out = res;
@@ -1227,6 +1285,8 @@ extern "C" int jb_result_fetch(jb_result *r, jb_hits *out)
     jb_context *c = r->ctx;
     CU(cudaSetDevice(c->device));
     if (!r->fetched) {
+        if (r->trim_epoch != c->trim_epoch)
+            return fail(JB_ERR_INVALID, "jb_result_fetch: the hits of this run were discarded by jb_context_trim");
         const double t_0 = now_ms();
         const size_t n = (size_t)r->count;
         int rc = result_alloc_block(r, n);
@@ -1291,6 +1351,7 @@ static int query_host_pipelined(jb_context *c, const jb_templates *t, const jb_m
     res->stride = std::max(t->nmax, 1);
     res->best_match = q->all_tuples ? 0 : q->best_match;
     res->n_templates = t->T;
+    res->trim_epoch = c->trim_epoch;
     int rc = result_alloc_block(res, (size_t)std::max<long long>(c->last_hits + c->last_hits / 8, 1 << 16));
     bool direct = rc == JB_OK;                        // hits still fit the block laid out above
     size_t copied = 0;
@@ -1331,8 +1392,22 @@ static int query_host_pipelined(jb_context *c, const jb_templates *t, const jb_m
     return jb_result_fetch(res, hits);
 }
 
+static int query_host_once(jb_context *c, const jb_templates *t, const jb_molecule_batch *b, const jb_query_params *q,
+                           jb_result **out, jb_hits *hits);
+
 extern "C" int jb_query_host(jb_context *c, const jb_templates *t, const jb_molecule_batch *b, const jb_query_params *q,
                              jb_result **out, jb_hits *hits)
+{
+    int rc = query_host_once(c, t, b, q, out, hits);
+    if (rc == JB_ERR_NOMEM && c) {                    // same policy as jb_query_run
+        context_trim(c);
+        rc = query_host_once(c, t, b, q, out, hits);
+    }
+    return rc;
+}
+
+static int query_host_once(jb_context *c, const jb_templates *t, const jb_molecule_batch *b, const jb_query_params *q,
+                           jb_result **out, jb_hits *hits)
 {
     if (!c || !b || !out || !hits) return fail(JB_ERR_INVALID, "jb_query_host: NULL argument");
     *out = nullptr;
@@ -1356,7 +1431,7 @@ extern "C" int jb_query_host(jb_context *c, const jb_templates *t, const jb_mole
     if (!c->scratch_mol) c->scratch_mol = new jb_molecules();
     int rc = fill_molecules(c, c->scratch_mol, b);      // grow-only device staging owned by the context
     if (rc != JB_OK) return rc;
-    rc = jb_query_run(c, t, c->scratch_mol, q, out);
+    rc = query_run_once(c, t, c->scratch_mol, q, out);
     if (rc == JB_OK) c->last_hits = (*out)->count;
     if (rc == JB_OK) rc = jb_result_fetch(*out, hits);
     if (rc != JB_OK && *out) { jb_result_free(*out); *out = nullptr; }

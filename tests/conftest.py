@@ -36,3 +36,15 @@ def engine():
     """The CUDA engine context on cuda:0 (gpu tests only)."""
     from pyjess_b200 import _capi
     return _capi.default_context()
+
+
+@pytest.fixture(autouse=True)
+def _device_memory_log(request):
+    """JB_MEMLOG=<file>: free device memory after every test (leak hunting on the GPU box)."""
+    yield
+    path = os.environ.get("JB_MEMLOG")
+    if path:
+        import torch
+        free, total = torch.cuda.mem_get_info()
+        with open(path, "a") as f:
+            f.write(f"{(total - free) / 2**20:10.0f} MiB used after {request.node.nodeid}\n")

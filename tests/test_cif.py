@@ -1,0 +1,200 @@
+"""mmCIF ingest without gemmi (pyjess_b200/_cif.py) against the reference's OWN mmCIF tests
+(src/pyjess/tests/test_molecule.py:254-397, skipped upstream when gemmi is missing): same files
+(tests/data/1AMY.cif / 1AMY.pdb from the reference's test data), same assertions -- the CIF
+molecule equals the PDB molecule atom by atom -- plus tokenizer cases (quotes, text fields,
+comments, pairs instead of loops, missing columns, several blocks)."""
+import datetime
+import io
+import itertools
+import os
+import textwrap
+import warnings
+
+import pytest
+
+from pyjess_b200 import Molecule
+from pyjess_b200 import _cif
+
+from _util import DATA
+
+PDB, CIF = os.path.join(DATA, "1AMY.pdb"), os.path.join(DATA, "1AMY.cif")
+
+
+def assert_atom_equal(a1, a2, hetero=False):
+    """assertAtomEqual / assertHeteroAtomEqual (test_molecule.py:46-77)."""
+    if not hetero:
+        assert a1.serial == a2.serial
+        assert a1.chain_id == a2.chain_id
+        assert a1.residue_number == a2.residue_number
+    assert a1.name == a2.name
+    assert a1.altloc == a2.altloc
+    assert a1.residue_name == a2.residue_name
+    assert a1.insertion_code == a2.insertion_code
+    assert a1.element == a2.element
+    for f in ("x", "y", "z", "occupancy", "temperature_factor", "charge"):
+        assert getattr(a1, f) == pytest.approx(getattr(a2, f), abs=1e-5)
+
+
+def _load_cif(**kw):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        with open(CIF) as f:
+            return Molecule.load(f, format="cif", **kw)
+
+
+def test_cif_dump():
+    """test_molecule.py:255-277"""
+    with open(CIF) as f:
+        text = f.read()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        cif_molecule = Molecule.loads(text, format="cif")
+    expected = textwrap.dedent(
+        """
+        HEADER    HYDROLASE (O-GLYCOSYL)                  13-MAY-95   1AMY
+        ATOM      1  N   GLN A   1       6.240  48.686  17.460  1.00 27.79           N
+        ATOM      2  CA  GLN A   1       5.440  49.851  17.773  1.00 16.62           C
+        ATOM      3  C   GLN A   1       6.628  50.721  18.086  1.00 14.24           C
+        ATOM      4  O   GLN A   1       7.313  50.396  19.052  1.00 11.61           O
+        ATOM      5  CB  GLN A   1       4.588  49.715  19.030  1.00 18.54           C
+        """
+    ).strip()
+    assert cif_molecule[0:5].dumps().strip() == expected
+
+
+def test_cif_vs_pdb():
+    """test_molecule.py:280-303"""
+    cif_molecule = _load_cif()
+    with open(PDB) as f:
+        pdb_molecule = Molecule.loads(f.read(), format="pdb")
+    first5_pdb, first5_cif = pdb_molecule[0:5], cif_molecule[0:5]
+    assert first5_pdb == first5_cif
+    assert first5_pdb.dumps(write_header=False).strip() == first5_cif.dumps(write_header=False).strip()
+
+
+@pytest.mark.parametrize("via", ["load", "loads"])
+def test_load_mmcif_comment(via):
+    """test_molecule.py:306-343: comment lines before data_, explicit and detected format."""
+    buffer = io.StringIO()
+    buffer.write("# this is a comment line \n")
+    buffer.write("# and a second comment line \n")
+    with open(CIF) as f:
+        buffer.write(f.read())
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for fmt in ("cif", "detect"):
+            if via == "load":
+                buffer.seek(0)
+                mol = Molecule.load(buffer, format=fmt)
+            else:
+                mol = Molecule.loads(buffer.getvalue(), format=fmt)
+            assert len(mol) == 3339
+
+
+@pytest.mark.parametrize("use_author", [False, True])
+def test_load_consistency_no_skip_hetatm(use_author):
+    """test_molecule.py:346-372"""
+    pdb_molecule = Molecule.load(PDB, format="pdb")
+    cif_molecule = _load_cif(use_author=use_author)
+    assert len(cif_molecule) == len(pdb_molecule) == 3339
+    for pdb_atom, cif_atom in itertools.islice(zip(pdb_molecule, cif_molecule), 3184):
+        assert_atom_equal(pdb_atom, cif_atom)
+    for pdb_atom, cif_atom in itertools.islice(zip(pdb_molecule, cif_molecule), 3184, 3339):
+        assert_atom_equal(pdb_atom, cif_atom, hetero=True)
+
+
+@pytest.mark.parametrize("use_author", [False, True])
+def test_load_consistency_skip_hetatm(use_author):
+    """test_molecule.py:375-397"""
+    pdb_molecule = Molecule.load(PDB, format="pdb", skip_hetatm=True)
+    cif_molecule = _load_cif(skip_hetatm=True, use_author=use_author)
+    assert len(cif_molecule) == len(pdb_molecule) == 3184
+    for pdb_atom, cif_atom in zip(pdb_molecule, cif_molecule):
+        assert_atom_equal(pdb_atom, cif_atom)
+
+
+def test_hetatm_without_residue_number_warns_and_numbers_like_the_reference():
+    """_io.py:185-199: label_seq_id '.' on a HETATM row -> UserWarning, the running maximum as
+    residue number (then incremented); use_author reads auth_seq_id instead (no warning)."""
+    with pytest.warns(UserWarning, match="HETATM line found without residue number"):
+        with open(CIF) as f:
+            mol = Molecule.load(f, format="cif")
+    het = [a for a in mol][3184:]
+    assert [a.residue_number for a in het[:3]] == [403, 404, 405]          # max label_seq_id is 403
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        with open(CIF) as f:
+            auth = Molecule.load(f, format="cif", use_author=True)
+    assert [a.residue_number for a in [a for a in auth][3184:3187]] == [500, 501, 502]
+    assert mol.id == "1AMY" and mol.name == "HYDROLASE (O-GLYCOSYL)"
+    assert mol.date == datetime.datetime(1995, 5, 13)                       # earliest revision_date
+
+
+MINI = """\
+# comment
+data_mini
+_entry.id 'MINI'
+_struct.title
+;A title in a
+text field
+;
+loop_
+_atom_site.group_PDB
+_atom_site.id
+_atom_site.type_symbol
+_atom_site.label_atom_id
+_atom_site.label_alt_id
+_atom_site.label_comp_id
+_atom_site.label_asym_id
+_atom_site.label_seq_id
+_atom_site.Cartn_x
+_atom_site.Cartn_y
+_atom_site.Cartn_z
+_atom_site.occupancy
+_atom_site.B_iso_or_equiv
+_atom_site.pdbx_PDB_model_num
+_atom_site.note
+ATOM 1 N N . GLY A 1 1.0 2.0 3.0 1.00 10.0 1 'two words' # trailing comment
+ATOM 2 C CA A GLY A 1 1.5 2.5 3.5 . . 1 'it's quoted'
+HETATM 3 O "O5'" . GLY A 2 4.0 5.0
+6.0 0.50 20.0 1
+;text
+field
+;
+ATOM 4 N N . GLY A 1 1.0 2.0 3.0 1.00 10.0 2 x#not-a-comment
+"""
+
+
+def test_tokenizer_cases():
+    mol = Molecule.loads(MINI)                       # detected: comment line, then data_
+    assert mol.id == "mini" and mol.date is None
+    assert mol.name == ";A title in a\ntext field\n;"            # raw value, like gemmi's find_value
+    atoms = list(mol)
+    assert len(atoms) == 3                            # model 2 stops the scan
+    assert [a.name for a in atoms] == ["N", "CA", "O5'"]
+    assert atoms[1].altloc == "A" and atoms[0].altloc == " "
+    assert atoms[1].occupancy == 0.0 and atoms[1].temperature_factor == 0.0
+    assert (atoms[2].x, atoms[2].y, atoms[2].z) == (4.0, 5.0, 6.0)
+    assert atoms[0].insertion_code == " " and atoms[0].charge == 0          # optional columns absent
+    assert len(Molecule.loads(MINI, ignore_endmdl=True)) == 4
+    assert len(Molecule.loads(MINI, skip_hetatm=True)) == 2
+    blocks = _cif.read_blocks(MINI)
+    assert blocks[0].find_value("_entry.id") == "'MINI'"
+    assert blocks[0].find("_atom_site.", ["id", "?nope"])[0] == ["1", None]
+    assert [r[0] for r in blocks[0].find("_atom_site.", ["note"])] == ["'two words'", "'it's quoted'", ";text\nfield\n;",
+                                                                       "x#not-a-comment"]
+
+
+def test_errors():
+    with pytest.raises(ValueError, match="missing columns"):
+        Molecule.loads(MINI.replace("_atom_site.Cartn_z\n", "_atom_site.Cartn_zz\n"), format="cif")
+    with pytest.raises(ValueError, match="missing columns"):
+        Molecule.loads("data_empty\n_entry.id X\n", format="cif")
+    with pytest.raises(RuntimeError, match="single data block"):
+        Molecule.loads(MINI + "data_second\n_entry.id Y\n", format="cif")
+    with pytest.raises(ValueError, match="CIF syntax error"):
+        Molecule.loads("data_x\nloop_\n_a.b\n_a.c\n1 2 3\n", format="cif")
+    with pytest.raises(ValueError, match="invalid value for `format`"):
+        Molecule.loads(MINI, format="xyz")
+    with pytest.raises(ValueError, match="mmCIF data tags found"):
+        Molecule.loads(MINI, format="pdb")

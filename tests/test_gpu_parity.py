@@ -249,3 +249,37 @@ def test_candidate_record_overflow_is_retried(engine, oracle_lib, monkeypatch):
     assert stats["retries"] > 0 and stats["candidate_records"] > 4096
     for a, b in zip(base.arrays(), table.arrays()):
         assert np.array_equal(a, b)
+
+
+def test_context_trim_releases_buffers_and_runs_again(engine):
+    """jb_context_trim: the grow-only device buffers go back to the driver, the next run
+    re-allocates them and returns the same table; hits of a run that was not fetched before the
+    trim are refused instead of being read from freed memory."""
+    import torch
+    from pyjess_b200 import _capi, synth
+    from pyjess_b200._tables import query_params
+    tpl, mols, thr, kw = synth.workload("cfg3", scale=0.05)
+    params = query_params(*thr, **kw)
+    base, _ = run_engine(engine, tpl, mols, params)
+    free0, _ = torch.cuda.mem_get_info()
+    engine.trim()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free1 > free0
+    again, _ = run_engine(engine, tpl, mols, params)
+    assert again.count == base.count > 0
+    for a, b in zip(base.arrays(), again.arrays()):
+        assert np.array_equal(a, b)
+    # un-fetched result across a trim
+    dev = _capi.DeviceTemplates(engine, TemplateTable(tpl))
+    dmol = _capi.DeviceMolecules(engine, MoleculeBatch(mols))
+    try:
+        res = _capi.query_run(engine, dev, dmol, params)
+        engine.trim()
+        with pytest.raises(_capi.EngineError, match="jb_context_trim"):
+            res.fetch()
+        res.close()
+        fresh = _capi.query_run(engine, dev, dmol, params).fetch()
+        assert fresh.count == base.count
+    finally:
+        dmol.close()
+        dev.close()
