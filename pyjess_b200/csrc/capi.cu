@@ -54,9 +54,11 @@ static double now_ms()
 struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0;
+    size_t recent = 0;        // largest request since the last context_decay
     // grow-only; contents are NOT preserved unless keep > 0 (bytes to copy over)
     cudaError_t ensure(size_t need, cudaStream_t st, size_t keep = 0)
     {
+        recent = std::max(recent, need);
         if (need <= bytes) return cudaSuccess;
         size_t nb = std::max(need, bytes + bytes / 2);
         nb = (nb + 255) & ~(size_t)255;
@@ -73,7 +75,7 @@ struct DevBuf {
         bytes = nb;
         return cudaSuccess;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; recent = 0; }
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
@@ -128,6 +130,8 @@ struct jb_context {
     std::vector<std::pair<void *, size_t>> pin_pool;           // page-locked result blocks, recycled
     long long hit_cap = 0;
     int hit_stride = 0;
+    size_t decay_bytes = (size_t)1 << 30;   // JB_DECAY_BYTES
+    int runs_since_decay = 0;     // context_decay: every kDecayRuns calls, buffers far larger than recently needed go back
     long long trim_epoch = 0;     // bumped by jb_context_trim: un-fetched results of earlier runs are gone
     Counters *host_ctr = nullptr; // pinned
     struct jb_molecules *scratch_mol = nullptr;   // reused by jb_query_host (no per-call cudaMalloc)
@@ -225,6 +229,7 @@ extern "C" int jb_context_create(int device, void *stream, int64_t workspace_byt
             if (*p == ',') p++;
         }
     }
+    if (const char *g = getenv("JB_DECAY_BYTES")) c->decay_bytes = (size_t)std::max(0ll, atoll(g));
     if (const char *g = getenv("JB_DEBUG")) c->debug = atoi(g);
     if (const char *g = getenv("JB_LEGACY")) c->legacy = atoi(g);
     if (const char *g = getenv("JB_PIPELINE")) c->pipeline_slices = atoi(g);
@@ -267,6 +272,36 @@ static void context_trim(jb_context *c)
     c->hit_cap = 0;
     c->hit_stride = 0;
     c->trim_epoch++;                                  // results not fetched yet lived in these buffers
+}
+
+// High-water marks are not forever: every kDecayRuns engine calls, a buffer of more than decay_bytes (1 GiB) that
+// no call since the last check needed a quarter of is released (one pathological query -- e.g. every
+// tuple of a 3-atom template -- otherwise pins tens of GB for the life of the context).  Called at the
+// start of a call: the previous run's un-fetched hits are invalid from here on anyway.
+constexpr int kDecayRuns = 8;
+
+static void context_decay(jb_context *c)
+{
+    if (++c->runs_since_decay < kDecayRuns) return;
+    c->runs_since_decay = 0;
+    std::vector<DevBuf *> bufs = context_buffers(c);
+    for (jb_molecules *m : { c->scratch_mol, c->slice_mol[0], c->slice_mol[1] })
+        if (m) for (DevBuf *b : m->all()) bufs.push_back(b);
+    bool synced = false, released = false;
+    for (DevBuf *b : bufs) {
+        if (b->bytes > c->decay_bytes && b->recent < b->bytes / 4) {
+            if (!synced) {
+                cudaSetDevice(c->device);
+                cudaStreamSynchronize(c->stream);
+                if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+                synced = true;
+            }
+            b->release();
+            released = true;
+        }
+        b->recent = 0;
+    }
+    if (released) { c->hit_cap = 0; c->hit_stride = 0; }   // grow_hits re-checks every hit array
 }
 
 extern "C" int jb_context_trim(jb_context *c)
@@ -1169,6 +1204,7 @@ static int query_run_once(jb_context *c, const jb_templates *t, const jb_molecul
 extern "C" int jb_query_run(jb_context *c, const jb_templates *t, const jb_molecules *mol, const jb_query_params *q,
                             jb_result **out)
 {
+    if (c) context_decay(c);
     int rc = query_run_once(c, t, mol, q, out);
     if (rc == JB_ERR_NOMEM && c) {
         context_trim(c);
@@ -1398,6 +1434,7 @@ static int query_host_once(jb_context *c, const jb_templates *t, const jb_molecu
 extern "C" int jb_query_host(jb_context *c, const jb_templates *t, const jb_molecule_batch *b, const jb_query_params *q,
                              jb_result **out, jb_hits *hits)
 {
+    if (c) context_decay(c);
     int rc = query_host_once(c, t, b, q, out, hits);
     if (rc == JB_ERR_NOMEM && c) {                    // same policy as jb_query_run
         context_trim(c);
