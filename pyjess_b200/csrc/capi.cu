@@ -978,6 +978,19 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
             S.classify_ms += ms[0]; S.pairs_ms += ms[1]; S.expand_ms += ms[2]; S.superpose_ms += ms[3];
         }
 
+        // what this chunk really used of the grow-only buffers (context_decay releases the ones left idle)
+        {
+            auto used = [](DevBuf &b, size_t bytes) { b.recent = std::max(b.recent, std::min(bytes, b.bytes)); };
+            used(c->crec, (size_t)hc.cand_total * sizeof(float4));
+            for (int l = 0; l < t->nmax; l++) used(c->fr[l & 1], (size_t)hc.level[l + 1] * (l + 2) * sizeof(int));
+            used(c->tuples, (size_t)hc.tuples * tuple_stride * sizeof(int));
+            const size_t nhits = (size_t)std::min<u64>(hc.hits, (u64)c->hit_cap);   // cumulative over the run
+            DevBuf *hb[] = { &c->h_mol, &c->h_tpl, &c->h_atoms, &c->h_rmsd, &c->h_rot, &c->h_c0, &c->h_c1, &c->f_mol, &c->f_tpl,
+                             &c->f_atoms, &c->f_rmsd, &c->f_rot, &c->f_c0, &c->f_c1, &c->h_pair, &c->h_keys };
+            for (DevBuf *b : hb)
+                if (c->hit_cap > 0) used(*b, (size_t)((double)b->bytes * (double)nhits / (double)c->hit_cap));
+        }
+
         // ---- capacity checks: grow and retry, or split the chunk --------------------
         bool retry = false, split = false;
         if ((long long)hc.cand_total > CT.cap) {

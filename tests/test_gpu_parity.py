@@ -286,29 +286,33 @@ def test_context_trim_releases_buffers_and_runs_again(engine):
 
 
 def test_oversized_buffers_decay_after_a_few_small_runs(monkeypatch):
-    """High-water marks are not forever (context_decay): a run reporting every tuple of 3-atom
-    templates inflates the hit buffers; after a handful of ordinary runs they are given back.
-    (JB_DECAY_BYTES lowers the 1 GiB per-buffer threshold so that a small workload shows it.)"""
+    """High-water marks are not forever (context_decay): after a large batch, a handful of small
+    runs give the candidate / pair / hit buffers back, and a steady workload keeps its buffers.
+    (JB_DECAY_BYTES lowers the 1 GiB per-buffer threshold so that a test-sized workload shows it.)"""
     import torch
     from _util import load_molecule, load_template
-    from pyjess_b200 import Template, _capi
+    from pyjess_b200 import _capi, synth
     from pyjess_b200._tables import query_params
-    monkeypatch.setenv("JB_DECAY_BYTES", str(8 << 20))
+    monkeypatch.setenv("JB_DECAY_BYTES", str(1 << 20))
     ctx = _capi.Context(0)
+    used = lambda: (lambda f, t: t - f)(*torch.cuda.mem_get_info())  # noqa: E731
     try:
-        full = [load_template(n) for n in ("template_01.qry", "template_02.qry", "1.3.3.tpl", "4.1.2.tpl")]
-        short = [Template(list(t)[k:k + 3], id=f"{t.id}-{k}") for t in full for k in (0, 3)]
-        mols = [load_molecule("pdb1lnb.ent"), load_molecule("1AMY.pdb")]
+        tpl, mols, thr, kw = synth.workload("cfg3", scale=0.3)
+        big = query_params(*thr, **kw)
+        first, _ = run_engine(ctx, tpl, mols, big)
+        steady = []
+        for _ in range(18):                                     # steady large workload: nothing is released
+            again, _ = run_engine(ctx, tpl, mols, big)
+            steady.append(used())
+        assert max(steady) - min(steady) < 4 << 20
+        assert again.count == first.count and all(np.array_equal(a, b) for a, b in zip(first.arrays(), again.arrays()))
+        few = [load_template("template_01.qry"), load_template("template_02.qry")]
+        one = [load_molecule("pdb1lnb.ent")]
         small = query_params(2.0, 3.0, 3.0)
-        base, _ = run_engine(ctx, full[:2], mols, small)
-        free_start, _ = torch.cuda.mem_get_info()
-        every, _ = run_engine(ctx, short, mols, query_params(2.0, 1.0, 1.0, all_tuples=True))
-        free_big, _ = torch.cuda.mem_get_info()
-        assert free_start - free_big > 256 << 20, "the workload no longer inflates the buffers: pick a larger one"
-        for _ in range(16):
-            again, _ = run_engine(ctx, full[:2], mols, small)
-        free_after, _ = torch.cuda.mem_get_info()
-        assert free_after - free_big > 128 << 20
-        assert again.count == base.count and all(np.array_equal(a, b) for a, b in zip(base.arrays(), again.arrays()))
+        base, _ = run_engine(ctx, few, one, small)
+        low = min(used() for _ in range(18) if run_engine(ctx, few, one, small))
+        assert steady[-1] - low > 16 << 20
+        back, _ = run_engine(ctx, tpl, mols, big)               # and the large batch still runs
+        assert back.count == first.count and all(np.array_equal(a, b) for a, b in zip(first.arrays(), back.arrays()))
     finally:
         ctx.close()
