@@ -131,6 +131,7 @@ struct jb_context {
     long long hit_cap = 0;
     int hit_stride = 0;
     size_t decay_bytes = (size_t)1 << 30;   // JB_DECAY_BYTES
+    int decay_runs = 64;                    // JB_DECAY_RUNS
     int runs_since_decay = 0;     // context_decay: every kDecayRuns calls, buffers far larger than recently needed go back
     long long trim_epoch = 0;     // bumped by jb_context_trim: un-fetched results of earlier runs are gone
     Counters *host_ctr = nullptr; // pinned
@@ -230,6 +231,7 @@ extern "C" int jb_context_create(int device, void *stream, int64_t workspace_byt
         }
     }
     if (const char *g = getenv("JB_DECAY_BYTES")) c->decay_bytes = (size_t)std::max(0ll, atoll(g));
+    if (const char *g = getenv("JB_DECAY_RUNS")) c->decay_runs = std::max(1, atoi(g));
     if (const char *g = getenv("JB_DEBUG")) c->debug = atoi(g);
     if (const char *g = getenv("JB_LEGACY")) c->legacy = atoi(g);
     if (const char *g = getenv("JB_PIPELINE")) c->pipeline_slices = atoi(g);
@@ -274,22 +276,23 @@ static void context_trim(jb_context *c)
     c->trim_epoch++;                                  // results not fetched yet lived in these buffers
 }
 
-// High-water marks are not forever: every kDecayRuns engine calls, a buffer of more than decay_bytes (1 GiB) that
-// no call since the last check needed a quarter of is released (one pathological query -- e.g. every
-// tuple of a 3-atom template -- otherwise pins tens of GB for the life of the context).  Called at the
-// start of a call: the previous run's un-fetched hits are invalid from here on anyway.
-constexpr int kDecayRuns = 8;
-
+// High-water marks are not forever: every decay_runs (64) engine calls, a buffer of more than decay_bytes
+// (1 GiB) that no call since the last check used an eighth of is released (one pathological query -- e.g.
+// every tuple of a 3-atom template -- otherwise pins tens of GB for the life of the context).  Lazy on
+// purpose: re-growing a frontier buffer costs a re-run of the chunk that overflowed, so a service that
+// alternates batch sizes (or bench.py, whose sliced end-to-end calls use a quarter of what its resident
+// calls sized) must not pay that every few calls -- measured with 8 calls / a quarter: cfg5 end to end
+// 85 -> 153 ms.  Called at the start of a call: the previous run's un-fetched hits are invalid from here on.
 static void context_decay(jb_context *c)
 {
-    if (++c->runs_since_decay < kDecayRuns) return;
+    if (++c->runs_since_decay < c->decay_runs) return;
     c->runs_since_decay = 0;
     std::vector<DevBuf *> bufs = context_buffers(c);
     for (jb_molecules *m : { c->scratch_mol, c->slice_mol[0], c->slice_mol[1] })
         if (m) for (DevBuf *b : m->all()) bufs.push_back(b);
     bool synced = false, released = false;
     for (DevBuf *b : bufs) {
-        if (b->bytes > c->decay_bytes && b->recent < b->bytes / 4) {
+        if (b->bytes > c->decay_bytes && b->recent < b->bytes / 8) {
             if (!synced) {
                 cudaSetDevice(c->device);
                 cudaStreamSynchronize(c->stream);

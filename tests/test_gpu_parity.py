@@ -288,12 +288,13 @@ def test_context_trim_releases_buffers_and_runs_again(engine):
 def test_oversized_buffers_decay_after_a_few_small_runs(monkeypatch):
     """High-water marks are not forever (context_decay): after a large batch, a handful of small
     runs give the candidate / pair / hit buffers back, and a steady workload keeps its buffers.
-    (JB_DECAY_BYTES lowers the 1 GiB per-buffer threshold so that a test-sized workload shows it.)"""
+    (JB_DECAY_BYTES / JB_DECAY_RUNS lower the 1 GiB / 64-call thresholds so that a test-sized workload shows it.)"""
     import torch
     from _util import load_molecule, load_template
     from pyjess_b200 import _capi, synth
     from pyjess_b200._tables import query_params
     monkeypatch.setenv("JB_DECAY_BYTES", str(1 << 20))
+    monkeypatch.setenv("JB_DECAY_RUNS", "8")
     ctx = _capi.Context(0)
     used = lambda: (lambda f, t: t - f)(*torch.cuda.mem_get_info())  # noqa: E731
     try:
