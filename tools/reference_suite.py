@@ -14,6 +14,16 @@ GPU box with `gpurun`), `--run` executes it there, `--clean` removes it.
 
 Round 1 result on a B200: 82 tests, OK (11 skipped: gemmi / biopython / biotite are not
 installed -- the same skips the reference itself reports in this image).
+
+`--cif-shim` additionally stages an empty stand-in module named `gemmi`: the reference gates its
+mmCIF tests on `import gemmi` (test_molecule.py:17-20,254-397), while this package reads mmCIF
+without it (`pyjess_b200/_cif.py`), so with the stand-in those tests run UNCHANGED against the
+gemmi-free loader; the one test that needs the real library (`test_from_gemmi`) skips itself
+through the stand-in's `read_pdb_string`.  `test_molecule` needs no GPU:
+
+    python tools/reference_suite.py --stage --cif-shim --run test_molecule
+
+With the stand-in on a B200: 82 tests, OK, 3 skipped (biopython, biotite and `test_from_gemmi`).
 """
 import argparse
 import os
@@ -29,12 +39,25 @@ EXPORTS = ("from pyjess_b200 import Atom, Mat4, Molecule, Template, TemplateAtom
 MODULES = ["test_atom", "test_molecule", "test_template", "test_template_atom", "test_jess", "test_hit"]
 
 
-def stage():
+GEMMI_STANDIN = '''"""Stand-in for `gemmi` (not installed): lets the reference's gemmi-gated mmCIF tests run against
+pyjess_b200's own reader.  Anything that needs the real library skips the test."""
+import unittest
+
+
+def read_pdb_string(*args, **kwargs):
+    raise unittest.SkipTest("the real gemmi library is not installed")
+'''
+
+
+def stage(cif_shim=False):
     clean()
     os.makedirs(os.path.join(SHIM, "pyjess"))
     for name in ("__init__.py", "_jess.py"):
         with open(os.path.join(SHIM, "pyjess", name), "w") as f:
             f.write(EXPORTS + ('__version__ = "0.10.1"\n' if name == "__init__.py" else ""))
+    if cif_shim:
+        with open(os.path.join(SHIM, "gemmi.py"), "w") as f:
+            f.write(GEMMI_STANDIN)
     shutil.copytree(os.path.join(REF, "src", "pyjess", "tests"), os.path.join(SHIM, "pyjess", "tests"), symlinks=False)
 
 
@@ -52,11 +75,12 @@ if __name__ == "__main__":
     ap.add_argument("--stage", action="store_true")
     ap.add_argument("--run", action="store_true")
     ap.add_argument("--clean", action="store_true")
+    ap.add_argument("--cif-shim", action="store_true", help="stage a stand-in `gemmi` module (see the module docstring)")
     ap.add_argument("modules", nargs="*", default=MODULES)
     args = ap.parse_args()
     rc = 0
     if args.stage:
-        stage()
+        stage(args.cif_shim)
     if args.run:
         rc = run(args.modules)
     if args.clean:
