@@ -198,3 +198,36 @@ def test_errors():
         Molecule.loads(MINI, format="xyz")
     with pytest.raises(ValueError, match="mmCIF data tags found"):
         Molecule.loads(MINI, format="pdb")
+
+
+@pytest.mark.parametrize("kw", [{}, {"skip_hetatm": True}, {"ignore_endmdl": True}])
+@pytest.mark.parametrize("columns", ["_PRIMARY", "_AUTHOR"])
+def test_column_builder_equals_the_reference_row_loop(kw, columns):
+    """`_records_from_columns` (what the loader runs) == `_records_from_rows` (the reference's loop
+    as written, one `Atom` per row), byte for byte, on 1AMY.cif and on the tokenizer example."""
+    for text in (open(CIF).read(), MINI):
+        block = _cif.read_blocks(text)[0]
+        cols = getattr(_cif, columns)
+        if block.find("_atom_site.", cols) is None:
+            continue                                   # MINI has no auth_* columns
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            fast = _cif._records_from_columns(block.find_columns("_atom_site.", cols), **kw)
+            slow = _cif._records_from_rows(block.find("_atom_site.", cols), **kw)
+        assert len(fast) == len(slow) > 0 and fast.tobytes() == slow.tobytes()
+
+
+def test_line_tokenizer_equals_the_grammar():
+    """The line-wise fast path of `_tokens` against the token grammar applied to the whole text."""
+    for text in (open(CIF).read(), MINI, MINI.replace("\n", "\r\n")):
+        want = [t for t in _cif._TOKEN.findall(text.replace("\r\n", "\n")) if not t.startswith("#")]
+        assert _cif._tokens(text) == want
+    with pytest.raises(ValueError, match="unterminated text field"):
+        _cif._tokens("data_x\n_a.b\n;never closed\n")
+
+
+def test_invalid_fields_raise_like_atom():
+    with pytest.raises(ValueError, match="Invalid residue name"):
+        Molecule.loads(MINI.replace(" GLY A 2 ", " GLYX A 2 "), format="cif")
+    with pytest.raises(ValueError):
+        Molecule.loads(MINI.replace("ATOM 1 N N . GLY A 1 ", "ATOM 1 N N . GLY A . "), format="cif")   # int(".")
