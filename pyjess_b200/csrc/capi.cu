@@ -304,7 +304,14 @@ static void context_decay(jb_context *c)
         }
         b->recent = 0;
     }
-    if (released) { c->hit_cap = 0; c->hit_stride = 0; }   // grow_hits re-checks every hit array
+    if (released) {
+        // hit_cap describes ALL hit arrays: it only survives when none of them went (a needless reset would cost
+        // the next large run a chunk re-run through grow_hits)
+        DevBuf *hb[] = { &c->h_mol, &c->h_tpl, &c->h_atoms, &c->h_rmsd, &c->h_rot, &c->h_c0, &c->h_c1, &c->f_mol, &c->f_tpl,
+                         &c->f_atoms, &c->f_rmsd, &c->f_rot, &c->f_c0, &c->f_c1, &c->h_pair, &c->h_keys };
+        for (DevBuf *b : hb)
+            if (b->bytes == 0) { c->hit_cap = 0; c->hit_stride = 0; break; }
+    }
 }
 
 extern "C" int jb_context_trim(jb_context *c)

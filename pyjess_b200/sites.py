@@ -110,6 +110,23 @@ def _residue_ids(records: np.ndarray) -> np.ndarray:
     return key | (records["resSeq"].astype(np.int64) + 1024)
 
 
+def _residue_ids_from_text(records: np.ndarray, atoms: np.ndarray, ids: dict) -> np.ndarray:
+    """Residue identifiers of the matched atoms `atoms` ([hit][atom], -1 padding) read from the
+    dumped lines themselves: a serial above 99,999 or a residue number above 9,999 widens its
+    field and shifts the columns the script slices, so only the text tells what it sees."""
+    from . import _capi
+    used = np.unique(atoms[atoms >= 0])
+    lines = _capi.format_atoms_pdb(np.ascontiguousarray(records[used])).splitlines()
+    key = np.empty(len(used), dtype=np.int64)
+    for j, line in enumerate(lines):
+        line = line.strip()
+        res = (line[17:20].strip(), line[20:22].strip(), line[22:26].strip())
+        key[j] = (1 << 62) + ids.setdefault(res, len(ids))   # above every packed key (< 2**56)
+    lookup = np.full(len(records), -1, dtype=np.int64)
+    lookup[used] = key
+    return np.where(atoms >= 0, lookup[np.maximum(atoms, 0)], -1)
+
+
 def _fixed_columns(records: np.ndarray) -> bool:
     """Whether every dumped line keeps the fixed columns the script slices: `%5i` serial and
     `%4i` residue number do not overflow their fields (_jess.pyx:1273-1291)."""
@@ -132,6 +149,7 @@ def best_sites(queries, all_instances: bool = True) -> list:
     sites, log_es, selfs, owners, pair_of_row = [], [], [], [], []
     mol_names: dict = {}
     tpl_names: dict = {}
+    text_ids: dict = {}        # residue strings of structures whose numbers overflow the fixed columns
     per_jess: dict = {}        # id(jess) -> (dim[t], name id[t]) of its templates
     for q, query in enumerate(queries):
         if not isinstance(query, Query):
@@ -144,8 +162,6 @@ def best_sites(queries, all_instances: bool = True) -> list:
         mol = query.molecule
         if mol.id is None:
             raise RuntimeError("cannot filter hits where `molecule.id` is `None`")
-        if not _fixed_columns(mol._atoms):
-            raise ValueError("serial or residue numbers overflow the fixed PDB columns the filter reads")
         if id(query.jess) not in per_jess:
             templates = query.jess._templates
             if any(t.id is None for t in templates):
@@ -155,9 +171,12 @@ def best_sites(queries, all_instances: bool = True) -> list:
                                                    dtype=np.int64))
         dim, tpl_name = per_jess[id(query.jess)]
         tpl = table.template[rows].astype(np.int64)
-        res = _residue_ids(mol._atoms)
         atoms = table.atoms[rows].astype(np.int64)
-        sites.append(np.where(atoms >= 0, res[np.maximum(atoms, 0)], -1))
+        if _fixed_columns(mol._atoms):
+            res = _residue_ids(mol._atoms)
+            sites.append(np.where(atoms >= 0, res[np.maximum(atoms, 0)], -1))
+        else:
+            sites.append(_residue_ids_from_text(mol._atoms, atoms, text_ids))
         # Hit.log_evalue (TessTemplate_logE) evaluated in the same order of operations
         log_es.append(-8.5 + 2.5 * table.rmsd[rows] + -0.7 * dim[tpl] + math.log(float(len(mol))))
         # Match.from_remark splits the REMARK line on blanks: names are compared as printed

@@ -102,13 +102,19 @@ def test_select_sites_empty_and_shapes():
     assert got.tolist() == [1, 2]
 
 
-def _fake_queries(n_hits, seed):
-    """`Query` objects over a hand-made hit table (the host layer only: no engine call)."""
+def _fake_queries(n_hits, seed, wide=False):
+    """`Query` objects over a hand-made hit table (the host layer only: no engine call).
+    `wide`: serial and residue numbers that overflow the fixed PDB columns in some structures."""
     import types
     from pyjess_b200 import Template, synth
     from pyjess_b200._jess import Jess, Query, _BatchRun
     tpl, mols, thr, _ = synth.workload("cfg3", scale=0.012)
     tpl = [Template(list(t), id=mols[1].id if i == 2 else t.id) for i, t in enumerate(tpl)]      # a self match
+    if wide:
+        mols = [type(m)._from_records(m._atoms.copy(), id=m.id) for m in mols]
+        for m in mols[::2]:
+            m._atoms["serial"] += 99990                      # six-digit serials shift every later column
+            m._atoms["resSeq"][m._atoms["resSeq"] > 150] += 9900     # five-digit residue numbers too
     jess = Jess.__new__(Jess)
     jess._templates = tpl
     rng = np.random.default_rng(seed)
@@ -131,20 +137,21 @@ def _fake_queries(n_hits, seed):
     return [Query(jess, m, 2.0, False, None, None, run, i) for i, m in enumerate(mols)]
 
 
+@pytest.mark.parametrize("wide", [False, True])
 @pytest.mark.parametrize("flag", [True, False])
-def test_best_sites_over_a_hit_table_equals_the_text_route(flag):
+def test_best_sites_over_a_hit_table_equals_the_text_route(flag, wide):
     """`best_sites` (arrays of the hit table) == `filter_text` (pinned to the script above) on
     the dump of every hit, `Hit.dump` text included."""
     from pyjess_b200 import sites
     text = io.StringIO()
-    for query in _fake_queries(3000, 5):
+    for query in _fake_queries(3000, 5, wide):
         for hit in query:
             hit.dump(text)
             text.write("\n")
     text.seek(0)
     want = io.StringIO()
     n = sites.filter_text(text, want, all_instances=flag)
-    hits = sites.best_sites(_fake_queries(3000, 5), all_instances=flag)
+    hits = sites.best_sites(_fake_queries(3000, 5, wide), all_instances=flag)
     got = io.StringIO()
     sites.write_hits(hits, got)
     assert 0 < n == len(hits) < 3000
