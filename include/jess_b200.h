@@ -278,6 +278,37 @@ typedef struct jb_pdb_info {
 int jb_pdb_parse(const char *text, int64_t n_bytes, int32_t flags,
                  jb_atom_record *records, int64_t capacity, jb_pdb_info *info);
 
+/* ---- mmCIF ingest (HOST code): replaces gemmi's reader + the row loop of
+ * CIFMoleculeParser._load_block (src/pyjess/_io.py:167-219) for well-formed files: one pass over
+ * the file image, the rows of the loop holding `_atom_site.id` -> `records`.  `flags`: the two
+ * JB_PDB_* flags (skip_hetatm; ignore_endmdl = every pdbx_PDB_model_num) and JB_CIF_USE_AUTHOR.
+ * Whatever the reference answers with an exception, and number spellings beyond plain decimals,
+ * are left to the host layer's generic loader: info->fallback != 0 (no records are valid).      */
+#define JB_CIF_USE_AUTHOR 4          /* CIFMoleculeParser(use_author=True): auth_* columns      */
+
+typedef enum jb_cif_fallback {
+    JB_CIF_NONE = 0,
+    JB_CIF_SYNTAX = 1,               /* unterminated text field, value without tag, ragged loop */
+    JB_CIF_BLOCKS = 2,               /* not exactly one data_ block (Document.sole_block)       */
+    JB_CIF_LAYOUT = 3,               /* no / duplicate / missing _atom_site columns, or pairs   */
+    JB_CIF_VALUE = 4                 /* a field Atom() rejects or int()/float() must judge      */
+} jb_cif_fallback;
+
+typedef struct jb_cif_info {
+    int64_t n_atoms;                 /* records found (may exceed capacity)                     */
+    int64_t loop_offset;             /* byte range of the _atom_site loop (`loop_` .. last      */
+    int64_t loop_end;                /* value): the metadata reader skips it                    */
+    int32_t n_blocks;
+    int32_t hetatm_unnumbered;       /* HETATM rows numbered from the running maximum: one
+                                      * UserWarning each in the reference (_io.py:185-199)      */
+    int32_t fallback;                /* jb_cif_fallback                                         */
+    int32_t reserved;
+} jb_cif_info;
+
+/* JB_ERR_CAPACITY: info->n_atoms tells the capacity to retry with.                            */
+int jb_cif_parse(const char *text, int64_t n_bytes, int32_t flags, jb_atom_record *records,
+                 int64_t capacity, jb_cif_info *info);
+
 /* ---- packing (HOST code): the per-molecule _Atom arrays of M Molecules -> the
  * SoA staging image of jb_molecule_batch (what Molecule.__init__,
  * src/pyjess/_jess.pyx:632-684, hands to the C library one struct at a time).

@@ -10,7 +10,7 @@ import os
 import threading
 from typing import Optional
 
-from ._tables import (HitTable, MoleculeBatch, TemplateTable, jb_hits, jb_molecule_batch, jb_pdb_info,
+from ._tables import (HitTable, MoleculeBatch, TemplateTable, jb_cif_info, jb_hits, jb_molecule_batch, jb_pdb_info,
                       jb_query_params, jb_stats, jb_template_table)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -22,7 +22,7 @@ EXPORTS = [
     "jb_templates_create", "jb_templates_free", "jb_templates_spec_count",
     "jb_molecules_upload", "jb_molecules_free",
     "jb_query_run", "jb_result_fetch", "jb_result_stats", "jb_result_free", "jb_query_host",
-    "jb_pdb_parse", "jb_format_atoms_pdb", "jb_molecules_pack",
+    "jb_pdb_parse", "jb_cif_parse", "jb_format_atoms_pdb", "jb_molecules_pack",
 ]
 
 _lib = None
@@ -68,6 +68,7 @@ def load_library():
                 "jb_result_free": (None, [vp]),
                 "jb_query_host": (i32, [vp, vp, P(jb_molecule_batch), P(jb_query_params), P(vp), P(jb_hits)]),
                 "jb_pdb_parse": (i32, [C.c_char_p, i64, i32, vp, i64, P(jb_pdb_info)]),
+                "jb_cif_parse": (i32, [C.c_char_p, i64, i32, vp, i64, P(jb_cif_info)]),
                 "jb_format_atoms_pdb": (i64, [vp, i64, vp, vp, i64]),
                 "jb_molecules_pack": (i32, [vp, vp, i32] + [vp] * 9),
             }
@@ -214,6 +215,25 @@ def pdb_parse(data: bytes, records, skip_hetatm: bool = False, ignore_endmdl: bo
     if rc not in (0, -4):
         _check(rc)
     return info
+
+
+def cif_parse(data: bytes, dtype, skip_hetatm: bool = False, ignore_endmdl: bool = False, use_author: bool = False):
+    """One-pass native reader of the `_atom_site` loop of an mmCIF file (`jb_cif_parse`).
+    Returns (info, records); `info.fallback != 0`: the generic Python loader must decide."""
+    import numpy as np
+    lib = load_library()
+    info = jb_cif_info()
+    flags = (1 if skip_hetatm else 0) | (2 if ignore_endmdl else 0) | (4 if use_author else 0)
+    cap = data.count(b"\nATOM") + data.count(b"\nHETATM") + 1
+    while True:
+        records = np.zeros(cap, dtype=dtype)
+        rc = lib.jb_cif_parse(data, len(data), flags, C.c_void_p(records.ctypes.data), len(records), C.byref(info))
+        if rc == -4 and not info.fallback:            # JB_ERR_CAPACITY: rows not at line starts
+            cap = int(info.n_atoms)
+            continue
+        if rc != 0:
+            _check(rc)
+        return info, records[:min(int(info.n_atoms), cap)]
 
 
 _fmt_buf = None

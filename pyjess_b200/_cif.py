@@ -198,16 +198,36 @@ _AUTHOR = ["id", "type_symbol", "auth_atom_id", "label_alt_id", "auth_comp_id", 
 
 def load_molecule(text: str, molecule_type, *, id=None, date=None, name=None, use_author=False, skip_hetatm=False,
                   ignore_endmdl=False):
-    """``CIFMoleculeParser._load_block`` (src/pyjess/_io.py:167-245) on `text`."""
+    """``CIFMoleculeParser._load_block`` (src/pyjess/_io.py:167-245) on `text` (str or bytes).
+
+    Well-formed files take the native one-pass reader of the engine library (`jb_cif_parse`,
+    csrc/ingest.cu) for the atom table -- the Python tokenizer then only sees the rest of the
+    file for the identifier, name and date; anything else (and every error) goes through the
+    generic loader below."""
+    arr = None
+    if isinstance(text, (bytes, bytearray)):
+        data = bytes(text)
+        from . import _capi
+        from ._model import ATOM_DTYPE
+        info, records = _capi.cif_parse(data, ATOM_DTYPE, skip_hetatm=skip_hetatm, ignore_endmdl=ignore_endmdl,
+                                        use_author=use_author)
+        if not info.fallback:
+            arr = records
+            for _ in range(info.hetatm_unnumbered):
+                warnings.warn(_HETATM_WARNING, UserWarning, stacklevel=4)
+            text = (data[:info.loop_offset] + b"\n" + data[info.loop_end:]).decode("utf-8")
+        else:
+            text = data.decode("utf-8")
     blocks = read_blocks(text)
     if len(blocks) != 1:
         # gemmi: Document.sole_block()
         raise RuntimeError(f"single data block expected, got {len(blocks)}")
     block = blocks[0]
-    if not block.find_columns("_atom_site.", _AUTHOR if use_author else _PRIMARY):
-        raise ValueError("missing columns in CIF files")
-    arr = _records_from_columns(block.find_columns("_atom_site.", _AUTHOR if use_author else _PRIMARY),
-                                skip_hetatm=skip_hetatm, ignore_endmdl=ignore_endmdl)
+    if arr is None:
+        if not block.find_columns("_atom_site.", _AUTHOR if use_author else _PRIMARY):
+            raise ValueError("missing columns in CIF files")
+        arr = _records_from_columns(block.find_columns("_atom_site.", _AUTHOR if use_author else _PRIMARY),
+                                    skip_hetatm=skip_hetatm, ignore_endmdl=ignore_endmdl)
     if id is None:
         id = block.name
     if name is None:

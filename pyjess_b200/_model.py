@@ -489,7 +489,7 @@ class Molecule:
             raise ValueError(f"invalid value for `format` argument: {format!r}")
         from . import _cif
         if format == "cif" or (format == "detect" and _cif.looks_like_cif(data)):
-            return _cif.load_molecule(data.decode("utf-8"), cls, id=id, date=date, name=name, use_author=use_author,
+            return _cif.load_molecule(data, cls, id=id, date=date, name=name, use_author=use_author,
                                       skip_hetatm=skip_hetatm, ignore_endmdl=ignore_endmdl)
         return cls._parse_pdb(data, id=id, date=date, name=name,
                               ignore_endmdl=ignore_endmdl, skip_hetatm=skip_hetatm, format=format)

@@ -83,6 +83,18 @@ class jb_pdb_info(C.Structure):
     ]
 
 
+class jb_cif_info(C.Structure):
+    _fields_ = [
+        ("n_atoms", C.c_int64),
+        ("loop_offset", C.c_int64),
+        ("loop_end", C.c_int64),
+        ("n_blocks", C.c_int32),
+        ("hetatm_unnumbered", C.c_int32),
+        ("fallback", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
 class jb_hits(C.Structure):
     _fields_ = [
         ("count", C.c_int64),

@@ -9,6 +9,7 @@
 // C atoi/atof PREFIX parsing from the field's first column, fields beyond the end of the
 // line keep their zero value, tokens copied with blanks/NULs turned into '_'.
 #include <cctype>
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstdint>
@@ -145,6 +146,286 @@ extern "C" int jb_pdb_parse(const char *text, int64_t n_bytes, int32_t flags, jb
     }
     info->n_atoms = n_atoms;
     info->stop_offset = pos;
+    return n_atoms > capacity ? JB_ERR_CAPACITY : JB_OK;
+}
+
+
+// ---- mmCIF: the _atom_site loop -> packed atom records (HOST code) ------------------------
+// CIFMoleculeParser._load_block (src/pyjess/_io.py:167-219) for well-formed files, in one pass over the
+// file image: a CIF 1.1 tokenizer (comments, quoted strings closed by quote + white space, `;` text fields)
+// that only looks INTO the tokens of the loop holding `_atom_site.id`, and the reference's row loop (first
+// model unless JB_PDB_IGNORE_ENDMDL, ATOM / HETATM selection, running-maximum numbering of HETATM rows
+// without a sequence number, `Atom.__init__` encodings).  Everything the reference would answer with an
+// exception, and everything Python's int()/float() accept beyond plain decimals, is NOT decided here:
+// info->fallback names the reason and the host layer runs its generic loader (pyjess_b200/_cif.py), which
+// produces the same records on the files both accept (tests/test_cif.py compares them byte for byte).
+namespace {
+
+struct Tok { const char *p; int64_t n; };
+
+struct CifScanner {
+    const char *s; int64_t n, i = 0;
+    bool bad = false;                                  // unterminated text field
+    static bool ws(unsigned char c) { return c == ' ' || (c >= '\t' && c <= '\r') || (c >= 0x1c && c <= 0x1f); }
+    bool line_start(int64_t k) const { return k == 0 || s[k - 1] == '\n' || s[k - 1] == '\r'; }
+    bool next(Tok *t)
+    {
+        for (;;) {
+            while (i < n && ws((unsigned char)s[i])) i++;
+            if (i >= n) return false;
+            const char c = s[i];
+            if (c == '#') { while (i < n && s[i] != '\n' && s[i] != '\r') i++; continue; }
+            if (c == ';' && line_start(i)) {           // text field: up to the next line starting with ';'
+                const int64_t b = i;
+                int64_t k = i + 1;
+                for (;;) {
+                    while (k < n && s[k] != '\n' && s[k] != '\r') k++;
+                    if (k >= n) { bad = true; return false; }
+                    k++;
+                    if (k < n && s[k] == ';') break;
+                    if (k >= n) { bad = true; return false; }
+                }
+                i = k + 1;
+                t->p = s + b; t->n = i - b;
+                return true;
+            }
+            const int64_t b = i;
+            if (c == '\'' || c == '"') {               // closed by the same quote followed by white space / end
+                for (int64_t k = i + 1; k < n && s[k] != '\n' && s[k] != '\r'; k++)
+                    if (s[k] == c && (k + 1 >= n || ws((unsigned char)s[k + 1]))) {
+                        i = k + 1;
+                        t->p = s + b; t->n = i - b;
+                        return true;
+                    }
+            }
+            while (i < n && !ws((unsigned char)s[i])) i++;     // bare word (or a quote that never closes)
+            t->p = s + b; t->n = i - b;
+            return true;
+        }
+    }
+};
+
+inline bool tok_ieq(const Tok &t, const char *lit)
+{
+    const int64_t m = (int64_t)strlen(lit);
+    if (t.n != m) return false;
+    for (int64_t k = 0; k < m; k++) if (tolower((unsigned char)t.p[k]) != tolower((unsigned char)lit[k])) return false;
+    return true;
+}
+inline bool tok_iprefix(const Tok &t, const char *lit)
+{
+    const int64_t m = (int64_t)strlen(lit);
+    if (t.n < m) return false;
+    for (int64_t k = 0; k < m; k++) if (tolower((unsigned char)t.p[k]) != tolower((unsigned char)lit[k])) return false;
+    return true;
+}
+inline bool tok_eq(const Tok &t, const char *lit) { return t.n == (int64_t)strlen(lit) && memcmp(t.p, lit, (size_t)t.n) == 0; }
+inline bool cif_keyword(const Tok &t)
+{
+    if (t.n == 0) return false;
+    if (t.p[0] == '_') return true;
+    return tok_iprefix(t, "data_") || tok_iprefix(t, "loop_") || tok_iprefix(t, "save_") || tok_ieq(t, "stop_") || tok_ieq(t, "global_");
+}
+inline bool tok_ascii(const Tok &t)
+{
+    for (int64_t k = 0; k < t.n; k++) if ((unsigned char)t.p[k] >= 0x80) return false;
+    return true;
+}
+// int(): plain [+-]digits only (underscores, blanks, other bases: the generic loader decides)
+inline bool tok_int(const Tok &t, int64_t *out)
+{
+    int64_t k = 0;
+    bool neg = false;
+    if (k < t.n && (t.p[k] == '+' || t.p[k] == '-')) { neg = t.p[k] == '-'; k++; }
+    if (k >= t.n || t.n - k > 15) return false;
+    int64_t v = 0;
+    for (; k < t.n; k++) {
+        if (t.p[k] < '0' || t.p[k] > '9') return false;
+        v = v * 10 + (t.p[k] - '0');
+    }
+    *out = neg ? -v : v;
+    return true;
+}
+// float(): [+-]digits[.digits][e[+-]digits] / [+-].digits -- correctly rounded like Python's (strtod)
+inline bool tok_float(const Tok &t, double *out)
+{
+    if (t.n == 0 || t.n > 40) return false;
+    int64_t k = 0;
+    if (t.p[k] == '+' || t.p[k] == '-') k++;
+    int64_t digits = 0;
+    while (k < t.n && t.p[k] >= '0' && t.p[k] <= '9') { k++; digits++; }
+    if (k < t.n && t.p[k] == '.') {
+        k++;
+        while (k < t.n && t.p[k] >= '0' && t.p[k] <= '9') { k++; digits++; }
+    }
+    if (digits == 0) return false;
+    if (k < t.n && (t.p[k] == 'e' || t.p[k] == 'E')) {
+        k++;
+        if (k < t.n && (t.p[k] == '+' || t.p[k] == '-')) k++;
+        int64_t ed = 0;
+        while (k < t.n && t.p[k] >= '0' && t.p[k] <= '9') { k++; ed++; }
+        if (ed == 0) return false;
+    }
+    if (k != t.n) return false;
+    char buf[48];
+    memcpy(buf, t.p, (size_t)t.n);
+    buf[t.n] = 0;
+    *out = parse_double(buf);
+    return true;
+}
+// _encode_token (src/pyjess/_jess.pyx:133-140): n bytes, blank / NUL -> '_'
+inline void encode_token(char *d, const char *s, int64_t len, int n)
+{
+    for (int k = 0; k < n; k++) {
+        const char c = k < len ? s[k] : 0;
+        d[k] = (c == ' ' || c == 0) ? '_' : c;
+    }
+}
+
+enum { C_ID, C_ELEM, C_NAME, C_ALT, C_RES, C_CHAIN, C_SEQ, C_ICODE, C_X, C_Y, C_Z, C_OCC, C_B, C_CHARGE, C_GROUP, C_MODEL, C_COUNT };
+const char *const kPrimary[C_COUNT] = { "id", "type_symbol", "label_atom_id", "label_alt_id", "label_comp_id", "label_asym_id",
+    "label_seq_id", "pdbx_PDB_ins_code", "Cartn_x", "Cartn_y", "Cartn_z", "occupancy", "B_iso_or_equiv", "pdbx_formal_charge",
+    "group_PDB", "pdbx_PDB_model_num" };
+const char *const kAuthor[C_COUNT] = { "id", "type_symbol", "auth_atom_id", "label_alt_id", "auth_comp_id", "auth_asym_id",
+    "auth_seq_id", "pdbx_PDB_ins_code", "Cartn_x", "Cartn_y", "Cartn_z", "occupancy", "B_iso_or_equiv", "pdbx_formal_charge",
+    "group_PDB", "pdbx_PDB_model_num" };
+inline bool optional_column(int c) { return c == C_ICODE || c == C_CHARGE || c == C_GROUP; }
+
+}  // namespace
+
+extern "C" int jb_cif_parse(const char *text, int64_t n_bytes, int32_t flags, jb_atom_record *records, int64_t capacity,
+                            jb_cif_info *info)
+{
+    if (!text || !info || n_bytes < 0 || capacity < 0 || (capacity > 0 && !records)) return JB_ERR_INVALID;
+    memset(info, 0, sizeof(*info));
+    info->loop_offset = info->loop_end = -1;
+    const bool skip_hetatm = (flags & JB_PDB_SKIP_HETATM) != 0, ignore_endmdl = (flags & JB_PDB_IGNORE_ENDMDL) != 0;
+    const char *const *names = (flags & JB_CIF_USE_AUTHOR) ? kAuthor : kPrimary;
+    const int kMaxTags = 256;
+    CifScanner sc{ text, n_bytes };
+    Tok t;
+    bool have = sc.next(&t), found = false;
+    int64_t n_atoms = 0;
+#define CIF_FALLBACK(code) do { info->fallback = (code); info->n_atoms = n_atoms; return JB_OK; } while (0)
+    while (have) {
+        if (tok_iprefix(t, "data_")) { info->n_blocks++; have = sc.next(&t); continue; }
+        if (info->n_blocks == 0) CIF_FALLBACK(JB_CIF_SYNTAX);
+        if (tok_iprefix(t, "save_")) { have = sc.next(&t); continue; }
+        if (!tok_ieq(t, "loop_")) {
+            if (t.p[0] != '_') CIF_FALLBACK(JB_CIF_SYNTAX);                   // a value outside any pair / loop
+            if (tok_ieq(t, "_atom_site.id")) CIF_FALLBACK(JB_CIF_LAYOUT);     // atom table given as pairs
+            have = sc.next(&t);
+            if (!have || cif_keyword(t)) CIF_FALLBACK(JB_CIF_SYNTAX);         // tag without a value
+            have = sc.next(&t);
+            continue;
+        }
+        // ---- a loop: tags, then values up to the next keyword -------------------------------
+        const int64_t loop_offset = t.p - text;
+        int col[C_COUNT];
+        for (int c = 0; c < C_COUNT; c++) col[c] = -1;
+        int n_tags = 0;
+        bool mine = false, dup = false;
+        while ((have = sc.next(&t)) && t.p[0] == '_') {
+            if (!found && tok_iprefix(t, "_atom_site.")) {
+                const Tok item{ t.p + 11, t.n - 11 };
+                if (tok_ieq(item, "id")) mine = true;
+                for (int c = 0; c < C_COUNT; c++)
+                    if (tok_ieq(item, names[c])) { if (col[c] >= 0) dup = true; col[c] = n_tags; }
+            }
+            n_tags++;
+        }
+        if (n_tags == 0) CIF_FALLBACK(JB_CIF_SYNTAX);
+        if (!mine) {                                                          // someone else's loop: skip its values
+            while (have && !cif_keyword(t)) have = sc.next(&t);
+            continue;
+        }
+        found = true;
+        info->loop_offset = loop_offset;
+        if (dup || n_tags > kMaxTags) CIF_FALLBACK(JB_CIF_LAYOUT);
+        for (int c = 0; c < C_COUNT; c++)
+            if (col[c] < 0 && !optional_column(c)) CIF_FALLBACK(JB_CIF_LAYOUT);   // "missing columns in CIF files"
+        Tok row[kMaxTags];
+        bool stopped = false;                  // a later model was met: the remaining rows are only skipped
+        int64_t highest = 0;                   // max_residue_number
+        int k = 0;
+        const char *last_end = t.p;
+        for (; have && !cif_keyword(t); have = sc.next(&t)) {
+            last_end = t.p + t.n;
+            row[k++] = t;
+            if (k < n_tags) continue;
+            k = 0;
+            if (stopped) continue;
+            if (!ignore_endmdl && !tok_eq(row[col[C_MODEL]], "1")) { stopped = true; continue; }
+            if (col[C_GROUP] < 0) continue;
+            const Tok &g = row[col[C_GROUP]];
+            const bool het = tok_eq(g, "HETATM");
+            if (!tok_eq(g, "ATOM") && (!het || skip_hetatm)) continue;
+            for (int c = 0; c < C_COUNT; c++)
+                if (col[c] >= 0 && !tok_ascii(row[col[c]])) CIF_FALLBACK(JB_CIF_VALUE);
+            int64_t seq = 0, serial = 0, charge = 0;
+            const Tok &ts = row[col[C_SEQ]];
+            if (het && tok_eq(ts, ".")) { seq = highest; highest++; info->hetatm_unnumbered++; }
+            else {
+                if (!tok_int(ts, &seq)) CIF_FALLBACK(JB_CIF_VALUE);
+                if (seq > highest) highest = seq;
+            }
+            if (!tok_int(row[col[C_ID]], &serial)) CIF_FALLBACK(JB_CIF_VALUE);
+            if (serial < INT32_MIN || serial > INT32_MAX || seq < INT32_MIN || seq > INT32_MAX) CIF_FALLBACK(JB_CIF_VALUE);
+            Tok name = row[col[C_NAME]];       // row[2].strip('"')
+            while (name.n > 0 && name.p[0] == '"') { name.p++; name.n--; }
+            while (name.n > 0 && name.p[name.n - 1] == '"') name.n--;
+            const Tok &elem = row[col[C_ELEM]], &alt = row[col[C_ALT]], &res = row[col[C_RES]], &chain = row[col[C_CHAIN]];
+            if (name.n > 4 || res.n > 3 || elem.n > 2 || chain.n > 2 || alt.n != 1) CIF_FALLBACK(JB_CIF_VALUE);
+            char icode = ' ';
+            if (col[C_ICODE] >= 0 && !tok_eq(row[col[C_ICODE]], "?")) {
+                if (row[col[C_ICODE]].n != 1) CIF_FALLBACK(JB_CIF_VALUE);
+                icode = row[col[C_ICODE]].p[0];
+            }
+            if (col[C_CHARGE] >= 0 && !tok_eq(row[col[C_CHARGE]], "?")) {
+                if (!tok_int(row[col[C_CHARGE]], &charge) || charge < -128 || charge > 127) CIF_FALLBACK(JB_CIF_VALUE);
+            }
+            double x[3], occ = 0.0, b = 0.0;
+            for (int d = 0; d < 3; d++) if (!tok_float(row[col[C_X + d]], &x[d])) CIF_FALLBACK(JB_CIF_VALUE);
+            if (!tok_eq(row[col[C_OCC]], ".") && !tok_float(row[col[C_OCC]], &occ)) CIF_FALLBACK(JB_CIF_VALUE);
+            if (!tok_eq(row[col[C_B]], ".") && !tok_float(row[col[C_B]], &b)) CIF_FALLBACK(JB_CIF_VALUE);
+            if (n_atoms < capacity) {
+                jb_atom_record *A = &records[n_atoms];
+                memset(A, 0, sizeof(*A));
+                A->x[0] = x[0]; A->x[1] = x[1]; A->x[2] = x[2];
+                A->occupancy = (float)occ;
+                A->temp_factor = (float)b;
+                A->serial = (int32_t)serial;
+                // Atom.__init__ (pyjess_b200/_model.py, src/pyjess/_jess.pyx:1010-1076): names shorter than four
+                // characters get a leading '_'; element right-justified; one-character chains go to chainID2
+                char raw[4];
+                int len = (int)name.n;
+                if (len < 4) { raw[0] = '_'; memcpy(raw + 1, name.p, (size_t)len); len++; } else memcpy(raw, name.p, 4);
+                encode_token(A->name, raw, len, 4);
+                A->alt_loc = (uint8_t)(tok_eq(alt, ".") ? ' ' : alt.p[0]);
+                encode_token(A->res_name, res.p, res.n, 3);
+                A->res_name[3] = 0;
+                if (chain.n == 2) { A->chain_id1 = (uint8_t)chain.p[0]; A->chain_id2 = (uint8_t)chain.p[1]; }
+                else if (chain.n == 1) { A->chain_id1 = ' '; A->chain_id2 = (uint8_t)chain.p[0]; }
+                else { A->chain_id1 = ' '; A->chain_id2 = '0'; }
+                A->res_seq = (int32_t)seq;
+                A->i_code = (uint8_t)icode;
+                memcpy(A->seg_id, "____", 4);
+                char e2[2] = { 0, 0 };
+                if (elem.n == 2) { e2[0] = elem.p[0]; e2[1] = elem.p[1]; } else if (elem.n == 1) e2[1] = elem.p[0];
+                encode_token(A->element, e2, 2, 2);
+                A->charge = (int8_t)charge;
+            }
+            n_atoms++;
+        }
+        if (k != 0) CIF_FALLBACK(JB_CIF_SYNTAX);                              // values do not fill the last row
+        info->loop_end = last_end - text;
+    }
+#undef CIF_FALLBACK
+    info->n_atoms = n_atoms;
+    if (sc.bad) info->fallback = JB_CIF_SYNTAX;
+    else if (info->n_blocks != 1) info->fallback = JB_CIF_BLOCKS;
+    else if (!found) info->fallback = JB_CIF_LAYOUT;
+    if (info->fallback) return JB_OK;
     return n_atoms > capacity ? JB_ERR_CAPACITY : JB_OK;
 }
 

@@ -10,6 +10,7 @@ import os
 import textwrap
 import warnings
 
+import numpy as np
 import pytest
 
 from pyjess_b200 import Molecule
@@ -231,3 +232,121 @@ def test_invalid_fields_raise_like_atom():
         Molecule.loads(MINI.replace(" GLY A 2 ", " GLYX A 2 "), format="cif")
     with pytest.raises(ValueError):
         Molecule.loads(MINI.replace("ATOM 1 N N . GLY A 1 ", "ATOM 1 N N . GLY A . "), format="cif")   # int(".")
+
+
+# ---- the native one-pass reader (jb_cif_parse) against the generic Python loader --------------
+
+def _both(text, **kw):
+    """(info, native records, records of the generic loader or the exception it raises)."""
+    from pyjess_b200 import _capi
+    from pyjess_b200._model import ATOM_DTYPE
+    data = text.encode("utf-8")
+    info, native = _capi.cif_parse(data, ATOM_DTYPE, **kw)
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            blocks = _cif.read_blocks(text)
+            if len(blocks) != 1:
+                raise RuntimeError("single data block expected")
+            cols = blocks[0].find_columns("_atom_site.", _cif._AUTHOR if kw.get("use_author") else _cif._PRIMARY)
+            if not cols:
+                raise ValueError("missing columns in CIF files")
+            generic = _cif._records_from_columns(cols, skip_hetatm=kw.get("skip_hetatm", False),
+                                                 ignore_endmdl=kw.get("ignore_endmdl", False))
+    except Exception as err:  # noqa: BLE001
+        generic = err
+    return info, native, generic
+
+
+def _synthetic_cif(seed, n=400):
+    """An _atom_site loop with every field shape the reader distinguishes: two-character chains,
+    negative / zero-padded / signed numbers, exponents, quoted names, alternate locations,
+    insertion codes, charges, '.' and '?' place holders, HETATM rows with and without numbers,
+    a second model, comments and rows broken over two lines."""
+    rng = np.random.default_rng(seed)
+    tags = ["group_PDB", "id", "type_symbol", "label_atom_id", "label_alt_id", "label_comp_id", "label_asym_id",
+            "label_entity_id", "label_seq_id", "pdbx_PDB_ins_code", "Cartn_x", "Cartn_y", "Cartn_z", "occupancy",
+            "B_iso_or_equiv", "pdbx_formal_charge", "auth_seq_id", "auth_comp_id", "auth_asym_id", "auth_atom_id",
+            "pdbx_PDB_model_num"]
+    out = ["# made by tests/test_cif.py", "data_SYN%d" % seed, "_entry.id SYN", "loop_"] + ["_atom_site." + t for t in tags]
+    names = ["N", "CA", "C", "O", "CB", '"O5\'"', '"C1\'"', "OXT", "HG21", "1HB"]
+    for i in range(n):
+        het = rng.random() < 0.15
+        model = "1" if i < n - 30 else "2"
+        seq = "." if het and rng.random() < 0.5 else rng.choice(["%d", "%03d", "+%d", "-%d"]) % int(rng.integers(0, 900))
+        x, y, z = rng.uniform(-99, 99, 3)
+        fx = rng.choice(["%.3f", "%.5f", "%.1e", "%+.2f", "%d."])
+        row = ["HETATM" if het else "ATOM", str(i + 1 if rng.random() < 0.9 else int(rng.integers(1, 2 ** 31 - 1))),
+               str(rng.choice(["C", "N", "O", "S", "CA", "FE"])), str(rng.choice(names)), str(rng.choice([".", ".", "A", "B"])),
+               str(rng.choice(["ALA", "GLY", "HOH", "CA", "A"])), str(rng.choice(["A", "B", "AA", "A1", "z"])), "1", seq,
+               str(rng.choice(["?", "?", "A", "P"])), fx % x if "d" not in fx else fx % int(x), "%.3f" % y, "%.3f" % z,
+               str(rng.choice(["1.00", "0.50", ".", "1"])), str(rng.choice(["20.11", ".", "0.0", "1.5e1"])),
+               str(rng.choice(["?", "?", "0", "-1", "+2"])), str(int(rng.integers(-50, 9000))), "ALA", str(rng.choice(["A", "B"])),
+               str(rng.choice(["N", "CA", "O"])), model]
+        if rng.random() < 0.1:
+            out.append(" ".join(row[:9]))
+            out.append("  " + " ".join(row[9:]) + "   # wrapped row")
+        else:
+            out.append((" " * int(rng.integers(1, 4))).join(row))
+    out += ["#", "loop_", "_pdbx_audit_revision_history.ordinal", "_pdbx_audit_revision_history.revision_date",
+            "1 2001-02-03", "2 1999-12-31", "_struct.title 'a synthetic; entry'", ""]
+    return "\n".join(out)
+
+
+@pytest.mark.parametrize("kw", [{}, {"skip_hetatm": True}, {"ignore_endmdl": True}, {"use_author": True}])
+@pytest.mark.parametrize("seed", range(4))
+def test_native_reader_equals_the_generic_loader(seed, kw):
+    for text in (_synthetic_cif(seed), _synthetic_cif(seed).replace("\n", "\r\n"), MINI, open(CIF).read()):
+        if kw.get("use_author") and text is MINI:
+            continue
+        info, native, generic = _both(text, **kw)
+        assert info.fallback == 0 and not isinstance(generic, Exception), (info.fallback, generic)
+        assert len(native) == len(generic) > 0 and native.tobytes() == generic.tobytes()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mol = Molecule.loads(_synthetic_cif(seed), **kw)           # end to end: metadata next to the native table
+    assert mol.id == "SYN%d" % seed and mol.name == "a synthetic; entry" and mol.date == datetime.datetime(1999, 12, 31)
+
+
+@pytest.mark.parametrize("edit,code", [
+    (("ATOM 1 N N . GLY A 1 ", "ATOM 1 N N . GLY A 1_0 "), 4),                 # int() accepts underscores: Python decides
+    (("ATOM 1 N N . GLY A 1 ", "ATOM 1 N N . GLY A . "), 4),                   # ATOM row without a number: int('.') raises
+    ((" 1.0 2.0 3.0 1.00 10.0 1 'two words'", " nan 2.0 3.0 1.00 10.0 1 'two words'"), 4),
+    (("ATOM 2 C CA A GLY", "ATOM 2 C CALPHA A GLY"), 4),                       # Atom() rejects the name
+    (("ATOM 2 C CA A GLY", "ATOM 2 C CA AB GLY"), 4),                          # alternate location of two characters
+    (("_atom_site.Cartn_z\n", "_atom_site.Cartn_zz\n"), 3),                    # missing column
+    (("_atom_site.id\n", "_atom_site.id\n_atom_site.id\n"), 3),                # duplicate tag (and a ragged loop)
+    (("data_mini", "data_mini\ndata_second"), 2),
+    (("# comment\ndata_mini", "_stray.tag 1\ndata_mini"), 1),
+    ((";A title in a", ";A title in a\n;\n;never closed"), 1),
+])
+def test_native_reader_leaves_the_hard_cases_to_python(edit, code):
+    text = MINI.replace(*edit)
+    assert text != MINI
+    info, native, generic = _both(text)
+    assert info.fallback == code
+    # ... and the public loader answers like the generic one (same exception type or same records)
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            got = Molecule.loads(text, format="cif")._atoms
+    except Exception as err:  # noqa: BLE001
+        got = err
+    if isinstance(generic, Exception):
+        assert type(got) is type(generic) or isinstance(got, (ValueError, RuntimeError))
+    else:
+        assert got.tobytes() == generic.tobytes()
+
+
+def test_native_reader_capacity_retry_and_warning_count():
+    from pyjess_b200 import _capi
+    from pyjess_b200._model import ATOM_DTYPE
+    loop = MINI[MINI.index("loop_"):MINI.index("HETATM 3")].replace("# trailing comment", "")
+    text = "data_mini\n_entry.id X\n" + " ".join(loop.split("\n")) * 1 + " ATOM 3 O O . GLY A 2 4.0 5.0 6.0 0.50 20.0 1 z"
+    assert "\nATOM" not in text                                               # every row on one line: nothing to count
+    info, native = _capi.cif_parse(text.encode(), ATOM_DTYPE)
+    assert info.fallback == 0 and len(native) == 3
+    with pytest.warns(UserWarning) as caught:
+        warnings.simplefilter("always")
+        mol = Molecule.load(CIF)
+    assert len(mol) == 3339 and len([w for w in caught if "HETATM line found" in str(w.message)]) == 155
