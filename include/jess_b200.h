@@ -270,7 +270,7 @@ typedef struct jb_pdb_info {
     int64_t header_length;
     int64_t stop_offset;             /* where the scan stopped (ENDMDL / end) */
     int32_t mmcif_tags;              /* a data_/loop_ line was met: not PDB   */
-    int32_t reserved;
+    int32_t n_headers;               /* HEADER lines before stop_offset       */
 } jb_pdb_info;
 
 /* Parses the ATOM/HETATM lines of `text` up to the first ENDMDL into `records`.
@@ -284,6 +284,7 @@ int jb_pdb_parse(const char *text, int64_t n_bytes, int32_t flags,
  * JB_PDB_* flags (skip_hetatm; ignore_endmdl = every pdbx_PDB_model_num) and JB_CIF_USE_AUTHOR.
  * Whatever the reference answers with an exception, and number spellings beyond plain decimals,
  * are left to the host layer's generic loader: info->fallback != 0 (no records are valid).      */
+#define JB_CIF_MAX_META 16
 #define JB_CIF_USE_AUTHOR 4          /* CIFMoleculeParser(use_author=True): auth_* columns      */
 
 typedef enum jb_cif_fallback {
@@ -302,7 +303,13 @@ typedef struct jb_cif_info {
     int32_t hetatm_unnumbered;       /* HETATM rows numbered from the running maximum: one
                                       * UserWarning each in the reference (_io.py:185-199)      */
     int32_t fallback;                /* jb_cif_fallback                                         */
-    int32_t reserved;
+    int32_t n_meta;
+    int64_t name_offset;             /* the block name (after `data_`)                          */
+    int64_t name_length;
+    int64_t meta[JB_CIF_MAX_META][2];/* byte ranges [begin, end) of the pairs / loops holding
+                                      * _entry.id, _struct_keywords.pdbx_keywords, _struct.title,
+                                      * _pdbx_audit_revision_history.revision_date: all the host
+                                      * layer still has to read (_io.py:221-243)                */
 } jb_cif_info;
 
 /* JB_ERR_CAPACITY: info->n_atoms tells the capacity to retry with.                            */

@@ -224,7 +224,7 @@ def cif_parse(data: bytes, dtype, skip_hetatm: bool = False, ignore_endmdl: bool
     lib = load_library()
     info = jb_cif_info()
     flags = (1 if skip_hetatm else 0) | (2 if ignore_endmdl else 0) | (4 if use_author else 0)
-    cap = data.count(b"\nATOM") + data.count(b"\nHETATM") + 1
+    cap = len(data) // 40 + 16                        # a row holds >= 16 values; the reader reports what it needs
     while True:
         records = np.zeros(cap, dtype=dtype)
         rc = lib.jb_cif_parse(data, len(data), flags, C.c_void_p(records.ctypes.data), len(records), C.byref(info))

@@ -201,8 +201,8 @@ def load_molecule(text: str, molecule_type, *, id=None, date=None, name=None, us
     """``CIFMoleculeParser._load_block`` (src/pyjess/_io.py:167-245) on `text` (str or bytes).
 
     Well-formed files take the native one-pass reader of the engine library (`jb_cif_parse`,
-    csrc/ingest.cu) for the atom table -- the Python tokenizer then only sees the rest of the
-    file for the identifier, name and date; anything else (and every error) goes through the
+    csrc/ingest.cu) for the atom table -- the Python tokenizer then only sees the handful of items behind
+    the identifier, name and date (their byte ranges come back with the table); anything else (and every error) goes through the
     generic loader below."""
     arr = None
     if isinstance(text, (bytes, bytearray)):
@@ -215,7 +215,10 @@ def load_molecule(text: str, molecule_type, *, id=None, date=None, name=None, us
             arr = records
             for _ in range(info.hetatm_unnumbered):
                 warnings.warn(_HETATM_WARNING, UserWarning, stacklevel=4)
-            text = (data[:info.loop_offset] + b"\n" + data[info.loop_end:]).decode("utf-8")
+            # what is left to read: the block name and the few items behind id / name / date
+            pieces = [b"data_" + data[info.name_offset:info.name_offset + info.name_length]]
+            pieces += [data[info.meta[k][0]:info.meta[k][1]] for k in range(info.n_meta)]
+            text = b"\n".join(pieces).decode("utf-8") + "\n"
         else:
             text = data.decode("utf-8")
     blocks = read_blocks(text)

@@ -23,7 +23,7 @@ import functools
 import io
 import os
 import re
-from typing import Iterable, Optional, Sequence
+from typing import Iterable, List, Optional, Sequence
 
 import numpy as np
 
@@ -495,6 +495,28 @@ class Molecule:
                               ignore_endmdl=ignore_endmdl, skip_hetatm=skip_hetatm, format=format)
 
     @classmethod
+    def load_many(cls, files, format: str = "detect", *, jobs: Optional[int] = None, **kwargs) -> List["Molecule"]:
+        """`load` for a list of files on `jobs` threads (default: the host cores available to the
+        process), results in input order.  The native parsers run without the GIL and the
+        Python part of a PDB load is a few tens of microseconds, so ingest scales with the cores:
+        what a batch for `Jess.query_many` needs (parsing, not querying, bounds a
+        file-based run once the queries take milliseconds)."""
+        files = list(files)
+        if jobs is None:
+            jobs = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        jobs = max(1, min(int(jobs), len(files)))
+        if jobs == 1:
+            return [cls.load(f, format, **kwargs) for f in files]
+        from concurrent.futures import ThreadPoolExecutor
+        # a few contiguous runs of files per worker: one task per file costs more in queue traffic and
+        # GIL hand-offs than a millisecond-sized parse gains
+        size = max(1, -(-len(files) // (4 * jobs)))
+        runs = [files[i:i + size] for i in range(0, len(files), size)]
+        with ThreadPoolExecutor(jobs) as pool:
+            parts = pool.map(lambda run: [cls.load(f, format, **kwargs) for f in run], runs)
+            return [mol for part in parts for mol in part]
+
+    @classmethod
     def loads(cls, text, format: str = "detect", **kwargs):
         return cls.load(io.BytesIO(text.encode("utf-8") if isinstance(text, str) else bytes(text)),
                         format=format, **kwargs)
@@ -505,12 +527,19 @@ class Molecule:
         over the file image; only the optional HEADER line is decoded in Python."""
         from . import _capi
         data = bytes(data)
-        cap = data.count(b"ATOM") + data.count(b"HETATM")
-        arr = np.zeros(cap, dtype=ATOM_DTYPE)
-        info = _capi.pdb_parse(data, arr, skip_hetatm=skip_hetatm, ignore_endmdl=ignore_endmdl)
-        if info.mmcif_tags:
-            raise ValueError("mmCIF data tags found, file is not in PDB format")
-        arr = arr[:info.n_atoms]
+        # capacity: an ATOM line with coordinates is at least 54 characters; shorter ones make the parser
+        # report the count it needs.  (No bytes.count / find over the file here: they hold the GIL, the
+        # parser does not -- `load_many` reads files on several threads.)
+        cap = len(data) // 54 + 16
+        while True:
+            arr = np.zeros(cap, dtype=ATOM_DTYPE)
+            info = _capi.pdb_parse(data, arr, skip_hetatm=skip_hetatm, ignore_endmdl=ignore_endmdl)
+            if info.mmcif_tags:
+                raise ValueError("mmCIF data tags found, file is not in PDB format")
+            if info.n_atoms <= cap:
+                break
+            cap = int(info.n_atoms)
+        arr = arr[:info.n_atoms].copy() if info.n_atoms * 2 < cap else arr[:info.n_atoms]
         pos = info.header_offset
         while pos >= 0 and pos < info.stop_offset and (id is None or date is None or name is None):
             end = data.find(b"\n", pos)
@@ -523,6 +552,8 @@ class Molecule:
                     date = datetime.datetime.strptime(date_text, "%d-%b-%y").date()
             if name is None:
                 name = text[10:50].strip() or None
+            if info.n_headers <= 1:
+                break
             pos = data.find(b"\nHEADER", pos + 1, info.stop_offset)
             pos = pos + 1 if pos >= 0 else -1
         return cls._from_records(arr, id=id, date=date, name=name)

@@ -79,7 +79,7 @@ class jb_pdb_info(C.Structure):
         ("header_length", C.c_int64),
         ("stop_offset", C.c_int64),
         ("mmcif_tags", C.c_int32),
-        ("reserved", C.c_int32),
+        ("n_headers", C.c_int32),
     ]
 
 
@@ -91,7 +91,10 @@ class jb_cif_info(C.Structure):
         ("n_blocks", C.c_int32),
         ("hetatm_unnumbered", C.c_int32),
         ("fallback", C.c_int32),
-        ("reserved", C.c_int32),
+        ("n_meta", C.c_int32),
+        ("name_offset", C.c_int64),
+        ("name_length", C.c_int64),
+        ("meta", (C.c_int64 * 2) * 16),
     ]
 
 

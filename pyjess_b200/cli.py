@@ -31,7 +31,7 @@ def argument_parser(prog: str = "pyjess_b200") -> argparse.ArgumentParser:
     parser.add_argument("-V", "--version", action="version", version=f"pyjess_b200 {__version__}",
                         help="Show the version number and exit.")
     parser.add_argument("-j", "--jobs", type=int, default=1,
-                        help="Accepted for compatibility; the search runs on the GPU.")
+                        help="Threads reading the query files of a batch (the search itself runs on the GPU).")
     parser.add_argument("--batch", type=int, default=256, help="Query structures per engine call.")
     group = parser.add_argument_group("Mandatory Parameters")
     group.add_argument("-T", "--templates", type=Path, required=True, help="The path to the template list file.")
@@ -81,9 +81,12 @@ def main(argv: typing.Optional[typing.List[str]] = None, stdout: typing.TextIO =
             filenames = [n for n in map(str.strip, f) if n]
         for start in range(0, len(filenames), max(1, args.batch)):
             mols = []
-            for filename in filenames[start:start + max(1, args.batch)]:
-                mol = Molecule.load(filename, id=filename if args.query_filename else None,
-                                    ignore_endmdl=args.ignore_endmdl)
+            names = filenames[start:start + max(1, args.batch)]
+            if args.query_filename:           # the identifier differs per file: one load per file
+                loaded = [Molecule.load(n, id=n, ignore_endmdl=args.ignore_endmdl) for n in names]
+            else:
+                loaded = Molecule.load_many(names, jobs=max(1, args.jobs), ignore_endmdl=args.ignore_endmdl)
+            for filename, mol in zip(names, loaded):
                 if mol.id is None:
                     warnings.warn(f"No id in molecule {filename}. Using filename instead.")
                     mol = Molecule(mol, id=filename, date=mol.date, name=mol.name)

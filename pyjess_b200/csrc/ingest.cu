@@ -137,6 +137,7 @@ extern "C" int jb_pdb_parse(const char *text, int64_t n_bytes, int32_t flags, jb
             } while (0);
         } else if (starts(line, len, "HEADER", 6)) {
             if (info->header_offset < 0) { info->header_offset = line - text; info->header_length = len; }
+            info->n_headers++;
         } else if (starts(line, len, "ENDMDL", 6)) {
             if (!ignore_endmdl) break;
         } else if (starts_lower(line, len, "data_", 5) || starts_lower(line, len, "loop_", 5)) {
@@ -291,6 +292,13 @@ const char *const kAuthor[C_COUNT] = { "id", "type_symbol", "auth_atom_id", "lab
     "group_PDB", "pdbx_PDB_model_num" };
 inline bool optional_column(int c) { return c == C_ICODE || c == C_CHARGE || c == C_GROUP; }
 
+// the items the host layer reads next to the atom table (id / name / date, _io.py:221-243)
+inline bool meta_tag(const Tok &t)
+{
+    return tok_ieq(t, "_entry.id") || tok_ieq(t, "_struct_keywords.pdbx_keywords") || tok_ieq(t, "_struct.title") ||
+           tok_ieq(t, "_pdbx_audit_revision_history.revision_date");
+}
+
 }  // namespace
 
 extern "C" int jb_cif_parse(const char *text, int64_t n_bytes, int32_t flags, jb_atom_record *records, int64_t capacity,
@@ -308,14 +316,26 @@ extern "C" int jb_cif_parse(const char *text, int64_t n_bytes, int32_t flags, jb
     int64_t n_atoms = 0;
 #define CIF_FALLBACK(code) do { info->fallback = (code); info->n_atoms = n_atoms; return JB_OK; } while (0)
     while (have) {
-        if (tok_iprefix(t, "data_")) { info->n_blocks++; have = sc.next(&t); continue; }
+        if (tok_iprefix(t, "data_")) {
+            if (info->n_blocks++ == 0) { info->name_offset = t.p + 5 - text; info->name_length = t.n - 5; }
+            have = sc.next(&t);
+            continue;
+        }
         if (info->n_blocks == 0) CIF_FALLBACK(JB_CIF_SYNTAX);
         if (tok_iprefix(t, "save_")) { have = sc.next(&t); continue; }
         if (!tok_ieq(t, "loop_")) {
             if (t.p[0] != '_') CIF_FALLBACK(JB_CIF_SYNTAX);                   // a value outside any pair / loop
             if (tok_ieq(t, "_atom_site.id")) CIF_FALLBACK(JB_CIF_LAYOUT);     // atom table given as pairs
+            const bool meta = meta_tag(t);
+            const char *item = t.p;
             have = sc.next(&t);
             if (!have || cif_keyword(t)) CIF_FALLBACK(JB_CIF_SYNTAX);         // tag without a value
+            if (meta) {
+                if (info->n_meta >= JB_CIF_MAX_META) CIF_FALLBACK(JB_CIF_LAYOUT);
+                info->meta[info->n_meta][0] = item - text;
+                info->meta[info->n_meta][1] = t.p + t.n - text;
+                info->n_meta++;
+            }
             have = sc.next(&t);
             continue;
         }
@@ -324,8 +344,9 @@ extern "C" int jb_cif_parse(const char *text, int64_t n_bytes, int32_t flags, jb
         int col[C_COUNT];
         for (int c = 0; c < C_COUNT; c++) col[c] = -1;
         int n_tags = 0;
-        bool mine = false, dup = false;
+        bool mine = false, dup = false, meta = false;
         while ((have = sc.next(&t)) && t.p[0] == '_') {
+            meta = meta || meta_tag(t);
             if (!found && tok_iprefix(t, "_atom_site.")) {
                 const Tok item{ t.p + 11, t.n - 11 };
                 if (tok_ieq(item, "id")) mine = true;
@@ -336,7 +357,14 @@ extern "C" int jb_cif_parse(const char *text, int64_t n_bytes, int32_t flags, jb
         }
         if (n_tags == 0) CIF_FALLBACK(JB_CIF_SYNTAX);
         if (!mine) {                                                          // someone else's loop: skip its values
-            while (have && !cif_keyword(t)) have = sc.next(&t);
+            const char *end = nullptr;
+            for (; have && !cif_keyword(t); have = sc.next(&t)) end = t.p + t.n;
+            if (meta && end) {
+                if (info->n_meta >= JB_CIF_MAX_META) CIF_FALLBACK(JB_CIF_LAYOUT);
+                info->meta[info->n_meta][0] = loop_offset;
+                info->meta[info->n_meta][1] = end - text;
+                info->n_meta++;
+            }
             continue;
         }
         found = true;

@@ -154,3 +154,32 @@ def test_native_atom_formatter_rounding_and_overflow_cases():
     # a block that ends inside the 2 KiB reserve of the output buffer goes through the bounded path
     small = recs[len(special):len(special) + 3]
     assert _capi.format_atoms_pdb(small) == "".join(_format_atom(small[k], small["x"][k]) for k in range(3))
+
+
+def test_load_many_equals_load_in_input_order():
+    """`Molecule.load_many` (threads over the GIL-free native parsers) == `Molecule.load` per file,
+    in input order, PDB and mmCIF mixed, whatever the number of threads; errors propagate."""
+    import warnings
+    names = ["1AMY.pdb", "pdb1lnb.ent", "1AMY.cif", "5ayx.EF.pdb", "pdb1a0p.ent"] * 5
+    files = [os.path.join(DATA, n) for n in names]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = [Molecule.load(f, skip_hetatm=True) for f in files]
+        for jobs in (1, 3, 64, None):
+            got = Molecule.load_many(files, jobs=jobs, skip_hetatm=True)
+            assert len(got) == len(want)
+            for a, b in zip(got, want):
+                assert a.id == b.id and a.name == b.name and a.date == b.date
+                assert a._atoms.tobytes() == b._atoms.tobytes()
+        assert Molecule.load_many([]) == []
+        with pytest.raises(FileNotFoundError):
+            Molecule.load_many(files[:3] + [os.path.join(DATA, "missing.pdb")] + files[3:], jobs=4)
+
+
+def test_pdb_capacity_estimate_is_retried():
+    """The record capacity is estimated from the file size (54 characters per ATOM line); files made
+    of shorter lines make the parser report what it needs and the load is repeated."""
+    text = "ATOM      1  N   GLN A   1\n" * 500 + "HEADER    X\n"
+    mol = Molecule.loads(text)
+    assert len(mol) == 500 and mol[499].residue_number == 1
+    assert mol._atoms.tobytes() == Molecule._parse_pdb_python(text.encode())._atoms.tobytes()
