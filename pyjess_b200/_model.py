@@ -495,25 +495,37 @@ class Molecule:
                               ignore_endmdl=ignore_endmdl, skip_hetatm=skip_hetatm, format=format)
 
     @classmethod
-    def load_many(cls, files, format: str = "detect", *, jobs: Optional[int] = None, **kwargs) -> List["Molecule"]:
+    def load_many(cls, files, format: str = "detect", *, jobs: Optional[int] = None,
+                  ids: Optional[Sequence[Optional[str]]] = None, **kwargs) -> List["Molecule"]:
         """`load` for a list of files on `jobs` threads (default: the host cores available to the
         process), results in input order.  The native parsers run without the GIL and the
         Python part of a PDB load is a few tens of microseconds, so ingest scales with the cores:
         what a batch for `Jess.query_many` needs (parsing, not querying, bounds a
-        file-based run once the queries take milliseconds)."""
+        file-based run once the queries take milliseconds).  `ids`: one identifier per file
+        (instead of the single `id` of `load`)."""
         files = list(files)
+        if ids is not None:
+            ids = list(ids)
+            if len(ids) != len(files):
+                raise ValueError("load_many: `ids` and `files` differ in length")
+            if "id" in kwargs:
+                raise TypeError("load_many: pass either `id` or `ids`")
+            files = list(zip(files, ids))
+            one = lambda item: cls.load(item[0], format, id=item[1], **kwargs)      # noqa: E731
+        else:
+            one = lambda f: cls.load(f, format, **kwargs)                          # noqa: E731
         if jobs is None:
             jobs = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
         jobs = max(1, min(int(jobs), len(files)))
         if jobs == 1:
-            return [cls.load(f, format, **kwargs) for f in files]
+            return [one(f) for f in files]
         from concurrent.futures import ThreadPoolExecutor
         # a few contiguous runs of files per worker: one task per file costs more in queue traffic and
         # GIL hand-offs than a millisecond-sized parse gains
         size = max(1, -(-len(files) // (4 * jobs)))
         runs = [files[i:i + size] for i in range(0, len(files), size)]
         with ThreadPoolExecutor(jobs) as pool:
-            parts = pool.map(lambda run: [cls.load(f, format, **kwargs) for f in run], runs)
+            parts = pool.map(lambda run: [one(f) for f in run], runs)
             return [mol for part in parts for mol in part]
 
     @classmethod

@@ -82,10 +82,8 @@ def main(argv: typing.Optional[typing.List[str]] = None, stdout: typing.TextIO =
         for start in range(0, len(filenames), max(1, args.batch)):
             mols = []
             names = filenames[start:start + max(1, args.batch)]
-            if args.query_filename:           # the identifier differs per file: one load per file
-                loaded = [Molecule.load(n, id=n, ignore_endmdl=args.ignore_endmdl) for n in names]
-            else:
-                loaded = Molecule.load_many(names, jobs=max(1, args.jobs), ignore_endmdl=args.ignore_endmdl)
+            loaded = Molecule.load_many(names, jobs=max(1, args.jobs), ids=names if args.query_filename else None,
+                                        ignore_endmdl=args.ignore_endmdl)
             for filename, mol in zip(names, loaded):
                 if mol.id is None:
                     warnings.warn(f"No id in molecule {filename}. Using filename instead.")

@@ -171,6 +171,10 @@ def test_load_many_equals_load_in_input_order():
             for a, b in zip(got, want):
                 assert a.id == b.id and a.name == b.name and a.date == b.date
                 assert a._atoms.tobytes() == b._atoms.tobytes()
+        named = Molecule.load_many(files[:4], jobs=2, ids=["a", None, "c", "d"])
+        assert [m.id for m in named] == ["a", want[1].id, "c", "d"]
+        with pytest.raises(ValueError):
+            Molecule.load_many(files[:2], ids=["a"])
         assert Molecule.load_many([]) == []
         with pytest.raises(FileNotFoundError):
             Molecule.load_many(files[:3] + [os.path.join(DATA, "missing.pdb")] + files[3:], jobs=4)
