@@ -8,6 +8,7 @@
 // host layer wraps without any per-atom Python work.  Field semantics are Atom_parse's:
 // C atoi/atof PREFIX parsing from the field's first column, fields beyond the end of the
 // line keep their zero value, tokens copied with blanks/NULs turned into '_'.
+#include <algorithm>
 #include <cctype>
 #include <climits>
 #include <cmath>
@@ -15,6 +16,8 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
+#include <vector>
 
 #include "../../include/jess_b200.h"
 
@@ -560,17 +563,14 @@ extern "C" int64_t jb_format_atoms_pdb(const jb_atom_record *atoms, int64_t n, c
 // What Molecule.__init__ + ResIndex_create consume in the reference (SURVEY 8b "bj_molecules_pack"):
 // reads the 59-byte records of every molecule once and writes the structure-of-arrays staging
 // buffers (pinned or pageable) that jb_molecules_upload / jb_query_host copy to HBM.
-extern "C" int jb_molecules_pack(const jb_atom_record *const *molecules, const int64_t *counts, int32_t n_molecules,
-                                 int64_t *atom_offset, double *x, double *y, double *z, uint32_t *name,
-                                 uint32_t *residue_name, int32_t *residue_number, uint8_t *chain_id2, int32_t *serial)
+static void pack_range(const jb_atom_record *const *molecules, const int64_t *atom_offset, int32_t m0, int32_t m1, double *x,
+                       double *y, double *z, uint32_t *name, uint32_t *residue_name, int32_t *residue_number,
+                       uint8_t *chain_id2, int32_t *serial)
 {
-    if (n_molecules < 0 || !atom_offset || (n_molecules > 0 && (!molecules || !counts))) return JB_ERR_INVALID;
-    int64_t pos = 0;
-    atom_offset[0] = 0;
-    for (int32_t m = 0; m < n_molecules; m++) {
+    for (int32_t m = m0; m < m1; m++) {
         const jb_atom_record *a = molecules[m];
-        const int64_t n = counts[m];
-        if (n < 0 || (n > 0 && !a)) return JB_ERR_INVALID;
+        int64_t pos = atom_offset[m];
+        const int64_t n = atom_offset[m + 1] - pos;
         for (int64_t i = 0; i < n; i++, pos++) {
             x[pos] = a[i].x[0]; y[pos] = a[i].x[1]; z[pos] = a[i].x[2];
             memcpy(&name[pos], a[i].name, 4);
@@ -579,7 +579,45 @@ extern "C" int jb_molecules_pack(const jb_atom_record *const *molecules, const i
             chain_id2[pos] = a[i].chain_id2;
             if (serial) serial[pos] = a[i].serial;
         }
-        atom_offset[m + 1] = pos;
     }
+}
+
+extern "C" int jb_molecules_pack(const jb_atom_record *const *molecules, const int64_t *counts, int32_t n_molecules,
+                                 int64_t *atom_offset, double *x, double *y, double *z, uint32_t *name,
+                                 uint32_t *residue_name, int32_t *residue_number, uint8_t *chain_id2, int32_t *serial)
+{
+    if (n_molecules < 0 || !atom_offset || (n_molecules > 0 && (!molecules || !counts))) return JB_ERR_INVALID;
+    atom_offset[0] = 0;
+    for (int32_t m = 0; m < n_molecules; m++) {
+        if (counts[m] < 0 || (counts[m] > 0 && !molecules[m])) return JB_ERR_INVALID;
+        atom_offset[m + 1] = atom_offset[m] + counts[m];
+    }
+    // the copy is a stream of 59-byte reads and 37-41-byte writes (memory bound): large batches are cut into
+    // runs of structures with equal shares of the atoms, one host thread each (JB_PACK_THREADS, default <= 8)
+    const int64_t total = atom_offset[n_molecules];
+    int threads = 1;
+    if (total >= 262144 && n_molecules >= 2) {
+        const char *env = getenv("JB_PACK_THREADS");
+        const int hw = (int)std::thread::hardware_concurrency();
+        threads = env ? atoi(env) : std::min(8, hw > 0 ? hw : 1);
+        threads = std::max(1, std::min(threads, (int)std::min<int64_t>(n_molecules, total / 131072)));
+    }
+    if (threads <= 1) {
+        pack_range(molecules, atom_offset, 0, n_molecules, x, y, z, name, residue_name, residue_number, chain_id2, serial);
+        return JB_OK;
+    }
+    std::vector<std::thread> pool;
+    int32_t m0 = 0;
+    for (int t = 0; t < threads; t++) {
+        const int64_t want = total * (t + 1) / threads;
+        int32_t m1 = t + 1 == threads ? n_molecules
+                                      : (int32_t)(std::upper_bound(atom_offset, atom_offset + n_molecules + 1, want) - atom_offset - 1);
+        m1 = std::max(m1, m0);
+        if (m1 > m0)
+            pool.emplace_back(pack_range, molecules, atom_offset, m0, m1, x, y, z, name, residue_name, residue_number, chain_id2,
+                              serial);
+        m0 = m1;
+    }
+    for (std::thread &th : pool) th.join();
     return JB_OK;
 }
