@@ -187,3 +187,22 @@ def test_pdb_capacity_estimate_is_retried():
     mol = Molecule.loads(text)
     assert len(mol) == 500 and mol[499].residue_number == 1
     assert mol._atoms.tobytes() == Molecule._parse_pdb_python(text.encode())._atoms.tobytes()
+
+
+def test_threaded_packing_is_identical(monkeypatch):
+    """jb_molecules_pack cuts batches of more than 262,144 atoms into runs of structures, one host
+    thread each (JB_PACK_THREADS): same staging image for every thread count, empty structures
+    and a thread count above the number of structures included."""
+    from pyjess_b200 import synth
+    from pyjess_b200._tables import MoleculeBatch
+    _, mols, _, _ = synth.workload("cfg3", scale=0.13)
+    mols = mols + [Molecule()] + mols[:5]
+    assert sum(len(m) for m in mols) > 262144
+    ref = None
+    for threads in ("1", "2", "7", "64"):
+        monkeypatch.setenv("JB_PACK_THREADS", threads)
+        b = MoleculeBatch(mols, serial=True)
+        cur = [b.atom_offset.copy()] + [np.asarray(getattr(b, k))[:b.n_atoms].copy()
+                                        for k in ("x", "y", "z", "name", "resname", "resseq", "chain", "serial")]
+        ref = ref or cur
+        assert all(np.array_equal(u, v) for u, v in zip(ref, cur)), threads

@@ -22,7 +22,7 @@ for threads in ("1", "2", "4", "8", "16"):
         t = time.perf_counter()
         b = MoleculeBatch(mols, serial=True, pool=_staging_pool())
         best = min(best, time.perf_counter() - t)
-    cur = [np.asarray(getattr(b, k))[:b.n_atoms].copy() for k in ("x", "y", "z", "name", "residue_name", "residue_number", "chain_id2", "serial")]
+    cur = [b.atom_offset.copy()] + [np.asarray(getattr(b, k))[:b.n_atoms].copy() for k in ("x", "y", "z", "name", "resname", "resseq", "chain", "serial")]
     ref = ref or cur
     out[f"pack_ms_{threads}"] = round(best * 1e3, 3)
     out[f"same_{threads}"] = all(np.array_equal(u, v) for u, v in zip(ref, cur))
