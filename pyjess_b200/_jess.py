@@ -178,6 +178,30 @@ def _staging_pool() -> dict:
     return pool
 
 
+def _iteration_rows(molecule: np.ndarray, template: np.ndarray, rows: np.ndarray) -> np.ndarray:
+    """`rows` (records of a table sorted by (structure, template)) in iteration order: structures
+    ascending, the (structure, template) RUNS of one structure in DESCENDING template order
+    (reverse insertion, eff:Jess.c:109-117), records inside a run untouched.  No sort: the runs of
+    a structure are contiguous and ascending, so they are simply mirrored inside their group."""
+    if len(rows) == 0:
+        return rows
+    mol, tpl = molecule[rows], template[rows]
+    head = np.ones(len(rows), dtype=bool)
+    head[1:] = (mol[1:] != mol[:-1]) | (tpl[1:] != tpl[:-1])
+    start = np.nonzero(head)[0]
+    length = np.diff(np.append(start, len(rows)))
+    run_mol = mol[start]
+    group_head = np.ones(len(start), dtype=bool)
+    group_head[1:] = run_mol[1:] != run_mol[:-1]
+    first = np.nonzero(group_head)[0]                         # first run of every structure
+    last = np.append(first[1:], len(start)) - 1
+    group = np.cumsum(group_head) - 1
+    perm = first[group] + last[group] - np.arange(len(start))  # position i takes the mirrored run
+    start, length = start[perm], length[perm]
+    offs = np.cumsum(length) - length
+    return rows[np.repeat(start - offs, length) + np.arange(len(rows))]
+
+
 class _BatchRun:
     """Shared, lazily executed engine call of one `query` / `query_many`."""
 
@@ -228,16 +252,7 @@ class _BatchRun:
         # iteration order per structure: template DESCENDING (reverse insertion), engine order within.
         # The table is sorted by (structure, template): only whole (structure, template) RUNS move.
         rows = np.arange(t.count, dtype=np.int64) if keep is None else np.nonzero(keep)[0]
-        mol, tpl = t.molecule[rows], t.template[rows]
-        if len(rows):
-            head = np.ones(len(rows), dtype=bool)
-            head[1:] = (mol[1:] != mol[:-1]) | (tpl[1:] != tpl[:-1])
-            start = np.nonzero(head)[0]
-            length = np.diff(np.append(start, len(rows)))
-            perm = np.lexsort((-tpl[start].astype(np.int64), mol[start]))          # runs, not records
-            start, length = start[perm], length[perm]
-            offs = np.cumsum(length) - length
-            rows = rows[np.repeat(start - offs, length) + np.arange(len(rows))]
+        rows = _iteration_rows(t.molecule, t.template, rows)
         bounds = np.searchsorted(t.molecule[rows], np.arange(len(mols) + 1))
         self._slices = [rows[bounds[m]:bounds[m + 1]] for m in range(len(mols))]
 

@@ -81,3 +81,22 @@ def test_molecule_basics():
     assert len(mol.conserved(10.0)) < len(mol)
     assert pickle.loads(pickle.dumps(mol)) == mol and mol.copy() == mol
     assert len(mol[:10]) == 10 and mol[0].serial == 1
+
+
+def test_iteration_rows_mirror_equals_the_sorted_formulation():
+    """`_iteration_rows` (runs of a structure mirrored in place) == a lexsort of the runs by
+    (structure ascending, template descending), on random tables incl. filtered rows."""
+    import numpy as np
+    from pyjess_b200._jess import _iteration_rows
+    rng = np.random.default_rng(3)
+    for case in range(20):
+        n = int(rng.integers(1, 3000))
+        mol = np.sort(rng.integers(0, 40, n)).astype(np.int32)
+        tpl = rng.integers(0, 12 if case % 2 else 400, n).astype(np.int32)
+        order = np.lexsort((tpl, mol))
+        mol, tpl = mol[order], tpl[order]
+        rows = np.nonzero(rng.random(n) < 0.9)[0] if case % 3 == 0 else np.arange(n)
+        got = _iteration_rows(mol, tpl, rows.astype(np.int64))
+        want = rows[np.lexsort((np.arange(len(rows)), -tpl[rows].astype(np.int64), mol[rows]))]
+        assert np.array_equal(got, want)
+    assert len(_iteration_rows(mol, tpl, np.zeros(0, dtype=np.int64))) == 0
