@@ -183,13 +183,18 @@ def _iteration_rows(molecule: np.ndarray, template: np.ndarray, rows: np.ndarray
     ascending, the (structure, template) RUNS of one structure in DESCENDING template order
     (reverse insertion, eff:Jess.c:109-117), records inside a run untouched.  No sort: the runs of
     a structure are contiguous and ascending, so they are simply mirrored inside their group."""
-    if len(rows) == 0:
-        return rows
-    mol, tpl = molecule[rows], template[rows]
-    head = np.ones(len(rows), dtype=bool)
+    if rows is None:                                         # every record of the table
+        n = len(molecule)
+        mol, tpl = molecule, template
+    else:
+        n = len(rows)
+        mol, tpl = molecule[rows], template[rows]
+    if n == 0:
+        return np.zeros(0, dtype=np.int64)
+    head = np.ones(n, dtype=bool)
     head[1:] = (mol[1:] != mol[:-1]) | (tpl[1:] != tpl[:-1])
     start = np.nonzero(head)[0]
-    length = np.diff(np.append(start, len(rows)))
+    length = np.diff(np.append(start, n))
     run_mol = mol[start]
     group_head = np.ones(len(start), dtype=bool)
     group_head[1:] = run_mol[1:] != run_mol[:-1]
@@ -199,7 +204,8 @@ def _iteration_rows(molecule: np.ndarray, template: np.ndarray, rows: np.ndarray
     perm = first[group] + last[group] - np.arange(len(start))  # position i takes the mirrored run
     start, length = start[perm], length[perm]
     offs = np.cumsum(length) - length
-    return rows[np.repeat(start - offs, length) + np.arange(len(rows))]
+    order = np.repeat(start - offs, length) + np.arange(n)
+    return order if rows is None else rows[order]
 
 
 class _BatchRun:
@@ -251,8 +257,7 @@ class _BatchRun:
             keep = ~(first & single[t.template])
         # iteration order per structure: template DESCENDING (reverse insertion), engine order within.
         # The table is sorted by (structure, template): only whole (structure, template) RUNS move.
-        rows = np.arange(t.count, dtype=np.int64) if keep is None else np.nonzero(keep)[0]
-        rows = _iteration_rows(t.molecule, t.template, rows)
+        rows = _iteration_rows(t.molecule, t.template, None if keep is None else np.nonzero(keep)[0])
         bounds = np.searchsorted(t.molecule[rows], np.arange(len(mols) + 1))
         self._slices = [rows[bounds[m]:bounds[m + 1]] for m in range(len(mols))]
 

@@ -99,4 +99,46 @@ def test_iteration_rows_mirror_equals_the_sorted_formulation():
         got = _iteration_rows(mol, tpl, rows.astype(np.int64))
         want = rows[np.lexsort((np.arange(len(rows)), -tpl[rows].astype(np.int64), mol[rows]))]
         assert np.array_equal(got, want)
+        if case % 3:
+            assert np.array_equal(_iteration_rows(mol, tpl, None), want)       # None: every record
     assert len(_iteration_rows(mol, tpl, np.zeros(0, dtype=np.int64))) == 0
+    assert len(_iteration_rows(mol[:0], tpl[:0], None)) == 0
+
+
+def test_batch_run_slices_with_a_stubbed_engine(monkeypatch):
+    """Host logic of `_BatchRun.run` (no engine call): per structure, the records come in
+    descending template order, table order inside a (structure, template) run, the first record
+    of single-atom templates dropped (the reference never reports its first candidate)."""
+    import types
+    import numpy as np
+    from pyjess_b200 import Jess, Template, _capi, synth
+    from pyjess_b200 import _jess
+    tpl, mols, thr, _ = synth.workload("cfg3", scale=0.01)
+    tpl = list(tpl) + [Template(list(tpl[0])[:1], id="single")]
+    rng = np.random.default_rng(11)
+    n = 5000
+    mol = np.sort(rng.integers(0, len(mols), n)).astype(np.int32)
+    t = rng.integers(0, len(tpl), n).astype(np.int32)
+    order = np.lexsort((t, mol))
+    mol, t = mol[order], t[order]
+    table = types.SimpleNamespace(count=n, molecule=mol, template=t, atoms=np.zeros((n, 18), np.int32),
+                                  rmsd=rng.uniform(0, 2, n), rotation=np.zeros((n, 3, 3)), centre0=np.zeros((n, 3)),
+                                  centre1=np.zeros((n, 3)))
+    monkeypatch.setattr(_capi, "default_context", lambda: None)
+    monkeypatch.setattr(Jess, "_device_templates", lambda self, ctx: None)
+    monkeypatch.setattr(_capi, "query_host", lambda ctx, dev, batch, params: (table, {"nan_dropped": 0}))
+    jess = Jess(tpl)
+    single = len(tpl) - 1
+    seen = 0
+    for m, query in enumerate(jess.query_many(mols, *thr)):
+        _, rows = query.hit_table()
+        want = [i for i in range(n) if mol[i] == m]
+        first_single = next((i for i in want if t[i] == single), None)
+        want = [i for i in want if i != first_single]
+        want.sort(key=lambda i: (-int(t[i]), i))
+        assert rows.tolist() == want
+        hits = list(query)
+        assert [h.rmsd for h in hits] == [float(table.rmsd[i]) for i in want]
+        assert all(h.template() is tpl[t[i]] and h.molecule() is mols[m] for h, i in zip(hits, want))
+        seen += len(rows)
+    assert seen == n - len({int(mol[i]) for i in range(n) if t[i] == single})
