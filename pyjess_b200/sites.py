@@ -247,3 +247,19 @@ def write_hits(hits, file: typing.TextIO, transform: bool = True) -> None:
         lines = [line.strip() for line in hit.dumps(format="pdb", transform=transform).splitlines()]
         file.write("\n".join(lines))
         file.write("\n\n")
+
+
+def main(argv: typing.Optional[typing.List[str]] = None) -> int:
+    """``python -m pyjess_b200.sites < hits.txt``: drop-in for ``filter_output.py`` on the command
+    line's text (``--best``: the script's other mode, one hit per (target, template) run)."""
+    import argparse
+    import sys
+    parser = argparse.ArgumentParser(prog="python -m pyjess_b200.sites", description=main.__doc__)
+    parser.add_argument("--best", action="store_true", help="only the best hit of every (target, template) run")
+    args = parser.parse_args(argv)
+    filter_text(sys.stdin, sys.stdout, all_instances=not args.best)
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

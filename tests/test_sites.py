@@ -167,3 +167,14 @@ def test_best_sites_rejects_what_it_cannot_filter():
     with pytest.raises(TypeError):
         sites.best_sites([object()])
     assert sites.best_sites([]) == []
+
+
+@pytest.mark.parametrize("tag,flags", [("all", []), ("best", ["--best"])])
+def test_module_entry_point_is_a_drop_in_for_the_script(tag, flags):
+    import subprocess
+    import sys
+    root = os.path.dirname(GOLD.rstrip(os.sep).rsplit(os.sep, 1)[0])
+    proc = subprocess.run([sys.executable, "-m", "pyjess_b200.sites", *flags], input=_input("synthetic"), text=True,
+                          capture_output=True, cwd=root, timeout=120)
+    assert proc.returncode == 0, proc.stderr
+    assert proc.stdout == _golden("synthetic", tag)
