@@ -26,8 +26,8 @@ import numpy as np
 # must be followed by white space), a comment, or a run of non-blanks
 _TOKEN = re.compile(
     r"""^;(?:.|\n)*?^;          # text field
-      | '(?:[^'\n]|'(?=\S))*'   # single-quoted
-      | "(?:[^"\n]|"(?=\S))*"   # double-quoted
+      | '(?:[^'\n]|'(?=\S))*'(?=\s|\Z)   # single-quoted
+      | "(?:[^"\n]|"(?=\S))*"(?=\s|\Z)   # double-quoted
       | \#[^\n]*                # comment
       | [^\s]+                  # bare word
     """, re.M | re.X)

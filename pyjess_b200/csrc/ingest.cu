@@ -361,7 +361,9 @@ extern "C" int jb_cif_parse(const char *text, int64_t n_bytes, int32_t flags, jb
         if (n_tags == 0) CIF_FALLBACK(JB_CIF_SYNTAX);
         if (!mine) {                                                          // someone else's loop: skip its values
             const char *end = nullptr;
-            for (; have && !cif_keyword(t); have = sc.next(&t)) end = t.p + t.n;
+            int64_t n_values = 0;
+            for (; have && !cif_keyword(t); have = sc.next(&t), n_values++) end = t.p + t.n;
+            if (n_values % n_tags) CIF_FALLBACK(JB_CIF_SYNTAX);                 // ragged loop
             if (meta && end) {
                 if (info->n_meta >= JB_CIF_MAX_META) CIF_FALLBACK(JB_CIF_LAYOUT);
                 info->meta[info->n_meta][0] = loop_offset;

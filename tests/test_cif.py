@@ -350,3 +350,31 @@ def test_native_reader_capacity_retry_and_warning_count():
         warnings.simplefilter("always")
         mol = Molecule.load(CIF)
     assert len(mol) == 3339 and len([w for w in caught if "HETATM line found" in str(w.message)]) == 155
+
+
+def test_native_reader_fuzz_never_disagrees_with_the_generic_loader():
+    """Random edits (replace / delete / insert of syntax-relevant characters) of three CIF documents:
+    the native reader either hands the file over (`fallback`) or returns exactly the records of the
+    generic loader -- it never accepts what the generic loader rejects, and never crashes."""
+    rng = np.random.default_rng(2026)
+    bases = [MINI, _synthetic_cif(1, 40), _synthetic_cif(2, 25).replace("\n", "\r\n")]
+    alphabet = list(" \n\t#;'\"._?-+0123456789eEATOMHLYGdatloop_")
+    accepted = 0
+    for it in range(1500):
+        s = list(bases[it % len(bases)])
+        for _ in range(int(rng.integers(1, 4))):
+            op, pos = int(rng.integers(0, 3)), int(rng.integers(0, len(s)))
+            if op == 0:
+                s[pos] = alphabet[int(rng.integers(len(alphabet)))]
+            elif op == 1:
+                del s[pos]
+            else:
+                s.insert(pos, alphabet[int(rng.integers(len(alphabet)))])
+        text = "".join(s)
+        kw = [{}, {"skip_hetatm": True}, {"ignore_endmdl": True}][it % 3]
+        info, native, generic = _both(text, **kw)
+        if info.fallback == 0:
+            accepted += 1
+            assert not isinstance(generic, Exception), (text, generic)
+            assert native.tobytes() == generic.tobytes(), text
+    assert accepted > 300
