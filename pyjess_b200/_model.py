@@ -77,6 +77,8 @@ def _api_atom_name(name) -> bytes:
     return raw
 
 
+_HEADER_EOL = re.compile(rb"[\r\n]")
+_NEXT_HEADER = re.compile(rb"[\r\n]HEADER")
 _INT_RE = re.compile(rb"[ \t\n\v\f\r]*([+-]?\d+)")
 _FLT_RE = re.compile(
     rb"[ \t\n\v\f\r]*([+-]?(?:(?:\d+\.?\d*|\.\d+)(?:[eE][+-]?\d+)?|inf(?:inity)?|nan))", re.I
@@ -554,8 +556,8 @@ class Molecule:
         arr = arr[:info.n_atoms].copy() if info.n_atoms * 2 < cap else arr[:info.n_atoms]
         pos = info.header_offset
         while pos >= 0 and pos < info.stop_offset and (id is None or date is None or name is None):
-            end = data.find(b"\n", pos)
-            text = data[pos:end if end >= 0 else len(data)].decode("utf-8", "replace")
+            end = _HEADER_EOL.search(data, pos)           # a lone "\r" ends a line too (text mode of the reference)
+            text = data[pos:end.start() if end else len(data)].decode("utf-8", "replace")
             if id is None:
                 id = text[62:66].strip() or None
             if date is None:
@@ -566,8 +568,8 @@ class Molecule:
                 name = text[10:50].strip() or None
             if info.n_headers <= 1:
                 break
-            pos = data.find(b"\nHEADER", pos + 1, info.stop_offset)
-            pos = pos + 1 if pos >= 0 else -1
+            nxt = _NEXT_HEADER.search(data, pos + 1, info.stop_offset)
+            pos = nxt.start() + 1 if nxt else -1
         return cls._from_records(arr, id=id, date=date, name=name)
 
     @classmethod
@@ -575,7 +577,10 @@ class Molecule:
         """Line-by-line Python restatement of the same loader (test reference for the
         native parser; `Atom.loads` shares `_parse_atom_line`)."""
         lines = []
-        for line in data.splitlines(keepends=True):
+        # the reference reads in text mode: universal newlines ("\r\n" and a lone "\r" end a line as "\n")
+        data = data.replace(b"\r\n", b"\n").replace(b"\r", b"\n")
+        for line in data.split(b"\n"):
+            line += b"\n"
             if line.startswith(b"HEADER"):
                 text = line.decode("utf-8", "replace")
                 if id is None:

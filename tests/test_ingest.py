@@ -206,3 +206,39 @@ def test_threaded_packing_is_identical(monkeypatch):
                                         for k in ("x", "y", "z", "name", "resname", "resseq", "chain", "serial")]
         ref = ref or cur
         assert all(np.array_equal(u, v) for u, v in zip(ref, cur)), threads
+
+
+def test_pdb_loader_fuzz_against_the_line_by_line_restatement():
+    """Random edits of a PDB excerpt (blanks, digits, NULs, lone carriage returns, truncated
+    lines): the product path (native one-pass parser + header decoding) and the line-by-line
+    restatement of the reference's text-mode loader give the same records, id, name and date."""
+    with open(os.path.join(DATA, "pdb1lnb.ent")) as f:
+        lines = f.read().split("\n")
+    base = "\n".join(lines[:3] + [l for l in lines if l.startswith(("ATOM", "HETATM", "ENDMDL", "HEADER"))][:60]) + "\n"
+    rng = np.random.default_rng(5)
+    alphabet = list(" \n\r\t.-+0123456789eExXATOMHETNDLRabc_\0")
+
+    def outcome(loader, data, **kw):
+        try:
+            with np.errstate(over="ignore"):
+                m = loader(data, **kw)
+            return m._atoms.tobytes(), m.id, m.name, m.date
+        except Exception as err:  # noqa: BLE001
+            return type(err).__name__
+
+    for it in range(500):
+        s = list(base)
+        for _ in range(int(rng.integers(1, 5))):
+            op, pos = int(rng.integers(0, 3)), int(rng.integers(0, len(s)))
+            if op == 0:
+                s[pos] = alphabet[int(rng.integers(len(alphabet)))]
+            elif op == 1:
+                del s[pos]
+            else:
+                s.insert(pos, alphabet[int(rng.integers(len(alphabet)))])
+        data = "".join(s).encode()
+        kw = [{}, {"skip_hetatm": True}, {"ignore_endmdl": True}][it % 3]
+        full = dict(ignore_endmdl=kw.get("ignore_endmdl", False), skip_hetatm=kw.get("skip_hetatm", False))
+        got = outcome(lambda d, **k: Molecule._parse_pdb(d, id=None, date=None, name=None, format="pdb", **k), data, **full)
+        want = outcome(Molecule._parse_pdb_python, data, **full)
+        assert got == want, data
