@@ -853,7 +853,12 @@ class TemplateAtom:
                         raise ValueError(f"Failed to parse template atom: {text!r}")
                     resnames.append(three.encode("ascii"))
                     m += 1
-                i += m
+                # The reference does NOT step over the codes it has just read (eff:TessAtom.c:236-252 leaves `q`
+                # where it is): while names are still owed, the same run of codes is read again, so " E   C"
+                # yields GLU, GLU and "W     L0.00" is accepted.  With an atom name still owed it would re-read
+                # them for ever, writing past its allocation: that input is refused here.
+                if len(names) < ac:
+                    raise ValueError(f"Failed to parse template atom: {text!r}")
         atom = cls.__new__(cls)
         atom._code = int(rec["serial"][0])
         atom._resseq = int(rec["resSeq"][0])

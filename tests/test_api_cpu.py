@@ -142,3 +142,25 @@ def test_batch_run_slices_with_a_stubbed_engine(monkeypatch):
         assert all(h.template() is tpl[t[i]] and h.molecule() is mols[m] for h, i in zip(hits, want))
         seen += len(rows)
     assert seen == n - len({int(mol[i]) for i in range(n) if t[i] == single})
+
+
+def test_template_atom_residue_codes_are_reread_like_the_reference():
+    """``TessAtom_create`` does not step over the one-letter residue codes it has just read
+    (eff:TessAtom.c:236-252): while names are still owed, the SAME run of codes is read again.
+    Expected values: the reference library (pyjess 0.10.1) on these lines; found by a differential
+    fuzz of ``Template.loads`` (4,500 mutated templates, no other difference)."""
+    from pyjess_b200 import TemplateAtom
+    cases = {
+        "ATOM      3  OE1ZGLU A  43      42.721 -29.948   8.832 E   C 2.08 ": ("GLU", "GLU", "GLU"),
+        "ATOM      0  NE1ZTRP A 204      43.868   1.684  54.342 W     L0.00 ": ("TRP", "TRP", "TRP"),
+        "ATOM      1  OG ZSER A  10       1.000   2.000   3.000 TY    1.50 ": ("SER", "THR", "TYR"),
+        ("ATOM      0  CZ2ZTRP A 204      41.395   1.476  53.906 W     0.00 "
+         "ATOM      0  CH2ZTRP A 204      40.173   1.626  54.507 W     0.00 "): ("TRP",) * 13,
+    }
+    for line, want in cases.items():
+        assert TemplateAtom.loads(line).residue_names == want
+    # an atom name still owed after a run of codes: the reference re-reads the codes for ever (and
+    # writes past its allocation); refused here
+    import pytest
+    with pytest.raises(ValueError):
+        TemplateAtom.loads("ATOM      1  OG ZSER A  10       1.000   2.000   3.000 T (OG1) 1.50 ")
