@@ -396,11 +396,11 @@ class Atom:
 
     @property
     def name(self) -> str:
-        return self._rec["name"][0].decode("ascii").strip("_")
+        return self._rec["name"].tobytes()[:4].decode("ascii").strip("_")       # raw bytes, like the reference
 
     @property
     def residue_name(self) -> str:
-        return self._rec["resName"][0][:3].decode("ascii").strip("_")
+        return self._rec["resName"].tobytes()[:3].decode("ascii").strip("_")
 
     @property
     def residue_number(self) -> int:
@@ -408,11 +408,11 @@ class Atom:
 
     @property
     def segment(self) -> str:
-        return self._rec["segID"][0].decode("ascii").strip("_")
+        return self._rec["segID"].tobytes()[:4].decode("ascii").strip("_")      # raw bytes: NULs of a short line stay
 
     @property
     def element(self) -> str:
-        return self._rec["element"][0].decode("ascii").strip("_")
+        return self._rec["element"].tobytes()[:2].decode("ascii").strip("_")
 
     @property
     def insertion_code(self) -> str:
