@@ -614,6 +614,67 @@ class Molecule:
         mol._pack = None
         return mol
 
+    # -- adapters to third-party structure objects (src/pyjess/_jess.pyx:444-631) --------------
+    # Duck-typed like the reference's: none of the three libraries is imported, only the
+    # attributes the reference reads are touched, so the keyword each one feeds `Atom` is the same.
+
+    @classmethod
+    def from_biopython(cls, structure, id=None, date=None, name=None) -> "Molecule":
+        """A `Bio.PDB` entity (structure, model or chain list) -> `Molecule`
+        (src/pyjess/_jess.pyx:444-513); ``id`` defaults to ``structure.id``."""
+        atoms = []
+        for chain in structure.get_chains():
+            for residue in chain.get_residues():
+                _, residue_number, insertion_code = residue.id
+                for a in residue.get_atoms():
+                    xyz = a.get_coord()
+                    atoms.append(Atom(
+                        serial=a.serial_number, name=a.fullname, altloc=a.altloc,
+                        residue_name=residue.resname, chain_id=chain.id,
+                        residue_number=residue_number, insertion_code=insertion_code,
+                        x=xyz[0], y=xyz[1], z=xyz[2],
+                        occupancy=a.occupancy, temperature_factor=a.bfactor,
+                        segment=residue.segid, element=a.element, charge=a.pqr_charge or 0,
+                    ))
+        return cls(atoms, id=structure.id if id is None else id, date=date, name=name)
+
+    @classmethod
+    def from_gemmi(cls, model, id=None, date=None, name=None) -> "Molecule":
+        """A `gemmi.Model` -> `Molecule` (src/pyjess/_jess.pyx:515-564): the CRA walk of
+        ``model.all()``; gemmi's NUL alternate location becomes a blank."""
+        atoms = []
+        for cra in model.all():
+            a, r, c = cra.atom, cra.residue, cra.chain
+            atoms.append(Atom(
+                serial=a.serial, name=a.padded_name(),
+                altloc=" " if a.altloc == "\0" else a.altloc,
+                residue_name=r.name, chain_id=c.name,
+                residue_number=r.seqid.num, insertion_code=r.seqid.icode,
+                x=a.pos[0], y=a.pos[1], z=a.pos[2],
+                occupancy=a.occ, temperature_factor=a.b_iso,
+                segment=r.segment, element=a.element.name.upper(), charge=a.charge,
+            ))
+        return cls(atoms, id=id, date=date, name=name)
+
+    @classmethod
+    def from_biotite(cls, atom_array, id=None, date=None, name=None) -> "Molecule":
+        """A `biotite.structure.AtomArray` -> `Molecule` (src/pyjess/_jess.pyx:566-631);
+        the optional annotations (altloc, charge, occupancy, segment) take the reference's
+        defaults when the array was read without them."""
+        atoms = []
+        for a in atom_array:
+            atoms.append(Atom(
+                serial=a.atom_id, name=str(a.atom_name),
+                altloc=str(getattr(a, "altloc", " ")),
+                residue_name=str(a.res_name), chain_id=str(a.chain_id),
+                residue_number=a.res_id, insertion_code=str(a.ins_code).ljust(1),
+                x=a.coord[0], y=a.coord[1], z=a.coord[2],
+                occupancy=getattr(a, "occupancy", 1.0), temperature_factor=a.b_factor,
+                segment=str(getattr(a, "segment", "")), element=str(a.element),
+                charge=getattr(a, "charge", 0),
+            ))
+        return cls(atoms, id=id, date=date, name=name)
+
     @classmethod
     def from_arrays(cls, *, name, residue_name, residue_number, chain_id, x, y, z,
                     serial=None, occupancy=None, temperature_factor=None, id=None) -> "Molecule":
