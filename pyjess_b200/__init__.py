@@ -16,3 +16,7 @@ def __getattr__(name):
         from . import _jess
         return getattr(_jess, name)
     raise AttributeError(name)
+
+
+def __dir__():
+    return sorted(set(globals()) | set(__all__))

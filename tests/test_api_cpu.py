@@ -164,3 +164,28 @@ def test_template_atom_residue_codes_are_reread_like_the_reference():
     import pytest
     with pytest.raises(ValueError):
         TemplateAtom.loads("ATOM      1  OG ZSER A  10       1.000   2.000   3.000 T (OG1) 1.50 ")
+
+
+# public members of the reference's classes (dir() of the PyJess 0.10.1 build under baseline/_ref)
+REFERENCE_SURFACE = {
+    "Atom": ["altloc", "chain_id", "charge", "copy", "dump", "dumps", "element", "insertion_code",
+             "load", "loads", "name", "occupancy", "residue_name", "residue_number", "segment",
+             "serial", "temperature_factor", "transform", "x", "y", "z"],
+    "Molecule": ["conserved", "copy", "date", "dump", "dumps", "from_biopython", "from_biotite",
+                 "from_gemmi", "id", "load", "loads", "name", "transform"],
+    "TemplateAtom": ["atom_names", "chain_id", "copy", "distance_weight", "dump", "dumps", "load",
+                     "loads", "match_mode", "residue_names", "residue_number", "transform", "x", "y", "z"],
+    "Template": ["copy", "dimension", "dump", "dumps", "id", "load", "loads", "transform"],
+    "Jess": ["copy", "query"],
+    "Query": ["best_match", "ignore_chain", "jess", "max_candidates", "molecule", "rmsd_threshold"],
+    "Hit": ["atoms", "determinant", "dump", "dumps", "evalue", "inverse_transformation",
+            "log_evalue", "molecule", "rmsd", "template", "transformation"],
+}
+
+
+def test_every_public_member_of_the_reference_classes_exists():
+    import pyjess_b200
+    assert set(REFERENCE_SURFACE) <= set(dir(pyjess_b200))
+    for cls, members in REFERENCE_SURFACE.items():
+        missing = [m for m in members if not hasattr(getattr(pyjess_b200, cls), m)]
+        assert not missing, (cls, missing)
