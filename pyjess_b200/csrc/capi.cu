@@ -19,6 +19,7 @@
 #include "../../include/jess_b200.h"
 #include "kernels.cuh"
 #include "expand_lv.cuh"
+#include "expand_grid.cuh"
 #include "hits.cuh"
 #include "order.cuh"
 #include <cub/device/device_radix_sort.cuh>
@@ -117,9 +118,10 @@ struct jb_context {
     int group_lv[kMaxN + 1] = {};  // per-level override (JB_GROUPS="g1,g2,..." for levels 1, 2, ...); 0: default
     int debug = 0;                // JB_DEBUG: per-level counts and times on stderr
     int legacy = 0;               // JB_LEGACY: run-time-level k_expand at every level (A/B comparisons)
+    int sweep = 1;                // JB_SWEEP: 1 cell-grid sweep (expand_grid.cuh), 0 x-range stream (expand_lv.cuh)
     cudaEvent_t lev[kMaxN + 1] = {};
     // workspace (grow only)
-    DevBuf crec, chead, cxtab, recs, ordbuf, fr[2], tuples, ctr;
+    DevBuf crec, chead, cxtab, cbin, cbinlist, recs, ordbuf, fr[2], tuples, ctr;
     DevBuf h_mol, h_tpl, h_atoms, h_rmsd, h_rot, h_c0, h_c1;   // hits as k_superpose appends them
     DevBuf f_mol, f_tpl, f_atoms, f_rmsd, f_rot, f_c0, f_c1;   // ... in canonical order (hits.cuh)
     DevBuf o_off, o_fill, o_grouped, o_order, o_tiles, o_runs, o_work;   // ordering workspace
@@ -135,6 +137,7 @@ struct jb_context {
     int runs_since_decay = 0;     // context_decay: every kDecayRuns calls, buffers far larger than recently needed go back
     long long trim_epoch = 0;     // bumped by jb_context_trim: un-fetched results of earlier runs are gone
     Counters *host_ctr = nullptr; // pinned
+    u64 *host_lv = nullptr;       // pinned, JB_DEBUG: (scan_tests, box_pass) after every level
     struct jb_molecules *scratch_mol = nullptr;   // reused by jb_query_host (no per-call cudaMalloc)
     struct jb_molecules *slice_mol[2] = { nullptr, nullptr };   // double-buffered staging of the pipelined jb_query_host
     cudaStream_t copy_stream = nullptr;           // H2D of the next slice / D2H of the previous slice's hits
@@ -221,7 +224,9 @@ extern "C" int jb_context_create(int device, void *stream, int64_t workspace_byt
         int v = atoi(g);
         if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) c->group = v;
     }
-    c->group_lv[1] = 1;   // level 1 stages a single atom per partial match: one lane each (measured -3 % per step)
+    // one lane per partial match at the hot levels: the cell-grid sweep works per lane, and a batch of 32
+    // partial matches halves the per-batch overheads (prefix sums, final partial drain)
+    c->group_lv[1] = c->group_lv[2] = c->group_lv[3] = 1;
     if (const char *g = getenv("JB_GROUPS")) {
         int l = 1;
         for (const char *p = g; *p && l <= kMaxN; l++) {
@@ -234,10 +239,12 @@ extern "C" int jb_context_create(int device, void *stream, int64_t workspace_byt
     if (const char *g = getenv("JB_DECAY_RUNS")) c->decay_runs = std::max(1, atoi(g));
     if (const char *g = getenv("JB_DEBUG")) c->debug = atoi(g);
     if (const char *g = getenv("JB_LEGACY")) c->legacy = atoi(g);
+    if (const char *g = getenv("JB_SWEEP")) c->sweep = atoi(g);
     if (const char *g = getenv("JB_PIPELINE")) c->pipeline_slices = atoi(g);
     if (c->debug) for (int i = 0; i <= kMaxN; i++) CU(cudaEventCreate(&c->lev[i]));
     CU(cudaMallocHost(&c->host_ctr, sizeof(Counters)));
     CU(cudaMallocHost(&c->host_work, sizeof(RunWork)));
+    CU(cudaMallocHost(&c->host_lv, 2 * (kMaxN + 2) * sizeof(u64)));
     CU(c->o_work.ensure(2 * sizeof(RunWork), c->stream));   // [0] tile work list, [1].n_runs = number of tie runs
     CU(c->ctr.ensure(sizeof(Counters), c->stream));
     CU(cudaEventCreate(&c->ev0));
@@ -251,7 +258,7 @@ extern "C" int jb_context_create(int device, void *stream, int64_t workspace_byt
 // ordering work list).  They only ever grow to the largest workload seen; jb_context_trim gives the memory back.
 static std::vector<DevBuf *> context_buffers(jb_context *c)
 {
-    return { &c->crec, &c->chead, &c->cxtab, &c->recs, &c->ordbuf, &c->fr[0], &c->fr[1],
+    return { &c->crec, &c->chead, &c->cxtab, &c->cbin, &c->cbinlist, &c->recs, &c->ordbuf, &c->fr[0], &c->fr[1],
              &c->tuples, &c->h_mol, &c->h_tpl, &c->h_atoms, &c->h_rmsd, &c->h_rot, &c->h_c0,
              &c->h_c1, &c->f_mol, &c->f_tpl, &c->f_atoms, &c->f_rmsd, &c->f_rot, &c->f_c0, &c->f_c1,
              &c->o_off, &c->o_fill, &c->o_grouped, &c->o_order, &c->o_tiles, &c->o_runs,
@@ -342,6 +349,7 @@ extern "C" void jb_context_destroy(jb_context *c)
     }
     if (c->host_ctr) cudaFreeHost(c->host_ctr);
     if (c->host_work) cudaFreeHost(c->host_work);
+    if (c->host_lv) cudaFreeHost(c->host_lv);
     for (auto &blk : c->pin_pool) cudaFreeHost(blk.first);
     c->pin_pool.clear();
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -691,6 +699,38 @@ static cudaError_t dispatch_expand_lv(int level, int g, int sm_count, cudaStream
 #undef JB_LV_CASE
 }
 
+// cell-grid sweep (expand_grid.cuh): levels 1..kMaxLv, G lanes per partial match
+template <int L, int G, bool ROOT = false>
+static cudaError_t launch_expand_grid(int sm_count, cudaStream_t st, const ExpandArgs &a, const GridArgs &b, int stats)
+{
+    constexpr size_t smem = expand_grid_smem<L, G>();
+    if (smem > 48 * 1024) {   // per device: set on every launch (a context per GPU may share this process)
+        cudaError_t e = cudaFuncSetAttribute(k_expand_grid<L, G, ROOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / (smem + 1024)));   // 227 KB per SM, 1 KB reserved per CTA
+    k_expand_grid<L, G, ROOT><<<sm_count * per_sm, kExpandThreads, smem, st>>>(a, b, stats);
+    return cudaGetLastError();
+}
+
+static cudaError_t dispatch_expand_grid(int level, int g, int sm_count, cudaStream_t st, const ExpandArgs &a, const GridArgs &b,
+                                        int stats)
+{
+    constexpr size_t budget = 200 * 1024;   // keep at least two CTAs per SM resident
+#define JB_GRID_CASE(LL)                                                                                                  \
+    case LL:                                                                                                              \
+        if (g <= 1 && 2 * expand_grid_smem<LL, 1>() <= budget) return launch_expand_grid<LL, 1>(sm_count, st, a, b, stats); \
+        if (g <= 2 && 2 * expand_grid_smem<LL, 2>() <= budget) return launch_expand_grid<LL, 2>(sm_count, st, a, b, stats); \
+        return launch_expand_grid<LL, 4>(sm_count, st, a, b, stats);
+    switch (level) {
+        JB_GRID_CASE(1) JB_GRID_CASE(2) JB_GRID_CASE(3) JB_GRID_CASE(4)
+        JB_GRID_CASE(5) JB_GRID_CASE(6) JB_GRID_CASE(7) JB_GRID_CASE(8)
+        JB_GRID_CASE(9) JB_GRID_CASE(10) JB_GRID_CASE(11) JB_GRID_CASE(12)
+    default: return cudaErrorInvalidValue;
+    }
+#undef JB_GRID_CASE
+}
+
 // Reference iteration order (order.cuh): builds the (structure, ordered spec) rank tables of
 // the chunk and the rank vector of every hit in [h0, h1).
 static int build_reference_keys(jb_context *c, const jb_templates *t, const jb_molecules *mol, const jb_query_params *q,
@@ -871,6 +911,13 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
             if (const char *g = getenv("JB_TEST_CREC")) init_records = std::max(64, atoi(g));   // tests: force the retry
             CU(c->crec.ensure((size_t)init_records * sizeof(float4), st));
         }
+        if (c->cbin.bytes == 0) {
+            // one bin per non-empty list + one per 64 further records; grown on demand like the record array
+            long long init_bins = std::max<long long>((long long)(c->crec.bytes / sizeof(float4)) / kBinRecs + (long long)Mc * t->S / 4, 1024);
+            if (const char *g = getenv("JB_TEST_CBIN")) init_bins = std::max(4, atoi(g));   // tests: force the retry
+            CU(c->cbin.ensure((size_t)init_bins * sizeof(BinTab), st));
+        }
+        CU(c->cbinlist.ensure(c->cbin.bytes / sizeof(BinTab) * sizeof(int), st));
         MolTable MT;
         MT.n_molecules = Mc;
         MT.atom_off = mol->d_off.as<long long>() + r.m0;
@@ -881,6 +928,8 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         CandTable CT;
         CT.head = c->chead.as<CandHead>(); CT.rec = c->crec.as<float4>(); CT.xtab = c->cxtab.as<unsigned short>();
         CT.cap = (long long)(c->crec.bytes / sizeof(float4));
+        CT.bins = c->cbin.as<BinTab>(); CT.binlist = c->cbinlist.as<int>();
+        CT.bin_cap = (long long)(c->cbin.bytes / sizeof(BinTab));
         Counters *dc = c->ctr.as<Counters>();
 
         // reset counters; the hit cursor continues after the chunks already done
@@ -891,6 +940,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         CU(cudaEventRecord(c->evs[0], st));
         k_classify<<<Mc, 256, classify_smem, st>>>(MT, ST, CT, dc, class_words);
         k_xindex<<<(unsigned)(((long long)Mc * t->S * 32 + 255) / 256), 256, 0, st>>>((long long)Mc * t->S, CT);
+        if (c->sweep) k_binindex<<<c->sm_count * 8, 256, 0, st>>>(CT, dc);
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->evs[1], st));
         if (q->reorder == 2) {
@@ -920,7 +970,12 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
             A.out_cap = fr_ints[l & 1] / (l + 2);
             A.tuples = c->tuples.as<int>(); A.tuple_cap = tuple_cap;
             A.ctr = dc;
-            if (c->debug) CU(cudaEventRecord(c->lev[l], st));
+            GridArgs GA;
+            GA.bins = CT.bins; GA.bin_cap = CT.bin_cap;
+            if (c->debug) {
+                CU(cudaEventRecord(c->lev[l], st));
+                CU(cudaMemcpyAsync(c->host_lv + 2 * l, &dc->scan_tests, 2 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+            }
             // lanes per partial match: the configured G, widened at deep levels so that at
             // least two CTAs per SM fit their staging areas in shared memory
             int g = (l <= kMaxN && c->group_lv[l] > 0) ? c->group_lv[l] : c->group;
@@ -931,13 +986,20 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
             if (l == 1 && fused_root) {
                 A.in = nullptr; A.in_count = &dc->live_pairs; A.in_cap = pairs;
                 const int stats = c->debug != 0;
+                if (c->sweep) {
+                    if (g <= 1) CU((launch_expand_grid<1, 1, true>(c->sm_count, st, A, GA, stats)));
+                    else if (g == 2) CU((launch_expand_grid<1, 2, true>(c->sm_count, st, A, GA, stats)));
+                    else CU((launch_expand_grid<1, 4, true>(c->sm_count, st, A, GA, stats)));
+                    continue;
+                }
                 if (g <= 1) CU((launch_expand_lv<1, 1, true>(c->sm_count, st, A, stats)));
                 else if (g == 2) CU((launch_expand_lv<1, 2, true>(c->sm_count, st, A, stats)));
                 else CU((launch_expand_lv<1, 4, true>(c->sm_count, st, A, stats)));
                 continue;
             }
             if (l >= 1 && l <= kMaxLv && !c->legacy) {
-                CU(dispatch_expand_lv(l, g, c->sm_count, st, A, c->debug != 0));
+                if (c->sweep) CU(dispatch_expand_grid(l, g, c->sm_count, st, A, GA, c->debug != 0));
+                else CU(dispatch_expand_lv(l, g, c->sm_count, st, A, c->debug != 0));
                 continue;
             }
             while (g < 16 && 2 * expand_smem(g, l) > 200 * 1024) g <<= 1;
@@ -956,7 +1018,10 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
             CU(e);
         }
         CU(cudaEventRecord(c->evs[3], st));
-        if (c->debug) CU(cudaEventRecord(c->lev[t->nmax], st));
+        if (c->debug) {
+            CU(cudaEventRecord(c->lev[t->nmax], st));
+            CU(cudaMemcpyAsync(c->host_lv + 2 * t->nmax, &dc->scan_tests, 2 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+        }
         HitBuf HB;
         HB.pair = q->hit_order != JB_ORDER_CANONICAL ? c->h_pair.as<int>() : nullptr;
         HB.mol = c->h_mol.as<int>(); HB.tpl = c->h_tpl.as<int>(); HB.atoms = c->h_atoms.as<int>();
@@ -977,8 +1042,9 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
             for (int l = 0; l < t->nmax; l++) {
                 float ms = 0.f;
                 cudaEventElapsedTime(&ms, c->lev[l], c->lev[l + 1]);
-                fprintf(stderr, "[jb]   level %2d: in=%12llu out=%12llu  %8.3f ms\n", l,
-                        l == 0 ? hc.live_pairs : hc.level[l], hc.level[l + 1], ms);
+                fprintf(stderr, "[jb]   level %2d: in=%12llu out=%12llu  %8.3f ms  covered=%12llu box=%12llu\n", l,
+                        l == 0 ? hc.live_pairs : hc.level[l], hc.level[l + 1], ms, c->host_lv[2 * l + 2] - c->host_lv[2 * l],
+                        c->host_lv[2 * l + 3] - c->host_lv[2 * l + 1]);
             }
         }
         S.launches += 4 + t->nmax - ((t->nmin >= 2 && !c->legacy && !getenv("JB_NO_ROOT_FUSION")) ? 1 : 0);
@@ -992,6 +1058,8 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         {
             auto used = [](DevBuf &b, size_t bytes) { b.recent = std::max(b.recent, std::min(bytes, b.bytes)); };
             used(c->crec, (size_t)hc.cand_total * sizeof(float4));
+            used(c->cbin, (size_t)hc.bin_total * sizeof(BinTab));
+            used(c->cbinlist, (size_t)hc.bin_total * sizeof(int));
             for (int l = 0; l < t->nmax; l++) used(c->fr[l & 1], (size_t)hc.level[l + 1] * (l + 2) * sizeof(int));
             used(c->tuples, (size_t)hc.tuples * tuple_stride * sizeof(int));
             const size_t nhits = (size_t)std::min<u64>(hc.hits, (u64)c->hit_cap);   // cumulative over the run
@@ -1006,6 +1074,11 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         if ((long long)hc.cand_total > CT.cap) {
             const size_t need = (size_t)hc.cand_total + (size_t)hc.cand_total / 8;
             CU(c->crec.ensure(need * sizeof(float4), st));
+            retry = true;
+        }
+        if (c->sweep && (long long)hc.bin_total > CT.bin_cap) {
+            const size_t need = (size_t)hc.bin_total + (size_t)hc.bin_total / 8;
+            CU(c->cbin.ensure(need * sizeof(BinTab), st));
             retry = true;
         }
         if (!retry) {

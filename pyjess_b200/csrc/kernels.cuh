@@ -103,7 +103,8 @@ struct alignas(32) CandHead {  // one candidate list = one (structure, spec): on
     int cnt;
     float x0;                  // x of the first (smallest-x) record
     float inv_w;               // kXBuckets / (x range of the list); 0: a single bucket
-    int pad[3];
+    int bin0;                  // first BinTab of the list (k_classify reserves ceil(cnt / kBinRecs) of them)
+    int pad[2];
 };
 
 // bucket of an x coordinate: monotone non-decreasing in x (no FMA: the TU is built with
@@ -113,11 +114,48 @@ __device__ __forceinline__ int x_bucket(float x, float x0, float inv_w)
     return (int)fminf(fmaxf((x - x0) * inv_w, 0.f), (float)(kXBuckets - 1));
 }
 
+// ---- the cell grid of a candidate list (k_binindex, expand_grid.cuh) ---------------------------
+// A list is cut into BINS of kBinRecs consecutive records (x-sorted, so a bin is an x slab).  Every
+// bin carries a uniform grid of kMaskBuckets cells per axis over its own bounding box, stored
+// separably: per axis and cell b the BIT MASK of the bin's records whose cell index is <= b.  The
+// records inside an axis-aligned box are then
+//     AND over the three axes of  upto[a][cell(hi_a)] & ~upto[a][cell(lo_a) - 1]
+// -- six 16-byte loads and a few logic operations per (partial match, bin) instead of one load and six
+// compares per RECORD (the k-d tree walk of eff:KdTree.c:238-296 becomes three slab look-ups).  The
+// same monotone cell function bins the records and the query bounds, so the result is a superset
+// of the records inside the box; the exact FP64 predicate still decides.
+constexpr int kBinRecs = 128;          // (64-record bins with 8-byte masks measured the same on cfg 3 and cfg 4, gpurun_out/r2c)
+constexpr int kMaskWords = kBinRecs / 32;
+constexpr int kMaskBuckets = 32;
+
+struct alignas(kBinRecs / 8) BinMask { unsigned w[kMaskWords]; };
+
+struct alignas(32) BinTab {            // 1568 bytes
+    float2 frame[4];                   // per axis: (smallest coordinate of the bin, cells per unit length); [3] unused
+    BinMask upto[3][kMaskBuckets];
+};
+
+__device__ __forceinline__ BinMask ldg_mask(const BinMask *p)
+{
+    BinMask r;
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+    r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
+    return r;
+}
+
+__device__ __forceinline__ int axis_cell(float v, float2 frame)
+{
+    return (int)fminf(fmaxf((v - frame.x) * frame.y, 0.f), (float)(kMaskBuckets - 1));
+}
+
 struct CandTable {
     CandHead *head;            // [M*S]
     unsigned short *xtab;      // [M*S][kXBuckets]: first record whose x bucket is >= b (lists <= 65535 records)
     float4 *rec;               // x-sorted copies of srec entries: FP32 is ONLY a conservative prefilter
     long long cap;             // capacity (records)
+    BinTab *bins;              // cell grids, one per bin (k_binindex)
+    int *binlist;              // bin -> list
+    long long bin_cap;         // capacity (bins)
 };
 
 struct alignas(32) ShellRec {  // constraint of an ORDERED template-atom pair (earlier i, later k)
@@ -140,6 +178,7 @@ struct alignas(16) PairRec {   // one live (structure, template) pair, 128 bytes
 
 struct Counters {              // device counters of one chunk attempt
     u64 cand_total;            // records reserved in CandTable
+    u64 bin_total;             // bins reserved in CandTable
     u64 live_pairs;
     u64 cand_atoms;            // sum_k |C_k| over live pairs
     u64 cand_tests;            // sum over partial matches of |C_level| (algorithm independent)
@@ -516,8 +555,15 @@ __global__ void __launch_bounds__(256) k_classify(MolTable M, SpecTable S, CandT
                     sh_cnt[v * ns + s] = run;
                     run += c;
                 }
-                CandHead h; h.off = 0; h.cnt = run; h.x0 = 0.f; h.inv_w = 0.f; h.pad[0] = h.pad[1] = h.pad[2] = 0;
-                if (run > 0) h.off = (long long)atomicAdd(&ctr->cand_total, (u64)run);
+                CandHead h; h.off = 0; h.cnt = run; h.x0 = 0.f; h.inv_w = 0.f; h.bin0 = 0; h.pad[0] = h.pad[1] = 0;
+                if (run > 0) {
+                    h.off = (long long)atomicAdd(&ctr->cand_total, (u64)run);
+                    const int nb = (run + kBinRecs - 1) / kBinRecs;
+                    const long long b0 = (long long)atomicAdd(&ctr->bin_total, (u64)nb);
+                    h.bin0 = (int)min(b0, 0x7fffffffll);
+                    for (int b = 0; b < nb; b++)
+                        if (b0 + b < C.bin_cap) C.binlist[b0 + b] = m * ns + s;
+                }
                 C.head[(long long)m * ns + s] = h;
             }
             __syncthreads();
@@ -552,6 +598,75 @@ __global__ void __launch_bounds__(256) k_xindex(long long n_lists, CandTable C)
     }
     const int bl = x_bucket(x1, x0, inv_w);
     for (int q = bl + 1 + lane; q < kXBuckets; q += 32) tab[q] = (unsigned short)hd.cnt;
+}
+
+// ---- K1c: cell grid of every bin --------------------------------------------------------
+// One warp per bin: bounding box (warp min / max), cell of every record along the three axes,
+// 32 ballots per axis and 32 records of the bin.  Records with a NaN coordinate enter no mask (the box
+// test they replace -- r.x >= lo && r.x <= hi ... -- never accepted them either).
+__global__ void __launch_bounds__(256) k_binindex(CandTable C, const Counters *ctr)
+{
+    const int lane = threadIdx.x & 31;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    long long n_bins = (long long)ctr->bin_total;
+    if (n_bins > C.bin_cap) n_bins = C.bin_cap;                 // the chunk is being re-run larger
+    const float INF = __int_as_float(0x7f800000);
+    for (long long bin = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; bin < n_bins; bin += n_warps) {
+        const CandHead hd = C.head[C.binlist[bin]];
+        if (hd.cnt <= 0 || hd.off + hd.cnt > C.cap) continue;
+        const int first = (int)(bin - hd.bin0) * kBinRecs;
+        if (first < 0 || first >= hd.cnt) continue;
+        const int n = min(hd.cnt - first, kBinRecs);
+        const float4 *rec = C.rec + hd.off + first;
+        float4 r[kMaskWords];
+        bool ok[kMaskWords];
+        float lo[3] = { INF, INF, INF }, hi[3] = { -INF, -INF, -INF };
+#pragma unroll
+        for (int h = 0; h < kMaskWords; h++) {
+            const int p = lane + 32 * h;
+            r[h] = p < n ? rec[p] : make_float4(0.f, 0.f, 0.f, 0.f);
+            ok[h] = p < n && r[h].x == r[h].x && r[h].y == r[h].y && r[h].z == r[h].z;
+            if (ok[h]) {
+                lo[0] = fminf(lo[0], r[h].x); hi[0] = fmaxf(hi[0], r[h].x);
+                lo[1] = fminf(lo[1], r[h].y); hi[1] = fmaxf(hi[1], r[h].y);
+                lo[2] = fminf(lo[2], r[h].z); hi[2] = fmaxf(hi[2], r[h].z);
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+                hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+            }
+        BinTab *T = C.bins + bin;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            float inv = 0.f;
+            if (hi[a] > lo[a]) inv = (float)kMaskBuckets / (hi[a] - lo[a]);
+            if (!(inv > 0.f) || !(inv < 3.0e38f)) inv = 0.f;    // NaN / overflow / a single point: one cell
+            const float2 fr = make_float2(lo[a] <= hi[a] ? lo[a] : 0.f, inv);
+            int cell[kMaskWords];
+#pragma unroll
+            for (int h = 0; h < kMaskWords; h++) {
+                const float v = a == 0 ? r[h].x : (a == 1 ? r[h].y : r[h].z);
+                cell[h] = ok[h] ? axis_cell(v, fr) : kMaskBuckets;
+            }
+            BinMask mine;
+#pragma unroll
+            for (int h = 0; h < kMaskWords; h++) mine.w[h] = 0u;
+            for (int b = 0; b < kMaskBuckets; b++) {
+#pragma unroll
+                for (int h = 0; h < kMaskWords; h++) {
+                    const unsigned mb = __ballot_sync(0xffffffffu, cell[h] <= b);
+                    if (lane == b) mine.w[h] = mb;
+                }
+            }
+            T->upto[a][lane] = mine;
+            if (lane == 0) T->frame[a] = fr;
+        }
+        if (lane == 0) T->frame[3] = make_float2(0.f, 0.f);
+    }
 }
 
 // ---- K: shell radii ------------------------------------------------------------
