@@ -41,12 +41,16 @@ __device__ __forceinline__ int nth_set_bit(unsigned x, int k)
 
 template <int L, int G> struct alignas(16) GridWarp {   // per-warp shared memory
     static constexpr int IPW = 32 / G;                  // partial matches per batch
-    double cx[L][IPW], cy[L][IPW], cz[L][IPW], clo2[L][IPW], chi2[L][IPW];
+    // placed atoms + shells towards the new atom, one array per field and [atom][partial match].  The FP32
+    // image decides all but the borderline cases (see the drain), the FP64 radii serve those.
+    float4 cf[L][IPW];                                  // centre relative to the structure origin (FP32), lo_reject
+    float4 th[L][IPW];                                  // lo_certain, hi_certain, hi_reject of the squared distance
+    double clo2[L][IPW], chi2[L][IPW];
     int cres[L][IPW], cflag[L][IPW];
     long long cbase[IPW];                               // first record of the candidate list
     long long abase[IPW];                               // first atom of the structure
     int2 meta[IPW];                                     // pair index, "this level completes the template"
-    int clen[IPW];                                      // records in the candidate list
+                                      // records in the candidate list
     int chain_atom[L][IPW];
     int stage[kStageItems * (L + 2)];                   // accepted extensions awaiting the flush
 };
@@ -79,28 +83,47 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_grid(const ExpandA
     unsigned n_scan = 0, n_box = 0;                   // per-lane partial sums (diagnostics)
     const float INF = __int_as_float(0x7f800000);
 
-    // exact predicate + emission: one box survivor per lane (record `pos` of the list of partial match g)
+    // Exact predicate + emission: one box survivor per lane (record `pos` of the list of partial match g).
+    // _Annulus_po (eff:Annulus.h:54-68) decides on s = ((dx^2 + dy^2) + dz^2) in FP64.  The FP32 image of
+    // the same difference (coordinates relative to the structure origin, |error of s| < e with
+    // e = 2^-20 rb (ext + rb), more than twice the worst case: DESIGN.md "FP32 first") settles every
+    // survivor whose s lies outside [lo2 - e, lo2 + e] and [hi2 - e, hi2 + e]; the others -- a few per
+    // million -- take the FP64 operations of the reference on the FP64 atom records.
     auto drain = [&](bool ok, const int pos, const int g) {
-        int a = 0;
-        // (positions beyond the list only exist while a chunk is re-run larger: stale grids)
-        if (ok) a = __float_as_int(__ldg(&A.cand[W.cbase[g] + (pos < W.clen[g] ? pos : 0)].w));
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) r = __ldg(&A.cand[W.cbase[g] + pos]);
+        const int a = __float_as_int(r.w);
         const int2 mt = W.meta[g];
+        bool unsure = false;
         if (ok) {
-            const AtomRec p = A.atoms[W.abase[g] + a];
-            // _Annulus_po (eff:Annulus.h:54-68): ((dx^2 + dy^2) + dz^2), centre - point
 #pragma unroll
             for (int j = 0; j < L; j++) {
-                const double t0 = __dsub_rn(W.cx[j][g], p.x), t1 = __dsub_rn(W.cy[j][g], p.y), t2 = __dsub_rn(W.cz[j][g], p.z);
-                const double s = __dadd_rn(__dadd_rn(__dmul_rn(t0, t0), __dmul_rn(t1, t1)), __dmul_rn(t2, t2));
-                if (s < W.clo2[j][g] || s > W.chi2[j][g]) { ok = false; break; }
+                const float4 c = W.cf[j][g], t = W.th[j][g];
+                const float dx = __fsub_rn(c.x, r.x), dy = __fsub_rn(c.y, r.y), dz = __fsub_rn(c.z, r.z);
+                const float s = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+                if (s < c.w || s > t.z) { ok = false; break; }
+                unsure = unsure || !(s >= t.x && s <= t.y);
             }
-            if (ok) {
+        }
+        if (__any_sync(FULL, ok && unsure)) {
+            if (ok && unsure) {
+                const AtomRec p = A.atoms[W.abase[g] + a];
 #pragma unroll
                 for (int j = 0; j < L; j++) {
-                    const int f = W.cflag[j][g];
-                    if (!pair_consistent(A.ignore_chain, (f & 0xff) == p.chain, (f & 0x100) != 0, W.cres[j][g] == p.resseq,
-                                         (f & 0x200) != 0)) { ok = false; break; }
+                    const AtomRec q = A.atoms[W.abase[g] + W.chain_atom[j][g]];
+                    const double t0 = __dsub_rn(q.x, p.x), t1 = __dsub_rn(q.y, p.y), t2 = __dsub_rn(q.z, p.z);
+                    const double s = __dadd_rn(__dadd_rn(__dmul_rn(t0, t0), __dmul_rn(t1, t1)), __dmul_rn(t2, t2));
+                    if (s < W.clo2[j][g] || s > W.chi2[j][g]) { ok = false; break; }
                 }
+            }
+        }
+        if (ok) {
+            const int2 rc = *reinterpret_cast<const int2 *>(&A.atoms[W.abase[g] + a].resseq);   // resseq, chain
+#pragma unroll
+            for (int j = 0; j < L; j++) {
+                const int f = W.cflag[j][g];
+                if (!pair_consistent(A.ignore_chain, (f & 0xff) == rc.y, (f & 0x100) != 0, W.cres[j][g] == rc.x,
+                                     (f & 0x200) != 0)) { ok = false; break; }
             }
         }
         const unsigned okm = __ballot_sync(FULL, ok);
@@ -249,10 +272,10 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_grid(const ExpandA
                 W.meta[grp] = make_int2(lp, (L + 1 == n) ? 1 : 0);
                 W.abase[grp] = h1.x;
                 W.cbase[grp] = coff;
-                W.clen[grp] = cnt;
             }
             const MolExt me = A.ext[h0.x];
             const float err = __double2float_ru(me.ext * 2.4e-7 + 1e-30);    // > ext * 2^-22: record rounding
+            const float extu = __double2float_ru(me.ext);
 #pragma unroll
             for (int jj = 0; jj < (L + G - 1) / G; jj++) {
                 const int j = jj * G + gl;
@@ -260,12 +283,18 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_grid(const ExpandA
                     const int a = ROOT ? root_a : it[1 + j];
                     const AtomRec ar = A.atoms[h1.x + a];
                     const ShellRec sh = A.shell[h1.y + (long long)rec->order[j] * n + k];
-                    W.cx[j][grp] = ar.x; W.cy[j][grp] = ar.y; W.cz[j][grp] = ar.z;
                     W.clo2[j][grp] = sh.lo2; W.chi2[j][grp] = sh.hi2;
                     W.cres[j][grp] = ar.resseq; W.cflag[j][grp] = ar.chain | (sh.flags << 8);
                     W.chain_atom[j][grp] = a;
                     const double dx = __dsub_rn(ar.x, me.ox), dy = __dsub_rn(ar.y, me.oy), dz = __dsub_rn(ar.z, me.oz);
                     const float rb = sh.rb;
+                    // FP32 image for the drain: the centre exactly as k_sort_atoms rounds the records, and the
+                    // squared radii moved outwards / inwards by the error bound of the FP32 squared distance
+                    const float eb = __fmul_ru(__fmul_ru(9.5367431640625e-07f, rb), __fadd_ru(extu, rb));   // 2^-20 rb (ext + rb)
+                    W.cf[j][grp] = make_float4(__double2float_rn(dx), __double2float_rn(dy), __double2float_rn(dz),
+                                               __fsub_rd(__double2float_rd(sh.lo2), eb));
+                    W.th[j][grp] = make_float4(__fadd_ru(__double2float_ru(sh.lo2), eb), __fsub_rd(__double2float_rd(sh.hi2), eb),
+                                               __fadd_ru(__double2float_ru(sh.hi2), eb), 0.f);
                     bx0 = fmaxf(bx0, __fsub_rd(__fsub_rd(__double2float_rd(dx), rb), err));
                     by0 = fmaxf(by0, __fsub_rd(__fsub_rd(__double2float_rd(dy), rb), err));
                     bz0 = fmaxf(bz0, __fsub_rd(__fsub_rd(__double2float_rd(dz), rb), err));

@@ -613,9 +613,19 @@ __global__ void __launch_bounds__(256) k_binindex(CandTable C, const Counters *c
     const float INF = __int_as_float(0x7f800000);
     for (long long bin = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; bin < n_bins; bin += n_warps) {
         const CandHead hd = C.head[C.binlist[bin]];
-        if (hd.cnt <= 0 || hd.off + hd.cnt > C.cap) continue;
+        BinTab *T = C.bins + bin;
         const int first = (int)(bin - hd.bin0) * kBinRecs;
-        if (first < 0 || first >= hd.cnt) continue;
+        if (hd.cnt <= 0 || hd.off + hd.cnt > C.cap || first < 0 || first >= hd.cnt) {
+            // a list cut by the end of the record array (the chunk is being re-run larger): an EMPTY grid, so
+            // that the sweep of this attempt never follows a stale mask to a record that was not written
+            BinMask none;
+#pragma unroll
+            for (int h = 0; h < kMaskWords; h++) none.w[h] = 0u;
+#pragma unroll
+            for (int a = 0; a < 3; a++) T->upto[a][lane] = none;
+            if (lane < 4) T->frame[lane] = make_float2(0.f, 0.f);
+            continue;
+        }
         const int n = min(hd.cnt - first, kBinRecs);
         const float4 *rec = C.rec + hd.off + first;
         float4 r[kMaskWords];
@@ -639,7 +649,6 @@ __global__ void __launch_bounds__(256) k_binindex(CandTable C, const Counters *c
                 lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
                 hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
             }
-        BinTab *T = C.bins + bin;
 #pragma unroll
         for (int a = 0; a < 3; a++) {
             float inv = 0.f;

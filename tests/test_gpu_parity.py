@@ -317,3 +317,51 @@ def test_oversized_buffers_decay_after_a_few_small_runs(monkeypatch):
         assert back.count == first.count and all(np.array_equal(a, b) for a, b in zip(first.arrays(), back.arrays()))
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("shift", [0.0, 731.25])
+def test_shell_boundary_candidates_take_the_exact_path(engine, oracle_lib, shift):
+    """The drain of the cell-grid sweep decides in FP32 and hands every candidate whose squared distance
+    lies within its error band of lo^2 / hi^2 to the reference's FP64 operations (expand_grid.cuh).  Here
+    most candidates sit ON the shell boundaries -- exactly, one FP64 ulp inside and outside, and a few
+    1e-7 A steps around them -- also with the structure origin far away (large FP32 error band).  The
+    tuple set and the counters must equal the oracle's (decisions bit for bit)."""
+    from pyjess_b200 import Molecule, Template, TemplateAtom
+    from pyjess_b200._tables import query_params
+    rng = np.random.default_rng(7)
+    dirs = [np.array(v, dtype=np.float64) for v in ((1, 0, 0), (0, 1, 0), (0, 0, -1), (0.6, 0.8, 0), (0, -0.6, 0.8),
+                                                      (2 / 3, 1 / 3, 2 / 3), (-3 / 7, 6 / 7, 2 / 7))]
+    radii = []
+    for r in (5.0, 7.0, 3.0, 9.0):
+        radii += [r, np.nextafter(r, 0), np.nextafter(r, 100), r - 1e-7, r + 1e-7, r - 3e-6, r + 3e-6, r - 1e-3, r + 1e-3]
+    pts = [np.zeros(3)]
+    for d in dirs:
+        for r in radii:
+            pts.append(d * r)
+    for _ in range(60):
+        v = rng.normal(size=3)
+        pts.append(v / np.linalg.norm(v) * rng.choice([5.0, 7.0, 6.0, 3.0, 9.0]))
+    xyz = np.array(pts) + np.array([shift, -shift / 2, shift / 4])
+    xyz = np.concatenate([[[0.0, 0.0, 0.0]], xyz]) if shift else xyz      # first atom = origin of the FP32 frame
+    n = len(xyz)
+    mol = Molecule.from_arrays(name=["CA"] * n, residue_name=["ALA"] * n, residue_number=np.arange(1, n + 1),
+                               chain_id="A", x=xyz[:, 0], y=xyz[:, 1], z=xyz[:, 2], id="EDGE")
+
+    def tpl(d, tid, extra=()):
+        atoms = [TemplateAtom(chain_id="A", residue_number=1 + k, x=p[0], y=p[1], z=p[2], residue_names=["ALA"],
+                              atom_names=["CA"], distance_weight=0.0, match_mode=0)
+                 for k, p in enumerate([(0.0, 0.0, 0.0), (d, 0.0, 0.0), *extra])]
+        return Template(atoms, id=tid)
+    # 2-atom templates: every decision is one shell test; the oracle drops their (rank-deficient, NaN) hits,
+    # so the engine's tuple count and work counters are compared; the 4-atom template gives real hits
+    templates = [tpl(6.0, "D6"), tpl(4.0, "D4"), tpl(8.0, "D8"),
+                 tpl(6.0, "Q6", extra=[(0.0, 6.0, 0.0), (0.0, 0.0, -6.0)])]
+    for reorder in (0, 1, 2):
+        params = query_params(50.0, 1.0, 10.0, reorder=reorder)
+        table, stats = run_engine(engine, templates, [mol], params)
+        ours, ostats = oracle_lib.query(TemplateTable(templates), MoleculeBatch([mol]), params, threads=2)
+        assert stats["tuples"] == ostats["tuples"] > 200
+        for key in ("frontier_items", "frontier_ints", "candidate_tests"):
+            assert stats[key] == ostats[key], key
+        mine = {k for k in table.keys() if k[1] == 3}
+        assert mine == {k for k in ours.keys() if k[1] == 3} and len(mine) > 0
