@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -130,12 +131,14 @@ struct jb_context {
     DevBuf q_ocnt, q_keyA, q_keyA2, q_keyB, q_keyB2, q_iota, q_perm, q_setpos, q_kdrank, q_coords, q_kdidx, q_cub;
     RunWork *host_work = nullptr;                              // pinned
     std::vector<std::pair<void *, size_t>> pin_pool;           // page-locked result blocks, recycled
+    std::mutex pool_mu;                                        // jb_result_free may run on another thread than a query
     long long hit_cap = 0;
     int hit_stride = 0;
     size_t decay_bytes = (size_t)1 << 30;   // JB_DECAY_BYTES
     int decay_runs = 64;                    // JB_DECAY_RUNS
     int runs_since_decay = 0;     // context_decay: every kDecayRuns calls, buffers far larger than recently needed go back
     long long trim_epoch = 0;     // bumped by jb_context_trim: un-fetched results of earlier runs are gone
+    long long run_epoch = 0;      // bumped by every engine run: the hit buffers hold the records of the LAST run only
     Counters *host_ctr = nullptr; // pinned
     u64 *host_lv = nullptr;       // pinned, JB_DEBUG: (scan_tests, box_pass) after every level
     struct jb_molecules *scratch_mol = nullptr;   // reused by jb_query_host (no per-call cudaMalloc)
@@ -179,6 +182,7 @@ struct jb_result {
     jb_stats stats{};
     bool fetched = false;
     long long trim_epoch = 0;
+    long long run_epoch = 0;
     void *block = nullptr;    // page-locked host block holding the fetched arrays (from ctx->pin_pool)
     size_t block_bytes = 0;
     size_t block_cap = 0;     // records the block is laid out for
@@ -276,8 +280,11 @@ static void context_trim(jb_context *c)
     for (DevBuf *b : context_buffers(c)) b->release();
     for (jb_molecules *m : { c->scratch_mol, c->slice_mol[0], c->slice_mol[1] })
         if (m) for (DevBuf *b : m->all()) b->release();
-    for (auto &blk : c->pin_pool) cudaFreeHost(blk.first);
-    c->pin_pool.clear();
+    {
+        std::lock_guard<std::mutex> g(c->pool_mu);
+        for (auto &blk : c->pin_pool) cudaFreeHost(blk.first);
+        c->pin_pool.clear();
+    }
     c->hit_cap = 0;
     c->hit_stride = 0;
     c->trim_epoch++;                                  // results not fetched yet lived in these buffers
@@ -844,6 +851,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
     CU(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     jb_stats &S = res->stats;
+    if (slice_base == 0) res->run_epoch = ++c->run_epoch;   // first slice of a run: earlier un-fetched results are overwritten
     S.pairs += (int64_t)t->T * mol->M;
     if (t->T == 0 || mol->M == 0 || t->TA == 0) return JB_OK;
 
@@ -1341,17 +1349,20 @@ static int result_alloc_block(jb_result *r, size_t cap)
     const size_t o_mol = 0, o_tpl = o_mol + align64(cap * 4), o_atoms = o_tpl + align64(cap * 4),
                  o_rmsd = o_atoms + align64(cap * stride * 4), o_rot = o_rmsd + align64(cap * 8),
                  o_c0 = o_rot + align64(cap * 72), o_c1 = o_c0 + align64(cap * 24), total = o_c1 + align64(cap * 24) + 64;
-    if (r->block) {   // a smaller block from the pipelined path: back to the pool
-        if (c->pin_pool.size() < 4) c->pin_pool.emplace_back(r->block, r->block_bytes);
-        else cudaFreeHost(r->block);
-        r->block = nullptr;
-    }
-    for (size_t i = 0; i < c->pin_pool.size(); i++)
-        if (c->pin_pool[i].second >= total) {
-            r->block = c->pin_pool[i].first; r->block_bytes = c->pin_pool[i].second;
-            c->pin_pool.erase(c->pin_pool.begin() + i);
-            break;
+    {
+        std::lock_guard<std::mutex> g(c->pool_mu);
+        if (r->block) {   // a smaller block from the pipelined path: back to the pool
+            if (c->pin_pool.size() < 4) c->pin_pool.emplace_back(r->block, r->block_bytes);
+            else cudaFreeHost(r->block);
+            r->block = nullptr;
         }
+        for (size_t i = 0; i < c->pin_pool.size(); i++)
+            if (c->pin_pool[i].second >= total) {
+                r->block = c->pin_pool[i].first; r->block_bytes = c->pin_pool[i].second;
+                c->pin_pool.erase(c->pin_pool.begin() + i);
+                break;
+            }
+    }
     if (!r->block) {
         const size_t want = total + total / 4;
         CU(cudaMallocHost(&r->block, want));
@@ -1419,6 +1430,9 @@ extern "C" int jb_result_fetch(jb_result *r, jb_hits *out)
     if (!r->fetched) {
         if (r->trim_epoch != c->trim_epoch)
             return fail(JB_ERR_INVALID, "jb_result_fetch: the hits of this run were discarded by jb_context_trim");
+        if (r->run_epoch != c->run_epoch)
+            return fail(JB_ERR_INVALID, "jb_result_fetch: a later run on this context has overwritten the hits of this one "
+                                        "(fetch a result before the next jb_query_run / jb_query_host)");
         const double t_0 = now_ms();
         const size_t n = (size_t)r->count;
         int rc = result_alloc_block(r, n);
@@ -1447,7 +1461,8 @@ extern "C" int jb_result_stats(jb_result *r, jb_stats *out)
 extern "C" void jb_result_free(jb_result *r)
 {
     if (!r) return;
-    if (r->block) {   // recycled by the next fetch (bounded pool)
+    if (r->block) {   // recycled by the next fetch (bounded pool); may run while another thread queries
+        std::lock_guard<std::mutex> g(r->ctx->pool_mu);
         if (r->ctx->pin_pool.size() < 4) r->ctx->pin_pool.emplace_back(r->block, r->block_bytes);
         else cudaFreeHost(r->block);
     }
