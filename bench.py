@@ -178,21 +178,100 @@ def load_workload(name, scale=1.0, rank=0):
     return synth.workload(name, scale=scale, rank=rank)
 
 
+def workload_config(name, tpl, n_structures, n_atoms, pairs, params, world, scale):
+    """The `config` object of the JSON line; both arms print the same one."""
+    return {"workload": name, "templates": len(tpl), "structures_per_gpu": int(n_structures),
+            "atoms_per_gpu": int(n_atoms), "pairs_per_step": int(pairs), "thresholds": list(params),
+            "sharding": f"structures x{world}, templates replicated",
+            "cache": "L2 flushed (512 MiB write) before every timed step", "scale": scale}
+
+
+# ---- parity of a GPU hit table against the reference library on the same structures ------------
+TOL = 1e-6
+
+
+def _sorted_view(t, rows=None):
+    """(keys, order): keys = [mol, tpl, atoms...] int64 rows sorted lexicographically."""
+    mol = t.molecule if rows is None else t.molecule[rows]
+    tp = t.template if rows is None else t.template[rows]
+    at = t.atoms if rows is None else t.atoms[rows]
+    keys = np.concatenate([mol[:, None].astype(np.int64), tp[:, None].astype(np.int64), at.astype(np.int64)], axis=1)
+    order = np.lexsort(keys.T[::-1]) if len(keys) else np.zeros(0, dtype=np.int64)
+    return keys[order], order if rows is None else rows[order]
+
+
+def parity_report(gpu, cpu, rmsd_threshold, templates, mols, gpu_rows=None):
+    """Hit key sets bit-exact; RMSD, rotation and centroids within 1e-6 -- against the UNMODIFIED
+    reference C library.  Listed separately, as north_star allows: hits within 1e-6 of the RMSD
+    threshold, and ill-conditioned superpositions (|dR| <= 1e-6 + 1e-14 cond)."""
+    kg, og = _sorted_view(gpu, gpu_rows)
+    kc, oc = _sorted_view(cpu)
+    out = {"against": "unmodified reference C library (oracle/_ref)", "hits_gpu": int(len(kg)), "hits_reference": int(len(kc)),
+           "tolerance": TOL}
+    edge = int((np.abs(gpu.rmsd[og] - rmsd_threshold) <= TOL).sum() + (np.abs(cpu.rmsd[oc] - rmsd_threshold) <= TOL).sum())
+    out["threshold_edge"] = edge
+    if kg.shape != kc.shape or not np.array_equal(kg, kc):
+        sg, sc = {tuple(r) for r in kg.tolist()}, {tuple(r) for r in kc.tolist()}
+        out.update(keys="MISMATCH", only_gpu=len(sg - sc), only_reference=len(sc - sg))
+        return out
+    out["keys"] = "identical"
+    d_rmsd = np.abs(gpu.rmsd[og] - cpu.rmsd[oc])
+    d_rot = np.abs(gpu.rotation[og] - cpu.rotation[oc]).reshape(len(og), -1).max(axis=1) if len(og) else np.zeros(0)
+    d_cen = max(float(np.abs(gpu.centre0[og] - cpu.centre0[oc]).max(initial=0.0)),
+                float(np.abs(gpu.centre1[og] - cpu.centre1[oc]).max(initial=0.0)))
+    ill, worst = 0, 0.0
+    for i in np.nonzero(d_rot > TOL)[0].tolist():
+        g = int(og[i])
+        tpl = templates[int(gpu.template[g])]
+        n = len(tpl)
+        x = mols[int(gpu.molecule[g])]._atoms["x"][gpu.atoms[g, :n]]
+        y = np.array([a._pos for a in tpl], dtype=np.float64)
+        sv = np.linalg.svd((x - x.mean(0)).T @ (y - y.mean(0)), compute_uv=False)
+        cond = float((sv[0] / max(sv[-1], 1e-300)) ** 2)
+        if d_rot[i] <= TOL + 1e-14 * cond:
+            ill += 1
+        else:
+            worst = max(worst, float(d_rot[i]))
+    out.update(max_abs_rmsd_diff=float(d_rmsd.max(initial=0.0)), max_abs_centroid_diff=d_cen,
+               max_abs_rotation_diff_well_conditioned=float(d_rot[d_rot <= TOL].max(initial=0.0)),
+               ill_conditioned=ill, rotation_out_of_tolerance=int((d_rot > TOL).sum()) - ill)
+    ok = out["rotation_out_of_tolerance"] == 0 and out["max_abs_rmsd_diff"] <= TOL and d_cen <= TOL
+    out["values"] = "within tolerance" if ok else f"OUT OF TOLERANCE (worst rotation diff {worst:.3g})"
+    return out
+
+
+def reference_fn():
+    import oracle
+    kind = "reference" if oracle.ref_available() else "port"
+    return kind, (oracle.ref_query if kind == "reference" else oracle.query)
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own C implementation (oracle/_ref, built from
-    the unmodified sources) on all host cores, on a bounded sample of the workload."""
+    """--impl reference: the reference's own C implementation (oracle/_ref, built from the
+    unmodified sources) on all host cores, on this arm's config.  Each step is the whole
+    workload when the run fits the time budget, else a stated share of its structures.  Inputs
+    are packed with numpy: this process never maps the product's engine library."""
     if rank != 0:
         return
     import oracle
-    from pyjess_b200 import synth
-    from pyjess_b200._tables import MoleculeBatch, TemplateTable, query_params
-    tpl, mols, params, kw = load_workload(args.workload)
-    sample = mols[:args.cpu_structures]
-    tt, mb = TemplateTable(tpl), MoleculeBatch(sample)
+    from pyjess_b200._tables import TemplateTable, query_params
+    tpl, mols, params, kw = load_workload(args.workload, scale=args.scale)
+    n_atoms = sum(len(m) for m in mols)
+    config = workload_config(args.workload, tpl, len(mols), n_atoms, len(tpl) * len(mols) * world, params, world, args.scale)
+    tt = TemplateTable(tpl)
     qp = query_params(*params, **kw)
     cores = host_cores()
-    kind = "reference" if oracle.ref_available() else "port"
-    fn = oracle.ref_query if kind == "reference" else oracle.query
+    kind, fn = reference_fn()
+    # one probe step sizes the sample: (steps + warmup) steps must fit the budget
+    probe = mols[:max(1, min(len(mols), args.cpu_structures or len(mols)) // 8)]
+    t0 = time.perf_counter()
+    fn(tt, oracle.numpy_batch(probe), qp, threads=cores)
+    per_structure = (time.perf_counter() - t0) / len(probe)
+    budget = args.reference_budget_s / max(1, args.steps + args.warmup)
+    want = world * len(mols) if args.cpu_structures <= 0 else args.cpu_structures
+    n = int(max(1, min(want, len(mols), budget / max(per_structure, 1e-9))))
+    sample = mols[:n]
+    mb = oracle.numpy_batch(sample)
     for _ in range(args.warmup):
         fn(tt, mb, qp, threads=cores)
     times = []
@@ -204,17 +283,208 @@ def run_reference(args, rank, world):
     pairs = len(tpl) * len(sample)
     sec = float(np.mean(times))
     value = pairs / sec
-    desc = f"{len(tpl)} templates x first {len(sample)} structures of {args.workload} per step, query loops only"
+    whole = n == len(mols) and world == 1
+    desc = (f"{len(tpl)} templates x {'all' if whole else 'the first'} {len(sample)} structures of {args.workload} "
+            f"per step ({pairs} pairs), query loops only" + ("" if whole else
+            f"; bounded by --reference-budget-s {args.reference_budget_s:.0f} over {args.steps}+{args.warmup} steps"))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "templates": len(tpl), "structures": len(sample),
-                   "thresholds": list(params)},
+        "config": config,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "hits_per_step": int(hits.count),
+        "hits_per_step": int(hits.count), "sample_structures": len(sample), "whole_workload_per_step": whole,
+        "engine_library_mapped": any("libjess_b200" in line for line in open("/proc/self/maps")),
     }))
+
+
+def gpu_present() -> bool:
+    """Asked of NVML / the device nodes, not of CUDA: the synthetic generators fork worker processes
+    and must run before this process initialises CUDA."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        return pynvml.nvmlDeviceGetCount() > 0
+    except Exception:
+        return os.path.exists("/dev/nvidiactl") or os.path.exists("/dev/nvidia0")
+
+
+def events(torch, n):
+    return [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+
+
+def run_cfg4_strong(args, env, tpl, tt, dev_tpl, qp_params, pre):
+    """BASELINE config 4, STRONG scaling: ONE fixed set of structures (300-1,500 residues) x the
+    1,000 templates, dealt to the ranks by `sharding.partition` (LPT).  The deal works on the
+    set's generation groups (64 structures of similar length with their own RNG stream) weighed by
+    residue count, so that every rank can generate exactly its share -- the stand-in for "every
+    rank loads its own files".  Each step: every rank runs its shard through the C ABI from host
+    buffers, the hit tables meet on rank 0 in shared memory (`sharding.HitExchange`) and rank 0
+    builds the per-structure index of the merged result (`ShardedHits`) -- all inside the timed
+    region.  Time = max over ranks."""
+    torch, dist, ctx, stream, rank, world = env["torch"], env["dist"], env["ctx"], env["stream"], env["rank"], env["world"]
+    from pyjess_b200 import _capi, sharding
+    from pyjess_b200._tables import MoleculeBatch, query_params
+    params, kw = qp_params
+    qp = query_params(*params, **kw)
+    ids, mols, shards, total_structures = pre["ids"], pre["mols"], pre["shards"], pre["total"]
+    flush = env["flush"]
+    batch = MoleculeBatch(mols, pinned=True)
+    steps = args.config_steps
+    barrier = env["barrier"]
+    # resident arm
+    dev_mol = _capi.DeviceMolecules(ctx, batch)
+    for _ in range(2):
+        res = _capi.query_run(ctx, dev_tpl, dev_mol, qp)
+        stats = res.stats()
+        res.close()
+    barrier()
+    ev = events(torch, steps)
+    for e0, e1 in ev:
+        flush.zero_()
+        e0.record(stream)
+        res = _capi.query_run(ctx, dev_tpl, dev_mol, qp)
+        e1.record(stream)
+        stats = res.stats()
+        res.close()
+    barrier()
+    resident_ms = float(np.sum([a.elapsed_time(b) for a, b in ev]))
+    dev_mol.close()
+    # end-to-end arm with the hit exchange
+    exchange = sharding.HitExchange(rank, world) if world > 1 else None
+    stride = tt.max_atoms
+
+    def step():
+        table, _ = _capi.query_host(ctx, dev_tpl, batch, qp)
+        t_own = time.perf_counter()
+        tables = exchange.gather(table, stride) if exchange else [table]
+        merged = sharding.ShardedHits(tables, shards) if rank == 0 else None
+        return table, merged, t_own
+
+    own_s, merged, table = 0.0, None, None
+    for _ in range(3):                                  # like the timed loop: the previous step's table is still alive while
+        table, merged, _ = step()                       # the next one runs (two page-locked result blocks alternate)
+    barrier()
+    ev = events(torch, steps)
+    own_s = 0.0
+    for e0, e1 in ev:
+        flush.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        table, merged, t_own = step()
+        e1.record(stream)
+        own_s += t_own - t0
+    barrier()
+    e2e_ms = float(np.sum([a.elapsed_time(b) for a, b in ev]))
+    red = torch.tensor([resident_ms, e2e_ms, own_s * 1e3], dtype=torch.float64, device="cuda")
+    lo = torch.tensor([own_s * 1e3], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(len(mols)), float(batch.n_atoms), float(stats["hits"]), float(batch.nbytes),
+                        float(stats["expand_ms"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    out = None
+    if rank == 0:
+        pairs = len(tpl) * total_structures
+        out = {
+            "workload": "cfg4 (strong scaling)", "scaling": "strong", "templates": len(tpl),
+            "structures": int(total_structures), "of_config_4": f"{total_structures} of the 50,000 structures "
+            "(seed 20000, 300-1,500 residues): the share that keeps the default run within minutes",
+            "atoms": int(tot[1]), "pairs_per_step": int(pairs), "thresholds": list(params), "steps": steps, "n_gpus": world,
+            "partition": "sharding.partition (LPT) over generation groups of 64 structures weighed by residue count",
+            "value": pairs * steps / (float(red[0]) / 1e3), "ms_per_step": float(red[0]) / steps,
+            "e2e": {"value": pairs * steps / (float(red[1]) / 1e3), "unit": UNIT, "ms_per_step": float(red[1]) / steps,
+                    "h2d_bytes_per_step": int(tot[3]), "d2h_bytes_per_step": int(tot[2]) * (8 + 4 * stride + 128),
+                    "includes": "per-rank jb_query_host from pinned host buffers + hit tables gathered on rank 0 "
+                                "(shared memory) + per-structure index of the merged result"},
+            "e2e_step_ms_rank0": [float(a.elapsed_time(b)) for a, b in ev],
+            "rank_ms_per_step": {"max": float(red[2]) / steps, "min": float(lo[0]) / steps,
+                                 "imbalance_max_over_min": float(red[2]) / max(float(lo[0]), 1e-9)},
+            "hits_per_step": int(merged.count), "hits_sum_over_ranks": int(tot[2]),
+            "merged_hit_set_checksum": f"{merged.checksum():016x}",
+            "merged_hit_set": "order-independent digest of {(structure id, template, atom tuple)}: equal across "
+                              "--gpus 1/2/4/8 = identical merged hit sets",
+        }
+        if not args.no_cpu_baseline:
+            import oracle
+            kind, fn = reference_fn()
+            n = min(args.cfg4_cpu_structures, len(mols))
+            sample = mols[:n]
+            t0 = time.perf_counter()
+            cpu_hits, cst = fn(tt, oracle.numpy_batch(sample), qp, threads=host_cores())
+            sec = cst["kernel_ms"] / 1e3 if kind == "reference" else time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": len(tpl) * n / sec, "unit": UNIT, "cores": host_cores(), "kind": kind,
+                                   "sample": f"{len(tpl)} templates x the first {n} structures of rank 0's shard, {sec:.2f} s"}
+            rows = np.nonzero(table.molecule < n)[0]
+            out["parity_on_sample"] = parity_report(table, cpu_hits, params[0], tpl, sample, rows)
+    if exchange:
+        exchange.close()
+    return out
+
+
+def run_single_gpu_config(args, env, name, cpu_structures):
+    """A further BASELINE config on rank 0's GPU (N=1 line only): resident + end-to-end + parity."""
+    torch, ctx, stream, flush = env["torch"], env["ctx"], env["stream"], env["flush"]
+    from pyjess_b200 import _capi
+    from pyjess_b200._tables import MoleculeBatch, TemplateTable, query_params
+    tpl, mols, params, kw = env["pre"][name]
+    qp = query_params(*params, **kw)
+    tt = TemplateTable(tpl)
+    dev_tpl = _capi.DeviceTemplates(ctx, tt)
+    batch = MoleculeBatch(mols, pinned=True)
+    dev_mol = _capi.DeviceMolecules(ctx, batch)
+    steps = args.config_steps
+    for _ in range(2):
+        res = _capi.query_run(ctx, dev_tpl, dev_mol, qp)
+        res.close()
+    torch.cuda.synchronize()
+    ev = events(torch, steps)
+    for e0, e1 in ev:
+        flush.zero_()
+        e0.record(stream)
+        res = _capi.query_run(ctx, dev_tpl, dev_mol, qp)
+        e1.record(stream)
+        stats = res.stats()
+        res.close()
+    torch.cuda.synchronize()
+    resident_ms = float(np.sum([a.elapsed_time(b) for a, b in ev]))
+    dev_mol.close()
+    for _ in range(2):
+        table, _ = _capi.query_host(ctx, dev_tpl, batch, qp)
+    torch.cuda.synchronize()
+    ev = events(torch, steps)
+    for e0, e1 in ev:
+        flush.zero_()
+        e0.record(stream)
+        table, _ = _capi.query_host(ctx, dev_tpl, batch, qp)
+        e1.record(stream)
+    torch.cuda.synchronize()
+    e2e_ms = float(np.sum([a.elapsed_time(b) for a, b in ev]))
+    pairs = len(tpl) * len(mols)
+    out = {"workload": name, "templates": len(tpl), "structures": len(mols), "atoms": int(batch.n_atoms),
+           "pairs_per_step": pairs, "thresholds": list(params), "kwargs": {k: str(v) for k, v in kw.items()}, "steps": steps,
+           "n_gpus": 1, "value": pairs * steps / (resident_ms / 1e3), "ms_per_step": resident_ms / steps,
+           "e2e": {"value": pairs * steps / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms / steps,
+                   "h2d_bytes_per_step": int(batch.nbytes),
+                   "d2h_bytes_per_step": int(table.count) * (8 + 4 * table.stride + 128)},
+           "hits_per_step": int(table.count),
+           "stage_ms": {k: stats[k] for k in ("kernel_ms", "classify_ms", "pairs_ms", "expand_ms", "superpose_ms")}}
+    if not args.no_cpu_baseline:
+        import oracle
+        kind, fn = reference_fn()
+        n = min(cpu_structures, len(mols))
+        sample = mols[:n]
+        t0 = time.perf_counter()
+        cpu_hits, cst = fn(tt, oracle.numpy_batch(sample), qp, threads=host_cores())
+        sec = cst["kernel_ms"] / 1e3 if kind == "reference" else time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": len(tpl) * n / sec, "unit": UNIT, "cores": host_cores(), "kind": kind,
+                               "sample": f"{len(tpl)} templates x the first {n} structures, {sec:.2f} s"}
+        out["parity_on_sample"] = parity_report(table, cpu_hits, params[0], tpl, sample, np.nonzero(table.molecule < n)[0])
+    dev_tpl.close()
+    return out
 
 
 def main():
@@ -226,14 +496,18 @@ def main():
     ap.add_argument("--workload", default="cfg3")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; invalid as a result)")
     ap.add_argument("--cpu-structures", type=int, default=0,
-                    help="structures in the bounded CPU-baseline sample (0: per-workload default, ~10-20 s of "
-                         "host time at N=1; a third of it per step of --impl reference)")
+                    help="structures in the CPU-baseline sample (0: the whole workload when it fits the time budget)")
+    ap.add_argument("--reference-budget-s", type=float, default=240.0,
+                    help="--impl reference: host seconds the (steps + warmup) steps may take in total")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--configs", default="auto",
+                    help="further BASELINE configs reported in the line's `configs` object: comma list of cfg4,cfg5, "
+                         "`none`, or `auto` (cfg4 strong-scaled over the ranks + cfg5 at N=1 when --workload is cfg3)")
+    ap.add_argument("--cfg4-structures", type=int, default=6250, help="size of the fixed cfg 4 set that is strong-scaled")
+    ap.add_argument("--cfg4-cpu-structures", type=int, default=150)
+    ap.add_argument("--config-steps", type=int, default=3)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    if args.cpu_structures <= 0:
-        full = {"cfg2": 132, "cfg3": 1000, "cfg3dense": 1000, "cfg4shard": 300, "cfg5": 60}.get(args.workload, 100)
-        args.cpu_structures = full if args.impl == "b200" else max(1, full // 3)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -242,18 +516,38 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    if args.cpu_structures <= 0:
+        args.cpu_structures = {"cfg2": 132, "cfg3": 1000, "cfg3dense": 1000, "cfg4shard": 300, "cfg5": 60}.get(args.workload, 100)
+    if args.configs == "auto":
+        extra = ["cfg4", "cfg5"] if (args.workload == "cfg3" and args.scale == 1.0) else []
+    else:
+        extra = [c for c in args.configs.split(",") if c and c != "none"]
 
+    if not gpu_present():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
     import torch
     import torch.distributed as dist
     from pyjess_b200 import _build
     _build.build()                         # no-op unless the (git-ignored) library is missing or stale; lock-protected
-    from pyjess_b200 import _capi, synth
+    from pyjess_b200 import _capi, sharding, synth
     from pyjess_b200._tables import MoleculeBatch, TemplateTable, query_params
 
     # ---- inputs (synthetic, seeded; structures differ per rank, templates replicated);
     # generated before CUDA is initialised: the cfg 4 generator forks worker processes
     tpl, mols, params, kw = load_workload(args.workload, scale=args.scale, rank=rank)
     qp = query_params(*params, **kw)
+    pre = {}
+    if "cfg4" in extra:
+        groups = synth.protein_groups(args.cfg4_structures, (300, 1500), seed=20000)
+        deal = sharding.partition([int(g[2].sum()) for g in groups], world)
+        shards = [np.sort(np.concatenate([groups[int(g)][1] for g in d])) if len(d) else np.zeros(0, np.int64) for d in deal]
+        ids, gm = synth.proteins_of_groups([groups[int(g)] for g in deal[rank]])
+        order = np.argsort(ids)
+        pre["cfg4"] = {"ids": ids[order], "mols": [gm[int(i)] for i in order], "shards": shards,
+                       "total": args.cfg4_structures}
+        assert np.array_equal(pre["cfg4"]["ids"], shards[rank])
+    if "cfg5" in extra and rank == 0:
+        pre["cfg5"] = load_workload("cfg5")
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
@@ -263,6 +557,8 @@ def main():
     stream = torch.cuda.Stream()           # the engine's stream; torch events are recorded on it
     torch.cuda.set_stream(stream)
     ctx = _capi.Context(local, stream=stream.cuda_stream)
+    _capi._default[local] = ctx            # the drop-in API (Jess.query_many) of this process runs on the same context
+    os.environ["JB_DEVICE"] = str(local)
     tt = TemplateTable(tpl)
     dev_tpl = _capi.DeviceTemplates(ctx, tt)
     batch = MoleculeBatch(mols, pinned=True)
@@ -284,7 +580,7 @@ def main():
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    evs = events(torch, args.steps)
     expand_ms, launches = [], 0
     t_wall = time.perf_counter()
     for e0, e1 in evs:
@@ -306,7 +602,7 @@ def main():
     for _ in range(2):
         table, _ = _capi.query_host(ctx, dev_tpl, batch, qp)
     barrier()
-    ee = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ee = events(torch, args.steps)
     d2h = 0
     for e0, e1 in ee:
         flush.zero_()
@@ -317,8 +613,32 @@ def main():
     barrier()
     e2e_ms = float(np.sum([a.elapsed_time(b) for a, b in ee]))
 
+    # ---- end-to-end through the drop-in Python API: Molecule objects -> host hit table -----------
+    # Jess.query_many packs the structures (inside the timed region), runs the engine and hands back the
+    # per-structure views of the hit table; forcing the first hit_table() runs the whole batch.
+    from pyjess_b200 import Jess
+    jess = Jess(tpl)
+    api_ms = {}
+    for order in ("canonical", "reference"):
+        for _ in range(2):
+            jess.query_many(mols, *params, hit_order=order, **kw)[0].hit_table()
+        barrier()
+        ea = events(torch, args.steps)
+        n_api = 0
+        for e0, e1 in ea:
+            flush.zero_()
+            e0.record(stream)
+            queries = jess.query_many(mols, *params, hit_order=order, **kw)
+            queries[0].hit_table()
+            e1.record(stream)
+            n_api = int(queries[0].stats["hits"])
+        barrier()
+        api_ms[order] = float(np.sum([a.elapsed_time(b) for a, b in ea]))
+        assert n_api == int(table.count), (n_api, table.count)
+        del queries
+
     # ---- reduce over ranks: MAX time, SUM pairs -----------------------------------------
-    red = torch.tensor([step_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    red = torch.tensor([step_ms, e2e_ms, api_ms["canonical"], api_ms["reference"]], dtype=torch.float64, device="cuda")
     tot = torch.tensor([float(pairs_rank), float(stats["hits"])], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
@@ -326,6 +646,7 @@ def main():
     step_ms, e2e_ms = float(red[0]), float(red[1])
     pairs_all, hits_all = float(tot[0]), int(tot[1])
 
+    out = None
     if rank == 0:
         value = pairs_all * args.steps / (step_ms / 1e3)
         e2e = pairs_all * args.steps / (e2e_ms / 1e3)
@@ -338,15 +659,21 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "templates": len(tpl), "structures_per_gpu": len(mols),
-                       "atoms_per_gpu": int(batch.n_atoms), "pairs_per_step": int(pairs_all),
-                       "thresholds": list(params), "sharding": f"structures x{world}, templates replicated",
-                       "cache": "L2 flushed (512 MiB write) before every timed step", "scale": args.scale},
+            "config": workload_config(args.workload, tpl, len(mols), batch.n_atoms, pairs_all, params, world, args.scale),
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": int(batch.nbytes), "d2h_bytes_per_step": int(d2h)},
+            "e2e_api": {"value": pairs_all * args.steps / (float(red[2]) / 1e3), "unit": UNIT,
+                        "ms_per_step": float(red[2]) / args.steps, "vs_e2e": float(red[2]) / e2e_ms,
+                        "call": "Jess(templates).query_many(molecules, 2.0, 1.5, 1.5, hit_order='canonical')[0].hit_table()",
+                        "includes": "packing the Molecule objects into page-locked staging (overlapped slice by slice "
+                                    "with the engine), upload, kernels, hit download, per-structure views",
+                        "reference_hit_order": {"value": pairs_all * args.steps / (float(red[3]) / 1e3),
+                                                "ms_per_step": float(red[3]) / args.steps,
+                                                "note": "default hit_order='reference': records of a template in the "
+                                                        "order the reference's scanner yields them"}},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_expand (frontier sweep: one launch per level, summed over a step)",
+            "roofline": {"bound": "hbm", "kernel": "k_expand_grid (frontier sweep: one launch per level, summed over a step)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": measured_traffic(args.workload),
                          "algorithmic_bytes_per_step": alg_bytes,
@@ -366,24 +693,33 @@ def main():
             import oracle
             cores = host_cores()
             sample = mols[:max(1, int(args.cpu_structures * args.scale))]
-            mb = MoleculeBatch(sample)
-            kind = "reference" if oracle.ref_available() else "port"
-            fn = oracle.ref_query if kind == "reference" else oracle.query
+            kind, fn = reference_fn()
             t0 = time.perf_counter()
-            cpu_hits, cst = fn(tt, mb, qp, threads=cores)
+            cpu_hits, cst = fn(tt, oracle.numpy_batch(sample), qp, threads=cores)
             wall = time.perf_counter() - t0
             sec = cst["kernel_ms"] / 1e3 if kind == "reference" else wall
             out["cpu_baseline"] = {
                 "value": len(tpl) * len(sample) / sec, "unit": UNIT, "cores": cores, "kind": kind,
                 "sample": f"{len(tpl)} templates x first {len(sample)} structures of rank 0 "
                           f"({len(tpl) * len(sample)} pairs), query loops only, {sec:.2f} s"}
-            # parity of the timed GPU result on that same sample (not timed)
-            keep = table.molecule < len(sample)
-            gpu_keys = sorted(zip(table.molecule[keep].tolist(), table.template[keep].tolist(),
-                                  map(tuple, table.atoms[keep].tolist())))
-            cpu_keys = sorted(zip(cpu_hits.molecule.tolist(), cpu_hits.template.tolist(),
-                                  map(tuple, cpu_hits.atoms.tolist())))
-            out["parity_on_sample"] = "identical hit set" if gpu_keys == cpu_keys else "MISMATCH"
+            # parity of the timed GPU result on that same sample (not timed): keys AND values
+            out["parity_on_sample"] = parity_report(table, cpu_hits, params[0], tpl, sample,
+                                                    np.nonzero(table.molecule < len(sample))[0])
+    # ---- further BASELINE configs (same run, same box) --------------------------------------------
+    dev_mol.close()
+    del batch
+    env = {"torch": torch, "dist": dist, "ctx": ctx, "stream": stream, "rank": rank, "world": world, "flush": flush,
+           "barrier": barrier, "pre": pre}
+    configs = {}
+    if "cfg4" in pre:
+        configs_cfg4 = run_cfg4_strong(args, env, tpl, tt, dev_tpl, (params, kw), pre["cfg4"])
+        if rank == 0:
+            configs["cfg4"] = configs_cfg4
+    if "cfg5" in pre and rank == 0:
+        configs["cfg5"] = run_single_gpu_config(args, env, "cfg5", 6)
+    if rank == 0:
+        if configs:
+            out["configs"] = configs
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

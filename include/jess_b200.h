@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define JB_ABI_VERSION 2
+#define JB_ABI_VERSION 3
 /* hard limit of the GPU path; larger templates are rejected loudly */
 #define JB_MAX_TEMPLATE_ATOMS 32
 
@@ -127,8 +127,16 @@ typedef struct jb_query_params {
                                       * superposition (no RMSD filter, NaN
                                       * rotations kept): what JessQuery_next
                                       * yields before Query.__next__ filters   */
-    int32_t reserved;
+    int32_t flags;                   /* JB_QUERY_* bits                       */
 } jb_query_params;
+
+/* jb_query_params.flags */
+#define JB_QUERY_COORDS 1            /* also return, per hit, the coordinates of the matched atoms
+                                      * transformed into the template frame on the device: what
+                                      * Hit.atoms(transform=True) computes atom by atom
+                                      * (src/pyjess/_jess.pyx:2454-2482 with Hit.transformation
+                                      * :2343-2377 and Atom._transform :1293-1307, same operation
+                                      * order) -> jb_hits.coords                                */
 
 /* compacted hits, host memory owned by the jb_result they were fetched from.
  * Order: (molecule, template) ascending, then jb_query_params.hit_order.
@@ -147,6 +155,8 @@ typedef struct jb_hits {
     const double *rotation;          /* [count*9] row major                   */
     const double *centre0;           /* [count*3] centroid of matched atoms   */
     const double *centre1;           /* [count*3] centroid of template atoms  */
+    const double *coords;            /* [count*stride*3] JB_QUERY_COORDS: transformed coordinates of
+                                      * atoms[i*stride + k] (zeros in the padding); NULL otherwise */
 } jb_hits;
 
 /* device-side counters of one query run (define the algorithmic bytes of the
@@ -183,6 +193,11 @@ typedef struct jb_result jb_result;
 int jb_abi_version(void);
 const char *jb_last_error(void);
 int jb_device_count(void);
+
+/* Page-locked ("pinned") host memory for the arrays of a jb_molecule_batch: uploads from it are
+ * asynchronous DMA transfers.  Usable with every context of the process.                      */
+int jb_host_alloc(int64_t bytes, void **out);
+void jb_host_free(void *ptr);
 
 /* One context per GPU.  `stream` is a cudaStream_t (0/NULL = a private
  * non-blocking stream).  `workspace_bytes` bounds the frontier workspace in
@@ -324,6 +339,16 @@ int jb_molecules_pack(const jb_atom_record *const *molecules, const int64_t *cou
                       int32_t n_molecules, int64_t *atom_offset, double *x, double *y,
                       double *z, uint32_t *name, uint32_t *residue_name,
                       int32_t *residue_number, uint8_t *chain_id2, int32_t *serial);
+
+/* End to end from the host layer's atom records (bj_molecules_pack + bj_query_run in one call;
+ * what Jess.query hands to Jess_query, src/pyjess/_jess.pyx:2855-2869, is exactly such an array of struct _Atom
+ * per Molecule).  Large batches run in slices: while the GPU searches slice k, host threads pack slice k+1 into
+ * page-locked staging and the copy engine uploads it, so the packing pass disappears behind the kernels.
+ * Atom.serial is shipped only when params->hit_order needs it.                                           */
+int jb_query_records(jb_context *ctx, const jb_templates *tpl,
+                     const jb_atom_record *const *molecules, const int64_t *counts,
+                     int32_t n_molecules, const jb_query_params *params, jb_result **out,
+                     jb_hits *hits);
 
 /* ---- hit output (HOST code): the per-atom sprintf loop of Hit.dump
  * (src/pyjess/_jess.pyx:2589-2620) for n records at once.  `xyz` (n*3, may be

@@ -54,6 +54,35 @@ def _load(path: str, prefix: str):
     return lib
 
 
+def numpy_batch(molecules, serial: bool = False) -> MoleculeBatch:
+    """SoA image of `molecules` packed with numpy alone: the reference arm of bench.py must not
+    even map the product's engine library, which `MoleculeBatch(...)` packs through."""
+    import numpy as np
+    mols = list(molecules)
+    b = MoleculeBatch.__new__(MoleculeBatch)
+    b._pool, b._keep, b._struct = None, [], None
+    b.molecules, b.n_molecules = mols, len(mols)
+    counts = np.asarray([len(m._atoms) for m in mols], dtype=np.int64)
+    b.atom_offset = np.zeros(len(mols) + 1, dtype=np.int64)
+    np.cumsum(counts, out=b.atom_offset[1:])
+    b.n_atoms = int(b.atom_offset[-1])
+    rec = np.concatenate([m._atoms for m in mols]) if mols and b.n_atoms else np.zeros(1, dtype=mols[0]._atoms.dtype if mols else "V1")
+    if b.n_atoms == 0:
+        z = lambda dt: np.zeros(1, dtype=dt)  # noqa: E731
+        b.x, b.y, b.z, b.name, b.resname, b.resseq, b.chain = (z(np.float64), z(np.float64), z(np.float64), z(np.uint32),
+                                                                z(np.uint32), z(np.int32), z(np.uint8))
+        b.serial = z(np.int32) if serial else None
+        return b
+    xyz = rec["x"]
+    b.x, b.y, b.z = (np.ascontiguousarray(xyz[:, k]) for k in range(3))
+    b.name = np.ascontiguousarray(rec["name"]).view(np.uint32).copy()
+    b.resname = np.ascontiguousarray(rec["resName"]).view(np.uint32).copy()
+    b.resseq = np.ascontiguousarray(rec["resSeq"], dtype=np.int32)
+    b.chain = np.ascontiguousarray(rec["chainID2"], dtype=np.uint8)
+    b.serial = np.ascontiguousarray(rec["serial"], dtype=np.int32) if serial else None
+    return b
+
+
 def ref_available() -> bool:
     return os.path.exists(REF_SO)
 

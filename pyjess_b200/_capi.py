@@ -17,11 +17,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("JB_LIB_PATH") or os.path.join(HERE, "libjess_b200.so")   # JB_LIB_PATH: A/B builds
 
 EXPORTS = [
-    "jb_abi_version", "jb_last_error", "jb_device_count",
+    "jb_abi_version", "jb_last_error", "jb_device_count", "jb_host_alloc", "jb_host_free",
     "jb_context_create", "jb_context_destroy", "jb_context_synchronize", "jb_context_trim",
     "jb_templates_create", "jb_templates_free", "jb_templates_spec_count",
     "jb_molecules_upload", "jb_molecules_free",
-    "jb_query_run", "jb_result_fetch", "jb_result_stats", "jb_result_free", "jb_query_host",
+    "jb_query_run", "jb_result_fetch", "jb_result_stats", "jb_result_free", "jb_query_host", "jb_query_records",
     "jb_pdb_parse", "jb_cif_parse", "jb_format_atoms_pdb", "jb_molecules_pack",
 ]
 
@@ -53,6 +53,8 @@ def load_library():
                 "jb_abi_version": (i32, []),
                 "jb_last_error": (C.c_char_p, []),
                 "jb_device_count": (i32, []),
+                "jb_host_alloc": (i32, [i64, P(vp)]),
+                "jb_host_free": (None, [vp]),
                 "jb_context_create": (i32, [i32, vp, i64, P(vp)]),
                 "jb_context_destroy": (None, [vp]),
                 "jb_context_synchronize": (i32, [vp]),
@@ -67,6 +69,7 @@ def load_library():
                 "jb_result_stats": (i32, [vp, P(jb_stats)]),
                 "jb_result_free": (None, [vp]),
                 "jb_query_host": (i32, [vp, vp, P(jb_molecule_batch), P(jb_query_params), P(vp), P(jb_hits)]),
+                "jb_query_records": (i32, [vp, vp, vp, vp, i32, P(jb_query_params), P(vp), P(jb_hits)]),
                 "jb_pdb_parse": (i32, [C.c_char_p, i64, i32, vp, i64, P(jb_pdb_info)]),
                 "jb_cif_parse": (i32, [C.c_char_p, i64, i32, vp, i64, P(jb_cif_info)]),
                 "jb_format_atoms_pdb": (i64, [vp, i64, vp, vp, i64]),
@@ -130,7 +133,8 @@ class DeviceTemplates:
 
     def close(self):
         if self._h and self.ctx._h:
-            self.ctx.lib.jb_templates_free(self._h)
+            with self.ctx.lock:           # never while another thread runs a query on this context
+                self.ctx.lib.jb_templates_free(self._h)
         self._h = C.c_void_p()
 
     def __del__(self):
@@ -144,11 +148,13 @@ class DeviceMolecules:
     def __init__(self, ctx: Context, batch: MoleculeBatch):
         self.ctx, self.batch = ctx, batch
         self._h = C.c_void_p()
-        _check(ctx.lib.jb_molecules_upload(ctx._h, C.byref(batch.as_struct()), C.byref(self._h)))
+        with ctx.lock:
+            _check(ctx.lib.jb_molecules_upload(ctx._h, C.byref(batch.as_struct()), C.byref(self._h)))
 
     def close(self):
         if self._h and self.ctx._h:
-            self.ctx.lib.jb_molecules_free(self._h)
+            with self.ctx.lock:
+                self.ctx.lib.jb_molecules_free(self._h)
         self._h = C.c_void_p()
 
     def __del__(self):
@@ -174,6 +180,9 @@ class Result:
         return st.as_dict()
 
     def close(self):
+        # No context lock here: a hit table is often garbage-collected in one thread while another thread
+        # queries (README thread-pool recipe), and jb_result_free only touches the pool of page-locked
+        # blocks, which the library guards with its own mutex.
         if self._h and self.ctx._h:       # a result never outlives its context
             self.ctx.lib.jb_result_free(self._h)
         self._h = C.c_void_p()
@@ -202,6 +211,25 @@ def query_host(ctx: Context, templates: DeviceTemplates, batch: MoleculeBatch, p
         _check(ctx.lib.jb_query_host(ctx._h, templates._h, C.byref(batch.as_struct()), C.byref(params), C.byref(h),
                                      C.byref(hits)))
     res = Result(ctx, h)
+    return HitTable(hits, owner=res), res.stats()
+
+
+def query_records(ctx: Context, templates: DeviceTemplates, molecules, params: jb_query_params):
+    """End to end from `Molecule` objects (`jb_query_records`): the engine packs their atom records
+    into page-locked staging slice by slice, overlapped with upload and kernels.
+    Returns (HitTable, stats)."""
+    import numpy as np
+    n = len(molecules)
+    recs = [m._records() for m in molecules]              # (array kept alive, address, count)
+    ptrs = np.fromiter((r[1] for r in recs), dtype=np.uintp, count=n)
+    counts = np.fromiter((r[2] for r in recs), dtype=np.int64, count=n)
+    h = C.c_void_p()
+    hits = jb_hits()
+    with ctx.lock:
+        _check(ctx.lib.jb_query_records(ctx._h, templates._h, C.c_void_p(ptrs.ctypes.data), C.c_void_p(counts.ctypes.data),
+                                        n, C.byref(params), C.byref(h), C.byref(hits)))
+    res = Result(ctx, h)
+    del recs                                              # (kept alive until the call returned)
     return HitTable(hits, owner=res), res.stats()
 
 
@@ -236,18 +264,17 @@ def cif_parse(data: bytes, dtype, skip_hetatm: bool = False, ignore_endmdl: bool
         return info, records[:min(int(info.n_atoms), cap)]
 
 
-_fmt_buf = None
+_fmt_tls = threading.local()
 
 
 def format_atoms_pdb(records, xyz=None) -> str:
     """ATOM lines of a block of atom records (`jb_format_atoms_pdb`): the sprintf loop of
     Hit.dump.  `records`: C-contiguous `ATOM_DTYPE` array; `xyz`: C-contiguous float64 (n, 3)."""
-    global _fmt_buf
     lib = _lib or load_library()
     n = len(records)
-    if _fmt_buf is None or len(_fmt_buf) < 96 * n + 1:
-        _fmt_buf = C.create_string_buffer(max(96 * n + 1, 1 << 14))
-    buf = _fmt_buf
+    buf = getattr(_fmt_tls, "buf", None)  # per thread: ctypes drops the GIL during the call
+    if buf is None or len(buf) < 96 * n + 1:
+        buf = _fmt_tls.buf = C.create_string_buffer(max(96 * n + 1, 1 << 14))
     if not records.flags.c_contiguous:
         records = records.copy()
     xp = None
@@ -261,7 +288,29 @@ def format_atoms_pdb(records, xyz=None) -> str:
     return C.string_at(buf, got).decode("ascii", "replace")
 
 
+class PinnedArray:
+    """numpy view of page-locked host memory from `jb_host_alloc` (freed with the object)."""
+
+    def __init__(self, n: int, dtype):
+        import numpy as np
+        self.lib = load_library()
+        self._p = C.c_void_p()
+        dt = np.dtype(dtype)
+        _check(self.lib.jb_host_alloc(int(n) * dt.itemsize, C.byref(self._p)))
+        raw = (C.c_uint8 * (max(int(n), 1) * dt.itemsize)).from_address(self._p.value)
+        self.array = np.frombuffer(raw, dtype=dt, count=int(n))
+
+    def __del__(self):
+        try:
+            if self._p:
+                self.lib.jb_host_free(self._p)
+                self._p = C.c_void_p()
+        except Exception:
+            pass
+
+
 _default = {}
+_default_lock = threading.Lock()
 
 
 def default_context(device: Optional[int] = None) -> Context:
@@ -270,5 +319,12 @@ def default_context(device: Optional[int] = None) -> Context:
         device = int(os.environ.get("JB_DEVICE", os.environ.get("LOCAL_RANK", "0")))
     ctx = _default.get(device)
     if ctx is None:
-        ctx = _default[device] = Context(device)
+        with _default_lock:
+            ctx = _default.get(device)
+            if ctx is None:
+                ctx = _default[device] = Context(device)
     return ctx
+
+
+def device_count() -> int:
+    return int(load_library().jb_device_count())

@@ -122,11 +122,19 @@ class Hit:
     def evalue(self) -> float:
         return math.exp(self.log_evalue)
 
+    def _transformed(self) -> np.ndarray:
+        """Matched atoms in the template frame: read from the device-computed table when the query
+        asked for it (`coordinates=True`, JB_QUERY_COORDS), else transformed here."""
+        t = self._table
+        if t is not None and getattr(t, "coords", None) is not None:
+            return t.coords[self._row, :len(self._template)]
+        return _transform_points(self._atoms["x"].copy(), np.asarray(self.transformation))
+
     def atoms(self, transform: bool = True) -> List[Atom]:
         recs = self._atoms
         if transform:
             recs = recs.copy()
-            recs["x"] = _transform_points(self._atoms["x"].copy(), np.asarray(self.transformation))
+            recs["x"] = self._transformed()
         return [Atom._view(recs[k:k + 1], owner=self) for k in range(len(recs))]
 
     def molecule(self, transform: bool = False) -> Molecule:
@@ -156,7 +164,7 @@ class Hit:
         file.write(self._template.id)
         file.write(f" Det={self.determinant:4,.1f} log(E)~ {self.log_evalue:4.2f}\n")
         from . import _capi
-        xyz = _transform_points(self._atoms["x"].copy(), np.asarray(self.transformation)) if transform else None
+        xyz = np.ascontiguousarray(self._transformed()) if transform else None
         file.write(_capi.format_atoms_pdb(self._atoms, xyz))          # the per-atom sprintf loop, natively
         file.write("ENDMDL\n")
 
@@ -165,17 +173,6 @@ def _rebuild_hit(state):
     hit = Hit.__new__(Hit)
     hit.__setstate__(state)
     return hit
-
-
-_tls = threading.local()
-
-
-def _staging_pool() -> dict:
-    """Per-thread staging arrays of the host -> device upload (re-used between queries)."""
-    pool = getattr(_tls, "pool", None)
-    if pool is None:
-        pool = _tls.pool = {}
-    return pool
 
 
 def _iteration_rows(molecule: np.ndarray, template: np.ndarray, rows: np.ndarray) -> np.ndarray:
@@ -208,62 +205,218 @@ def _iteration_rows(molecule: np.ndarray, template: np.ndarray, rows: np.ndarray
     return order if rows is None else rows[order]
 
 
+def _best_of_runs(molecule: np.ndarray, template: np.ndarray, rmsd: np.ndarray, rows: np.ndarray) -> np.ndarray:
+    """best_match on the host (`Query.__next__`, _jess.pyx:2238,2275-2283): of every (structure,
+    template) run of `rows` the record with the smallest RMSD, the FIRST of equal ones."""
+    if len(rows) == 0:
+        return rows
+    mol, tpl, r = molecule[rows], template[rows], rmsd[rows]
+    head = np.ones(len(rows), dtype=bool)
+    head[1:] = (mol[1:] != mol[:-1]) | (tpl[1:] != tpl[:-1])
+    start = np.nonzero(head)[0]
+    run = np.cumsum(head) - 1
+    best = np.minimum.reduceat(r, start)
+    pos = np.where(r == best[run], np.arange(len(rows)), len(rows))
+    return rows[np.minimum.reduceat(pos, start)]
+
+
+def _resolve_devices(devices) -> List[int]:
+    """`devices` of `Jess.query_many`: None -> $JB_DEVICES ("all" or "0,1,..") or the process's
+    default device ($JB_DEVICE / $LOCAL_RANK / 0); "all"; an int; a sequence of ints."""
+    import os
+    from . import _capi
+    if devices is None:
+        devices = os.environ.get("JB_DEVICES") or None
+        if devices is None:
+            return [int(os.environ.get("JB_DEVICE", os.environ.get("LOCAL_RANK", "0")))]
+    if isinstance(devices, str):
+        if devices.strip().lower() == "all":
+            return list(range(max(1, _capi.device_count())))
+        devices = [int(d) for d in devices.split(",") if d.strip()]
+    elif isinstance(devices, int):
+        devices = [devices]
+    devices = [int(d) for d in devices]
+    if not devices or len(set(devices)) != len(devices):
+        raise ValueError(f"invalid value for `devices`: {devices!r}")
+    return devices
+
+
 class _BatchRun:
-    """Shared, lazily executed engine call of one `query` / `query_many`."""
+    """Shared, lazily executed engine work of one `query` / `query_many`.
 
-    __slots__ = ("jess", "molecules", "args", "all_tuples", "table", "stats", "_slices", "done")
+    The batch is cut into one shard of structures per device (`sharding.partition`: LPT by atom
+    count).  Every device is driven by its own host thread and engine context
+    (`jb_query_records`: the engine packs the atom records slice by slice while it uploads and
+    searches the previous slice).  Each shard yields its own hit table (page-locked memory of the
+    engine, zero-copy): nothing is merged or copied, a `Query` only remembers which table and
+    which rows belong to its structure -- and puts them into iteration order when it is first read."""
 
-    def __init__(self, jess, molecules, args, all_tuples):
+    __slots__ = ("jess", "molecules", "args", "all_tuples", "devices", "hit_order", "coords", "tables", "stats",
+                 "item_stats", "_slices", "_where", "_lo", "_hi", "_keep", "done", "_lock", "_error")
+
+    def __init__(self, jess, molecules, args, all_tuples, devices=None, hit_order="reference", coords=False):
         self.jess = jess
         self.molecules = molecules
         self.args = args                  # rmsd, distance, max_dynamic, ignore_chain, reorder, best_match
         self.all_tuples = all_tuples      # stream of every tuple (max_candidates replay) instead of hits
-        self.table: Optional[HitTable] = None
+        self.devices = devices
+        self.hit_order = hit_order        # "reference" | "canonical"
+        self.coords = coords              # JB_QUERY_COORDS: matched atoms in the template frame, from the device
+        self.tables: List[HitTable] = []  # one per work item
         self.stats = None
-        self._slices = None
-        self.done = False
+        self.item_stats = []
+        self._slices = None               # per structure: rows of ITS table in iteration order
+        self._where = None                # per structure: index into `tables`
+        self._lo = self._hi = self._keep = None   # per structure: its block of the table (of tables[k][keep[k]])
+        self.done = False                 # set once tables and slices are in place (or the run has failed)
+        self._lock = threading.Lock()     # the Query objects of one batch may be consumed from several threads
+        self._error = None
+
+    # single-table view (one work item): kept for callers and tests that predate sharded runs
+    @property
+    def table(self) -> Optional[HitTable]:
+        return self.tables[0] if self.tables else None
+
+    @table.setter
+    def table(self, value):
+        self.tables = [value]
+        if self._where is None and self._slices is not None:
+            self._where = [0] * len(self._slices)
+
+    def table_of(self, m: int) -> HitTable:
+        return self.tables[self._where[m] if self._where is not None else 0]
 
     def run(self):
-        if self.done:
-            return
-        self.done = True
+        if not self.done:
+            with self._lock:
+                if not self.done:
+                    try:
+                        self._run_locked()
+                    except BaseException as exc:      # every later next() re-raises the real error
+                        self._error = exc
+                        raise
+                    finally:
+                        self.done = True
+                    return
+        if self._error is not None:
+            raise self._error
+
+    def _plan(self):
+        """[(device, ascending input indices of its shard)]."""
+        mols = self.molecules
+        devices = _resolve_devices(self.devices)
+        if len(devices) > 1 and len(mols) >= 2 * len(devices):
+            from .sharding import partition
+            shards = partition([len(m) for m in mols], len(devices))
+        else:
+            devices, shards = devices[:1], [np.arange(len(mols), dtype=np.int64)]
+        return [(dev, idx) for dev, idx in zip(devices, shards) if len(idx)]
+
+    def _run_device(self, dev, idx, params, out):
+        """Worker of one device: its shard through `jb_query_records` (the engine packs the atom
+        records slice by slice while it uploads and searches the previous slice)."""
+        from . import _capi  # raises if the CUDA engine is missing: no fallback
+        ctx = _capi.default_context(dev)
+        dev_tpl = self.jess._device_templates(ctx)
+        mols = self.molecules
+        sub = mols if len(idx) == len(mols) else [mols[int(i)] for i in idx]
+        out.append((idx,) + _capi.query_records(ctx, dev_tpl, sub, params))
+
+    def _run_locked(self):
         jess, mols = self.jess, self.molecules
+        n_mol = len(mols)
         if len(jess) == 0 or not mols or all(len(m) == 0 for m in mols) or jess._table.max_atoms == 0:
             self._slices = [np.zeros(0, dtype=np.int64) for _ in mols]
+            self._where = [0] * n_mol
             return
-        from . import _capi  # raises if the CUDA engine is missing: no fallback
-        ctx = _capi.default_context()
-        dev_tpl = jess._device_templates(ctx)
-        batch = MoleculeBatch(mols, serial=True, pool=_staging_pool())
         rmsd, dist, maxdyn, ignore_chain, reorder, best_match = self.args
-        # the engine searches in its own scan order; the ORDER of the records is the
-        # reference's for the `reorder` flag the caller passed
-        params = query_params(rmsd, dist, maxdyn, ignore_chain, 2, best_match and not self.all_tuples,
-                              hit_order="reference" if reorder else "reference-noreorder",
-                              all_tuples=self.all_tuples)
-        self.table, self.stats = _capi.query_host(ctx, dev_tpl, batch, params)
-        if self.stats["nan_dropped"]:
-            warnings.warn("Jess returned a superposition matrix with NaN values", UserWarning, stacklevel=4)
-        t = self.table
+        single = np.asarray([len(tpl) == 1 for tpl in jess._templates], dtype=bool)
         # single-atom templates: the engine reports every candidate, the reference never the
         # FIRST of its candidate list (Scanner_reuse pre-selects index 0 and Scanner_next
-        # pre-increments, eff:Scanner.c:176-181,212-227) -- in reference order that is the
-        # first record of the (structure, template) run
-        keep = None
-        single = np.asarray([len(tpl) == 1 for tpl in jess._templates], dtype=bool)
-        if single.any() and t.count:
-            first = np.ones(t.count, dtype=bool)
-            first[1:] = (t.molecule[1:] != t.molecule[:-1]) | (t.template[1:] != t.template[:-1])
-            keep = ~(first & single[t.template])
-        # iteration order per structure: template DESCENDING (reverse insertion), engine order within.
-        # The table is sorted by (structure, template): only whole (structure, template) RUNS move.
-        rows = _iteration_rows(t.molecule, t.template, None if keep is None else np.nonzero(keep)[0])
-        bounds = np.searchsorted(t.molecule[rows], np.arange(len(mols) + 1))
-        self._slices = [rows[bounds[m]:bounds[m + 1]] for m in range(len(mols))]
+        # pre-increments, eff:Scanner.c:176-181,212-227) -- in reference order that is the first
+        # record of the (structure, template) run.  best_match must choose AFTER that record is
+        # gone (all single-atom tuples have RMSD 0: the engine would keep exactly the one the
+        # reference never reports), so with such templates the selection moves to the host.
+        host_best = bool(best_match) and not self.all_tuples and bool(single.any())
+        hit_order = self.hit_order
+        if single.any() or self.all_tuples or best_match:
+            hit_order = "reference"          # first-candidate drop, max_candidates and the best_match tie rule need it
+        # the engine searches in its own scan order; the ORDER of the records is the
+        # reference's for the `reorder` flag the caller passed
+        params = query_params(rmsd, dist, maxdyn, ignore_chain, 2,
+                              best_match and not self.all_tuples and not host_best,
+                              hit_order="canonical" if hit_order == "canonical"
+                              else ("reference" if reorder else "reference-noreorder"),
+                              all_tuples=self.all_tuples, coords=self.coords)
+        plan = self._plan()
+        results = [[] for _ in plan]
+        if len(plan) == 1:
+            self._run_device(plan[0][0], plan[0][1], params, results[0])
+        else:
+            errors = []
+
+            def work(i):
+                try:
+                    self._run_device(plan[i][0], plan[i][1], params, results[i])
+                except BaseException as exc:
+                    errors.append(exc)
+
+            threads = [threading.Thread(target=work, args=(i,)) for i in range(len(plan))]
+            for th in threads:
+                th.start()
+            for th in threads:
+                th.join()
+            if errors:
+                raise errors[0]
+        self._slices = [None] * n_mol
+        where = np.zeros(n_mol, dtype=np.int64)
+        self._lo = np.zeros(n_mol, dtype=np.int64)
+        self._hi = np.zeros(n_mol, dtype=np.int64)
+        self._keep = []
+        total: dict = {}
+        for items in results:
+            for idx, t, st in items:
+                k = len(self.tables)
+                self.tables.append(t)
+                self.item_stats.append(st)
+                for key, v in st.items():
+                    total[key] = total.get(key, 0) + v
+                if t.count and len(idx) != n_mol:
+                    t.molecule[:] = idx[t.molecule]            # the table speaks the caller's numbering
+                keep = None
+                if single.any() and t.count:
+                    first = np.ones(t.count, dtype=bool)
+                    first[1:] = (t.molecule[1:] != t.molecule[:-1]) | (t.template[1:] != t.template[:-1])
+                    keep = np.nonzero(~(first & single[t.template]))[0]
+                    if host_best:
+                        keep = _best_of_runs(t.molecule, t.template, t.rmsd, keep)
+                # The table is sorted by (structure, template): the records of a structure are one block of it
+                # (of `keep`, when records were dropped).  Only the block boundaries are computed here -- two
+                # binary searches per structure; a block is put into iteration order when its Query first asks.
+                tm = t.molecule[:t.count] if keep is None else t.molecule[keep]
+                where[idx] = k
+                if len(tm):
+                    self._lo[idx] = np.searchsorted(tm, idx, side="left")
+                    self._hi[idx] = np.searchsorted(tm, idx, side="right")
+                self._keep.append(keep)
+        self._where = where.tolist()
+        self.stats = total
+        if total.get("nan_dropped"):
+            warnings.warn("Jess returned a superposition matrix with NaN values", UserWarning, stacklevel=5)
 
     def indices(self, m: int) -> np.ndarray:
+        """Rows (of `table_of(m)`) holding the hits of structure `m`, in iteration order: templates DESCENDING
+        (reverse insertion, eff:Jess.c:109-117), engine order within a template."""
         self.run()
-        return self._slices[m]
+        rows = self._slices[m]
+        if rows is None:
+            k = self._where[m]
+            t, keep = self.tables[k], self._keep[k]
+            block = np.arange(self._lo[m], self._hi[m], dtype=np.int64)
+            if keep is not None:
+                block = keep[block]
+            rows = self._slices[m] = _iteration_rows(t.molecule, t.template, block)
+        return rows
 
 
 class Query:
@@ -298,6 +451,16 @@ class Query:
     def ignore_chain(self, value):
         if value not in (None, "residues", "atoms"):
             raise ValueError(f"invalid value for `ignore_chain`: {value!r}")
+        # The reference reads the property at every `next()` (_jess.pyx:2215-2221); here the whole
+        # batch is searched by ONE engine run on the first `next()`: a new value reaches the search
+        # until then (single-structure queries), afterwards it cannot be honoured -- say so loudly.
+        run = self._run
+        if value != run.args[3]:
+            with run._lock:
+                if run.done or len(run.molecules) != 1:
+                    raise RuntimeError("ignore_chain cannot be changed once the query has started "
+                                       "(or for one query of a `query_many` batch)")
+                run.args = run.args[:3] + (value,) + run.args[4:]
         self._ignore_chain = value
 
     @property
@@ -309,9 +472,10 @@ class Query:
         if value is not None and value < 0:
             raise ValueError(f"invalid value for `max_candidates` argument: {value!r}")
         if value is not None and not self._run.all_tuples:
-            if self._run.done:
-                raise RuntimeError("max_candidates cannot be enabled once the query has started")
-            self._run.all_tuples = True      # lazily executed: switch the shared run to the tuple stream
+            with self._run._lock:            # a run in flight on another thread finishes first
+                if self._run.done:
+                    raise RuntimeError("max_candidates cannot be enabled once the query has started")
+                self._run.all_tuples = True  # lazily executed: switch the shared run to the tuple stream
         self._max_candidates = value
 
     def __iter__(self):
@@ -333,7 +497,7 @@ class Query:
         best_match, and the max_candidates counter with its quirks (the counter restarts
         on every call because the local `tpl` starts as NULL, :2203,2222; exceeding it
         abandons the rest of the template, JessQuery_nextTemplate eff:Jess.c:197-205)."""
-        t = self._run.table
+        t = self._run.table_of(self._index)
         limit = -1 if self._max_candidates is None else int(self._max_candidates)
         tpl = None
         hit_i, hit_rmsd, hit_tpl = -1, math.inf, None
@@ -376,7 +540,7 @@ class Query:
         return self._make_hit(hit_i)
 
     def _make_hit(self, i: int) -> Hit:
-        t = self._run.table
+        t = self._run.table_of(self._index)
         hit = Hit.__new__(Hit)
         hit.rmsd = float(t.rmsd[i])
         hit._rot = hit._cen = hit._at = None
@@ -389,7 +553,7 @@ class Query:
     def hit_table(self):
         """(HitTable, row indices of this structure) of the underlying batch."""
         rows = self._run.indices(self._index)        # runs the batch on first use: fetch it before the table
-        return self._run.table, rows
+        return self._run.table_of(self._index), rows
 
     @property
     def stats(self):
@@ -411,12 +575,16 @@ class Jess:
         # objects cannot affect it (the reference deep-copies, _jess.pyx:2703-2707)
         self._table = TemplateTable(self._templates)
         self._device = {}
+        self._device_lock = threading.Lock()
 
     def _device_templates(self, ctx):
         from . import _capi
         dev = self._device.get(id(ctx))
         if dev is None:
-            dev = self._device[id(ctx)] = _capi.DeviceTemplates(ctx, self._table)
+            with self._device_lock:      # several device workers / user threads may arrive at once
+                dev = self._device.get(id(ctx))
+                if dev is None:
+                    dev = self._device[id(ctx)] = _capi.DeviceTemplates(ctx, self._table)
         return dev
 
     def __copy__(self):
@@ -472,18 +640,33 @@ class Jess:
 
     def query(self, molecule: Molecule, rmsd_threshold: float, distance_cutoff: float, max_dynamic_distance: float, *,
               max_candidates: Optional[int] = None, ignore_chain=None, best_match: bool = False,
-              reorder: bool = True) -> Query:
+              reorder: bool = True, hit_order: str = "reference", coordinates: bool = False) -> Query:
         """Scan one structure (_jess.pyx:2758-2869).  Lazy: the engine runs on the
-        first ``next()``."""
+        first ``next()``.  `hit_order`, `coordinates`: see `query_many`."""
         return self.query_many([molecule], rmsd_threshold, distance_cutoff, max_dynamic_distance,
                                max_candidates=max_candidates, ignore_chain=ignore_chain, best_match=best_match,
-                               reorder=reorder)[0]
+                               reorder=reorder, hit_order=hit_order, coordinates=coordinates)[0]
 
     def query_many(self, molecules: Sequence[Molecule], rmsd_threshold: float, distance_cutoff: float,
                    max_dynamic_distance: float, *, max_candidates: Optional[int] = None, ignore_chain=None,
-                   best_match: bool = False, reorder: bool = True) -> List[Query]:
-        """Scan a batch of structures with ONE engine call; returns one `Query`
-        per structure, in input order."""
+                   best_match: bool = False, reorder: bool = True, hit_order: str = "reference",
+                   coordinates: bool = False, devices=None) -> List[Query]:
+        """Scan a batch of structures; returns one `Query` per structure, in input order.
+
+        Beyond the reference's arguments (keyword only, defaults = reference behaviour):
+
+        `hit_order`: ``"reference"`` -- the hits of one template come in the order the reference's
+        depth-first scanner yields them (rebuilt on the device); ``"canonical"`` -- ascending atom
+        tuples, which skips that ranking (the reference documents the order under ``reorder=True`` as
+        an implementation detail).  `best_match`, `max_candidates` and single-atom templates always
+        use the reference order, their results depend on it.
+        `coordinates`: also fetch, per hit, the matched atoms transformed into the template frame,
+        computed on the device (`Hit.atoms(transform=True)`, `Hit.dump` and `Query.hit_table()` read
+        them instead of transforming atom by atom).
+        `devices`: GPUs to spread the batch over -- ``None`` ($JB_DEVICES, else the process's default
+        device), ``"all"``, or a list of device indices.  Structures are dealt to the devices by atom
+        count (`sharding.partition`), one host thread and engine context per device; large shards
+        run in slices so that packing overlaps the engine."""
         molecules = list(molecules)
         for m in molecules:
             if not isinstance(m, Molecule):
@@ -493,8 +676,11 @@ class Jess:
             raise ValueError(f"invalid value for `ignore_chain`: {ignore_chain!r}")
         if max_candidates is not None and max_candidates < 0:
             raise ValueError(f"invalid value for `max_candidates` argument: {max_candidates!r}")
+        if hit_order not in ("reference", "canonical"):
+            raise ValueError(f"invalid value for `hit_order`: {hit_order!r}")
         run = _BatchRun(self, molecules,
                         (rmsd_threshold, distance_cutoff, max_dynamic_distance, ignore_chain, bool(reorder),
-                         bool(best_match)), all_tuples=max_candidates is not None)
+                         bool(best_match)), all_tuples=max_candidates is not None, devices=devices,
+                        hit_order=hit_order, coords=bool(coordinates))
         return [Query(self, m, rmsd_threshold, best_match, ignore_chain, max_candidates, run, i)
                 for i, m in enumerate(molecules)]

@@ -467,7 +467,7 @@ class Atom:
 class Molecule:
     """A sequence of atoms (_jess.pyx:446-900), stored as one record array."""
 
-    __slots__ = ("_atoms", "_id", "_date", "_name", "_pack", "__weakref__")
+    __slots__ = ("_atoms", "_id", "_date", "_name", "_pack", "_rec", "__weakref__")
 
     @classmethod
     def load(cls, file, format: str = "detect", *, id=None, date=None, name=None,
@@ -810,6 +810,22 @@ class Molecule:
                 handle.close()
 
     # --- device image ---------------------------------------------------------
+    def _records(self):
+        """(array, address, count) of the atom records as `jb_query_records` reads them (the
+        reference hands Jess_query its `_Atom` array the same way).  The address is cached with
+        the array it belongs to: taking it costs ~2 us, a batch holds thousands of structures."""
+        a = self._atoms
+        try:
+            c = self._rec
+        except AttributeError:
+            c = None
+        if c is None or c[0] is not a:
+            if not a.flags.c_contiguous:
+                b = np.ascontiguousarray(a)
+                return b, b.ctypes.data, len(b)             # a copy: not cached, later edits must be seen
+            c = self._rec = (a, a.ctypes.data, len(a))
+        return c
+
     def _packed(self) -> dict:
         """Structure-of-arrays image of the fields the query path reads
         (jb_molecule_batch, include/jess_b200.h); built once, cached."""

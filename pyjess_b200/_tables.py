@@ -68,7 +68,7 @@ class jb_query_params(C.Structure):
         ("best_match", C.c_int32),
         ("hit_order", C.c_int32),
         ("all_tuples", C.c_int32),
-        ("reserved", C.c_int32),
+        ("flags", C.c_int32),
     ]
 
 
@@ -110,6 +110,7 @@ class jb_hits(C.Structure):
         ("rotation", c_f64p),
         ("centre0", c_f64p),
         ("centre1", c_f64p),
+        ("coords", c_f64p),
     ]
 
 
@@ -213,6 +214,22 @@ class TemplateTable:
         return self._struct
 
 
+class _PlainArray:
+    def __init__(self, n, dtype):
+        self.array = np.zeros(n, dtype=dtype)
+
+
+def _staging_array(n, dtype):
+    """Long-lived staging memory of a thread's pool: page-locked through the engine library
+    (`jb_host_alloc`) so that the upload is one asynchronous DMA; pageable numpy memory where
+    no CUDA device exists (host-logic tests over a stubbed engine -- staging, never compute)."""
+    from . import _capi
+    try:
+        return _capi.PinnedArray(n, dtype)
+    except _capi.EngineError:
+        return _PlainArray(n, dtype)
+
+
 class MoleculeBatch:
     """Structure-of-arrays image of a list of molecules.
 
@@ -259,9 +276,9 @@ class MoleculeBatch:
             key = (len(self._keep), np.dtype(dtype).str)
             self._keep.append(key)
             buf = self._pool.get(key)
-            if buf is None or len(buf) < n:
-                buf = self._pool[key] = np.zeros(max(n, 1 << 16) + n // 4, dtype=dtype)
-            return buf[:n]
+            if buf is None or len(buf.array) < n:
+                buf = self._pool[key] = _staging_array(max(n, 1 << 16) + n // 4, dtype)
+            return buf.array[:n]
         if pinned:
             import torch
             t = torch.empty(n * np.dtype(dtype).itemsize, dtype=torch.uint8, pin_memory=True)
@@ -295,12 +312,14 @@ HIT_ORDER = {"canonical": 0, "reference": 1, "reference-noreorder": 2}
 
 
 def query_params(rmsd_threshold, distance_cutoff, max_dynamic_distance, ignore_chain=None,
-                 reorder=True, best_match=False, hit_order="canonical", all_tuples=False) -> jb_query_params:
+                 reorder=True, best_match=False, hit_order="canonical", all_tuples=False,
+                 coords=False) -> jb_query_params:
     """`reorder`: True -> 2 (the engine's expected-fan-out scan order), False -> 0
     (template order); an int selects the mode explicitly (1 = the reference's argsort
     by |C_k|).  The hit set never depends on it.  `hit_order`: "canonical" (atom tuple
     ascending) or the reference's own iteration order for its reorder=True /
-    reorder=False runs ("reference" / "reference-noreorder", include/jess_b200.h)."""
+    reorder=False runs ("reference" / "reference-noreorder", include/jess_b200.h).  `coords`:
+    also return the matched atoms transformed into the template frame (JB_QUERY_COORDS)."""
     if ignore_chain not in IGNORE_CHAIN:
         raise ValueError(f"invalid value for `ignore_chain`: {ignore_chain!r}")
     if isinstance(reorder, bool):
@@ -309,14 +328,14 @@ def query_params(rmsd_threshold, distance_cutoff, max_dynamic_distance, ignore_c
         raise ValueError(f"invalid value for `hit_order`: {hit_order!r}")
     return jb_query_params(float(rmsd_threshold), float(distance_cutoff), float(max_dynamic_distance),
                            IGNORE_CHAIN[ignore_chain], int(reorder), int(bool(best_match)), HIT_ORDER[hit_order],
-                           int(bool(all_tuples)), 0)
+                           int(bool(all_tuples)), 1 if coords else 0)
 
 
 class HitTable:
     """Host copy of a `jb_hits` record set as numpy arrays (canonical order)."""
 
     __slots__ = ("count", "stride", "molecule", "template", "atoms", "rmsd", "rotation", "centre0", "centre1",
-                 "_owner")
+                 "coords", "_owner")
 
     def __init__(self, hits: jb_hits, owner=None):
         """With `owner` (the object that keeps the C arrays alive, e.g. a `_capi.Result`)
@@ -339,6 +358,8 @@ class HitTable:
         self.rotation = grab(hits.rotation, (n, 3, 3), np.float64)
         self.centre0 = grab(hits.centre0, (n, 3), np.float64)
         self.centre1 = grab(hits.centre1, (n, 3), np.float64)
+        # JB_QUERY_COORDS: matched atoms in the template frame, (n, stride, 3); None when not requested
+        self.coords = grab(hits.coords, (n, stride, 3), np.float64) if hits.coords else None
 
     @classmethod
     def from_arrays(cls, molecule, template, atoms, rmsd, rotation, centre0, centre1) -> "HitTable":
@@ -347,6 +368,7 @@ class HitTable:
         self._owner = None
         self.molecule, self.template, self.atoms, self.rmsd = molecule, template, atoms, rmsd
         self.rotation, self.centre0, self.centre1 = rotation, centre0, centre1
+        self.coords = None
         return self
 
     def arrays(self):

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <map>
 #include <mutex>
 #include <numeric>
@@ -21,9 +22,17 @@
 #include "kernels.cuh"
 #include "expand_lv.cuh"
 #include "expand_grid.cuh"
+#include "expand_dfs.cuh"
 #include "hits.cuh"
 #include "order.cuh"
 #include <cub/device/device_radix_sort.cuh>
+#include <nvtx3/nvToolsExt.h>   // header-only: ranges are no-ops unless a profiler is attached
+
+// NVTX range around one stage of a run (tracing): visible to nsys / ncu --nvtx.
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 using namespace jb;
 
@@ -120,11 +129,13 @@ struct jb_context {
     int debug = 0;                // JB_DEBUG: per-level counts and times on stderr
     int legacy = 0;               // JB_LEGACY: run-time-level k_expand at every level (A/B comparisons)
     int sweep = 1;                // JB_SWEEP: 1 cell-grid sweep (expand_grid.cuh), 0 x-range stream (expand_lv.cuh)
+    long long dfs_pairs = 4096;   // JB_DFS_PAIRS: chunks of at most that many pairs take the one-launch depth-first sweep
     cudaEvent_t lev[kMaxN + 1] = {};
     // workspace (grow only)
     DevBuf crec, chead, cxtab, cbin, cbinlist, recs, ordbuf, fr[2], tuples, ctr;
     DevBuf h_mol, h_tpl, h_atoms, h_rmsd, h_rot, h_c0, h_c1;   // hits as k_superpose appends them
     DevBuf f_mol, f_tpl, f_atoms, f_rmsd, f_rot, f_c0, f_c1;   // ... in canonical order (hits.cuh)
+    DevBuf f_xyz;                                              // JB_QUERY_COORDS: transformed coordinates of the matched atoms
     DevBuf o_off, o_fill, o_grouped, o_order, o_tiles, o_runs, o_work;   // ordering workspace
     DevBuf k_key, k_key2, k_iota, k_runid, k_scan;             // keyed hit ordering (hits.cuh)
     DevBuf h_pair, h_keys;                                     // reference-order mode: pair of each hit, rank vectors
@@ -144,6 +155,7 @@ struct jb_context {
     struct jb_molecules *scratch_mol = nullptr;   // reused by jb_query_host (no per-call cudaMalloc)
     struct jb_molecules *slice_mol[2] = { nullptr, nullptr };   // double-buffered staging of the pipelined jb_query_host
     cudaStream_t copy_stream = nullptr;           // H2D of the next slice / D2H of the previous slice's hits
+    PinBuf host_stage[2];                         // jb_query_records: page-locked SoA image of the slice being packed
     cudaEvent_t ev_up[2] = { nullptr, nullptr };
     int pipeline_slices = 0;                      // JB_PIPELINE: 0 auto, 1 off, n >= 2 forced
     long long last_hits = 0;                      // sizes the pinned result block of the next pipelined call
@@ -160,6 +172,9 @@ struct jb_templates {
     bool order_ok = true;                         // false: an atom lists > 31 distinct residue names
     DevBuf o_spec, o_byres, o_roff, o_res, d_ospec;
     long long n_dist = 0;
+    // the shell radii (k_shells) of the last query: a service asks the same thresholds again and again
+    mutable bool shells_valid = false;
+    mutable double shells_cutoff = 0.0, shells_maxdyn = 0.0;
 };
 
 struct jb_molecules {
@@ -189,6 +204,9 @@ struct jb_result {
     long long kept = 0;       // records after best_match selection
     int32_t *mol = nullptr, *tpl = nullptr, *atoms = nullptr;
     double *rmsd = nullptr, *rot = nullptr, *c0 = nullptr, *c1 = nullptr;
+    int coords = 0;           // JB_QUERY_COORDS: xyz holds count * stride * 3 transformed coordinates
+    double *xyz = nullptr;
+    bool direct = false;      // small result: the ordering kernel wrote the records straight into `block`
 };
 
 static void context_trim(jb_context *c);
@@ -201,6 +219,26 @@ extern "C" int jb_device_count(void)
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
+}
+
+// Page-locked host memory for the staging arrays of jb_molecule_batch (portable across contexts): an upload from
+// it is one asynchronous DMA, from pageable memory the driver stages it through its own bounce buffers.
+extern "C" int jb_host_alloc(int64_t bytes, void **out)
+{
+    if (!out || bytes < 0) return fail(JB_ERR_INVALID, "jb_host_alloc: bad argument");
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(JB_ERR_CUDA, "no CUDA device available; the engine has no CPU fallback");
+    }
+    CU(cudaHostAlloc(out, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocPortable));
+    return JB_OK;
+}
+
+extern "C" void jb_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
 }
 
 extern "C" int jb_context_create(int device, void *stream, int64_t workspace_bytes, jb_context **out)
@@ -244,6 +282,7 @@ extern "C" int jb_context_create(int device, void *stream, int64_t workspace_byt
     if (const char *g = getenv("JB_DEBUG")) c->debug = atoi(g);
     if (const char *g = getenv("JB_LEGACY")) c->legacy = atoi(g);
     if (const char *g = getenv("JB_SWEEP")) c->sweep = atoi(g);
+    if (const char *g = getenv("JB_DFS_PAIRS")) c->dfs_pairs = atoll(g);
     if (const char *g = getenv("JB_PIPELINE")) c->pipeline_slices = atoi(g);
     if (c->debug) for (int i = 0; i <= kMaxN; i++) CU(cudaEventCreate(&c->lev[i]));
     CU(cudaMallocHost(&c->host_ctr, sizeof(Counters)));
@@ -264,7 +303,7 @@ static std::vector<DevBuf *> context_buffers(jb_context *c)
 {
     return { &c->crec, &c->chead, &c->cxtab, &c->cbin, &c->cbinlist, &c->recs, &c->ordbuf, &c->fr[0], &c->fr[1],
              &c->tuples, &c->h_mol, &c->h_tpl, &c->h_atoms, &c->h_rmsd, &c->h_rot, &c->h_c0,
-             &c->h_c1, &c->f_mol, &c->f_tpl, &c->f_atoms, &c->f_rmsd, &c->f_rot, &c->f_c0, &c->f_c1,
+             &c->h_c1, &c->f_mol, &c->f_tpl, &c->f_atoms, &c->f_rmsd, &c->f_rot, &c->f_c0, &c->f_c1, &c->f_xyz,
              &c->o_off, &c->o_fill, &c->o_grouped, &c->o_order, &c->o_tiles, &c->o_runs,
              &c->k_key, &c->k_key2, &c->k_iota, &c->k_runid, &c->k_scan, &c->h_pair, &c->h_keys, &c->q_ocnt, &c->q_keyA,
              &c->q_keyA2, &c->q_keyB, &c->q_keyB2, &c->q_iota, &c->q_perm, &c->q_setpos, &c->q_kdrank, &c->q_coords,
@@ -280,6 +319,7 @@ static void context_trim(jb_context *c)
     for (DevBuf *b : context_buffers(c)) b->release();
     for (jb_molecules *m : { c->scratch_mol, c->slice_mol[0], c->slice_mol[1] })
         if (m) for (DevBuf *b : m->all()) b->release();
+    for (PinBuf &b : c->host_stage) b.release();
     {
         std::lock_guard<std::mutex> g(c->pool_mu);
         for (auto &blk : c->pin_pool) cudaFreeHost(blk.first);
@@ -354,6 +394,7 @@ extern "C" void jb_context_destroy(jb_context *c)
         cudaStreamDestroy(c->copy_stream);
         for (int i = 0; i < 2; i++) if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]);
     }
+    for (PinBuf &b : c->host_stage) b.release();
     if (c->host_ctr) cudaFreeHost(c->host_ctr);
     if (c->host_work) cudaFreeHost(c->host_work);
     if (c->host_lv) cudaFreeHost(c->host_lv);
@@ -560,7 +601,11 @@ static int prepare_molecules(jb_context *c, jb_molecules *m, cudaStream_t st)
     (void)c;
     const int M = m->M;
     cudaError_t e = m->atoms.ensure(std::max<size_t>((size_t)m->NA, 1) * sizeof(AtomRec), st);
-    if (e == cudaSuccess && m->NA > 0) {
+    long long amax_all = 0;
+    for (int i = 0; i < M; i++) amax_all = std::max(amax_all, m->atom_off[i + 1] - m->atom_off[i]);
+    // small batches: the sort kernel builds the 32-byte records of its structure itself (one launch less)
+    const bool fused_pack = M > 0 && M <= 64 && amax_all <= 16384;
+    if (e == cudaSuccess && m->NA > 0 && !fused_pack) {
         k_pack_atoms<<<(unsigned)((m->NA + 255) / 256), 256, 0, st>>>(m->NA, m->x.as<double>(), m->y.as<double>(),
                                                                      m->z.as<double>(), m->resseq.as<int>(),
                                                                      m->chain.as<unsigned char>(), m->atoms.as<AtomRec>());
@@ -606,11 +651,14 @@ static int prepare_molecules(jb_context *c, jb_molecules *m, cudaStream_t st)
         if (e == cudaSuccess && smem > 48 * 1024)
             e = cudaFuncSetAttribute(k_sort_atoms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) {
+            RawAtoms raw{ nullptr, nullptr, nullptr, nullptr, nullptr };
+            if (fused_pack) raw = RawAtoms{ m->x.as<double>(), m->y.as<double>(), m->z.as<double>(), m->resseq.as<int>(),
+                                            m->chain.as<unsigned char>() };
             k_sort_atoms<<<M, kSortThreads, smem, st>>>(m->d_off.as<long long>(), m->atoms.as<AtomRec>(),
                                                         m->name.as<uint32_t>(), m->res.as<uint32_t>(),
                                                         m->ext.as<MolExt>(), m->srec.as<float4>(),
                                                         m->sname.as<uint32_t>(), m->sres.as<uint32_t>(),
-                                                        m->sort_scratch.as<u64>(), smem_keys);
+                                                        m->sort_scratch.as<u64>(), smem_keys, raw);
             e = cudaGetLastError();
         }
         }
@@ -618,6 +666,47 @@ static int prepare_molecules(jb_context *c, jb_molecules *m, cudaStream_t st)
     if (e != cudaSuccess)
         return fail(e == cudaErrorMemoryAllocation ? JB_ERR_NOMEM : JB_ERR_CUDA, "molecule upload: %s", cudaGetErrorString(e));
     return JB_OK;
+}
+
+// Where the structures of a host call come from: a SoA image packed by the caller (jb_query_host), or the host
+// layer's atom records, which the engine packs itself slice by slice (jb_query_records).
+struct HostSource {
+    const jb_molecule_batch *soa = nullptr;
+    const jb_atom_record *const *recs = nullptr;
+    const int64_t *counts = nullptr;
+    int M = 0;
+    bool serial = false;
+    std::vector<int64_t> off;                         // [M + 1] atom offsets (records mode)
+    const int64_t *offsets() const { return soa ? soa->atom_offset : off.data(); }
+};
+
+// Structures [m0, m1) of the source -> device staging `m` on stream `st` (copies only, no kernels, no sync).
+// Records mode packs them first into the page-locked block `stg` (jb_molecules_pack: one host thread per share of the
+// atoms), which must stay untouched until the stream has passed the copies.
+static int stage_source(jb_context *c, jb_molecules *m, const HostSource &src, int m0, int m1, cudaStream_t st, PinBuf &stg)
+{
+    if (src.soa) return stage_molecules(c, m, src.soa, m0, m1, st);
+    const int M = m1 - m0;
+    const int64_t NA = src.off[m1] - src.off[m0];
+    const size_t n = (size_t)std::max<int64_t>(NA, 1);
+    auto up8 = [](size_t v) { return (v + 7) & ~(size_t)7; };
+    const size_t o_x = 0, o_y = o_x + 8 * n, o_z = o_y + 8 * n, o_name = o_z + 8 * n, o_res = o_name + up8(4 * n),
+                 o_seq = o_res + up8(4 * n), o_ser = o_seq + up8(4 * n), o_chain = o_ser + (src.serial ? up8(4 * n) : 0),
+                 o_off = o_chain + up8(n), total = o_off + 8 * ((size_t)M + 1);
+    if (stg.ensure(total) != cudaSuccess) { cudaGetLastError(); return fail(JB_ERR_NOMEM, "page-locked staging of %zu bytes", total); }
+    char *base = stg.as<char>();
+    jb_molecule_batch view;
+    view.n_molecules = M;
+    int64_t *off = reinterpret_cast<int64_t *>(base + o_off);
+    double *x = reinterpret_cast<double *>(base + o_x), *y = reinterpret_cast<double *>(base + o_y), *z = reinterpret_cast<double *>(base + o_z);
+    uint32_t *name = reinterpret_cast<uint32_t *>(base + o_name), *res = reinterpret_cast<uint32_t *>(base + o_res);
+    int32_t *seq = reinterpret_cast<int32_t *>(base + o_seq), *ser = src.serial ? reinterpret_cast<int32_t *>(base + o_ser) : nullptr;
+    uint8_t *chain = reinterpret_cast<uint8_t *>(base + o_chain);
+    const int rc = jb_molecules_pack(src.recs + m0, src.counts + m0, M, off, x, y, z, name, res, seq, chain, ser);
+    if (rc != JB_OK) return fail(rc, "jb_molecules_pack failed on structures [%d, %d)", m0, m1);
+    view.atom_offset = off; view.x = x; view.y = y; view.z = z; view.name = name; view.residue_name = res;
+    view.residue_number = seq; view.chain_id2 = chain; view.serial = ser;
+    return stage_molecules(c, m, &view, 0, M, st);
 }
 
 static int fill_molecules(jb_context *c, jb_molecules *m, const jb_molecule_batch *b)
@@ -665,11 +754,9 @@ static size_t expand_smem(int group, int level) { return (size_t)kExpandWarps * 
 
 template <int G, bool STATS> static cudaError_t launch_expand(int grid, size_t smem, cudaStream_t st, const ExpandArgs &a)
 {
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    if (smem > 48 * 1024) {   // per device: set on every launch (a context per GPU may share this process)
         cudaError_t e = cudaFuncSetAttribute(k_expand<G, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
     }
     k_expand<G, STATS><<<grid, kExpandThreads, smem, st>>>(a);
     return cudaGetLastError();
@@ -845,8 +932,10 @@ static int grow_hits(jb_context *c, long long need, int stride)
 
 // `slice_base`: index of mol's first structure in the caller's batch (jb_query_host runs a batch
 // slice by slice); hits are appended after the res->count records already in the device buffers.
+static int result_alloc_block(jb_result *r, size_t cap);
+
 static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecules *mol, const jb_query_params *q,
-                          jb_result *res, int slice_base = 0)
+                          jb_result *res, int slice_base = 0, bool single_call = false)
 {
     CU(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
@@ -880,9 +969,12 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         CU(cudaFuncSetAttribute(k_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)classify_smem));
 
     CU(cudaEventRecord(c->ev0, st));
-    k_shells<<<t->T, 128, 0, st>>>(TT, q->distance_cutoff, q->max_dynamic_distance);
-    CU(cudaGetLastError());
-    S.launches++;
+    if (!(t->shells_valid && t->shells_cutoff == q->distance_cutoff && t->shells_maxdyn == q->max_dynamic_distance)) {
+        k_shells<<<t->T, 128, 0, st>>>(TT, q->distance_cutoff, q->max_dynamic_distance);
+        CU(cudaGetLastError());
+        S.launches++;
+        t->shells_valid = true; t->shells_cutoff = q->distance_cutoff; t->shells_maxdyn = q->max_dynamic_distance;
+    }
 
     // initial capacities (grow on demand, see the retry loop)
     if (c->fr[0].bytes == 0) {
@@ -946,11 +1038,15 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         CU(cudaMemcpyAsync(dc, c->host_ctr, sizeof(Counters), cudaMemcpyHostToDevice, st));
 
         CU(cudaEventRecord(c->evs[0], st));
-        k_classify<<<Mc, 256, classify_smem, st>>>(MT, ST, CT, dc, class_words);
-        k_xindex<<<(unsigned)(((long long)Mc * t->S * 32 + 255) / 256), 256, 0, st>>>((long long)Mc * t->S, CT);
-        if (c->sweep) k_binindex<<<c->sm_count * 8, 256, 0, st>>>(CT, dc);
+        nvtxRangePushA("jb:candidate lists (k_classify, k_xindex, k_binindex)");
+        k_classify<<<Mc, 256, classify_smem, st>>>(MT, ST, CT, dc, class_words);   // + the x index of its lists (K1b)
+        // small chunks: ONE depth-first launch instead of one launch per level (expand_dfs.cuh); it reads the lists directly
+        const bool dfs = !c->legacy && pairs <= c->dfs_pairs;
+        if (c->sweep && !dfs) k_binindex<<<c->sm_count * 8, 256, 0, st>>>(CT, dc);
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->evs[1], st));
+        nvtxRangePop();
+        nvtxRangePushA("jb:pair set-up (k_order, k_pairs)");
         if (q->reorder == 2) {
             CU(c->ordbuf.ensure((size_t)pairs * kMaxN, st));
             k_order<<<dim3((unsigned)t->T, (unsigned)((Mc + 127) / 128)), 128, 0, st>>>(
@@ -962,10 +1058,25 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
                                                                  c->ordbuf.as<unsigned char>(), c->recs.as<PairRec>(), dc);
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->evs[2], st));
+        nvtxRangePop();
+        nvtxRangePushA("jb:frontier sweep (k_expand_grid per level) + k_superpose");
 
         const long long fr_ints[2] = { (long long)(c->fr[0].bytes / sizeof(int)), (long long)(c->fr[1].bytes / sizeof(int)) };
         const long long tuple_cap = (long long)(c->tuples.bytes / sizeof(int)) / tuple_stride;
-        for (int l = 0; l < t->nmax; l++) {
+        if (dfs) {
+            ExpandArgs A;
+            A.level = 0; A.n_specs = t->S; A.tuple_stride = tuple_stride; A.ignore_chain = q->ignore_chain;
+            A.recs = c->recs.as<PairRec>(); A.shell = TT.shell; A.atoms = MT.atoms; A.ext = MT.ext;
+            A.head = CT.head; A.xtab = CT.xtab; A.cand = CT.rec; A.cand_cap = CT.cap;
+            A.in = nullptr; A.in_count = &dc->live_pairs; A.in_cap = pairs;
+            A.out = nullptr; A.out_count = nullptr; A.out_cap = 0;
+            A.tuples = c->tuples.as<int>(); A.tuple_cap = tuple_cap;
+            A.ctr = dc;
+            const long long want = (pairs * kRootSlices + kDfsWarps - 1) / kDfsWarps;
+            k_expand_dfs<<<(unsigned)std::max<long long>(1, std::min<long long>(want, (long long)c->sm_count * 16)), kDfsThreads, 0, st>>>(A);
+            CU(cudaGetLastError());
+        }
+        for (int l = 0; l < t->nmax && !dfs; l++) {
             ExpandArgs A;
             A.level = l; A.n_specs = t->S; A.tuple_stride = tuple_stride; A.ignore_chain = q->ignore_chain;
             A.recs = c->recs.as<PairRec>(); A.shell = TT.shell; A.atoms = MT.atoms; A.ext = MT.ext;
@@ -1042,6 +1153,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         CU(cudaEventRecord(c->evs[4], st));
         CU(cudaMemcpyAsync(c->host_ctr, dc, sizeof(Counters), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
+        nvtxRangePop();
         const Counters &hc = *c->host_ctr;
         attempts++;
         if (c->debug) {
@@ -1055,7 +1167,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
                         c->host_lv[2 * l + 3] - c->host_lv[2 * l + 1]);
             }
         }
-        S.launches += 4 + t->nmax - ((t->nmin >= 2 && !c->legacy && !getenv("JB_NO_ROOT_FUSION")) ? 1 : 0);
+        S.launches += dfs ? 3 : 3 + t->nmax - ((t->nmin >= 2 && !c->legacy && !getenv("JB_NO_ROOT_FUSION")) ? 1 : 0);
         {
             float ms[4] = { 0, 0, 0, 0 };
             for (int i = 0; i < 4; i++) CU(cudaEventElapsedTime(&ms[i], c->evs[i], c->evs[i + 1]));
@@ -1091,7 +1203,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         }
         if (!retry) {
             long long need_ints[2] = { 0, 0 };
-            for (int l = 0; l < t->nmax; l++)
+            for (int l = 0; l < t->nmax && !dfs; l++)        // (the depth-first sweep keeps no frontier)
                 need_ints[l & 1] = std::max(need_ints[l & 1], (long long)hc.level[l + 1] * (l + 2));
             for (int b = 0; b < 2; b++)
                 if (need_ints[b] > fr_ints[b]) {
@@ -1123,7 +1235,45 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
 
         // ---- chunk done: put its hits into canonical order on the device ------------------
         work.pop_back();
-        if (hc.hits > hits_done) {
+        NvtxRange order_range("jb:hit ordering + gather");
+        bool ordered = false;
+        if (hc.hits > hits_done && (long long)(hc.hits - hits_done) <= kSmallHits && !getenv("JB_ORDER_GENERAL")) {
+            // ---- small result: ONE kernel orders the records and writes them out -- straight into the page-locked
+            // result block when this chunk is the whole run (no device -> host copies left for jb_result_fetch)
+            const long long h0 = (long long)hits_done, h1 = (long long)hc.hits, nh = h1 - h0;
+            const bool to_host = single_call && h0 == 0 && r.m0 == 0 && r.m1 == mol->M;
+            HitBuf DB = HB;
+            DB.mol = c->f_mol.as<int>(); DB.tpl = c->f_tpl.as<int>(); DB.atoms = c->f_atoms.as<int>();
+            DB.rmsd = c->f_rmsd.as<double>(); DB.rot = c->f_rot.as<double>(); DB.c0 = c->f_c0.as<double>();
+            DB.c1 = c->f_c1.as<double>();
+            double *xyz = nullptr;
+            if (to_host) {
+                int rc = result_alloc_block(res, (size_t)nh);
+                if (rc != JB_OK) return rc;
+                DB.mol = res->mol; DB.tpl = res->tpl; DB.atoms = res->atoms; DB.rmsd = res->rmsd; DB.rot = res->rot;
+                DB.c0 = res->c0; DB.c1 = res->c1;
+                xyz = res->xyz;
+            } else if (res->coords) {
+                CU(c->f_xyz.ensure((size_t)c->hit_cap * c->hit_stride * 3 * sizeof(double), st, (size_t)h0 * c->hit_stride * 3 * sizeof(double)));
+                xyz = c->f_xyz.as<double>();
+            }
+            int *flag = reinterpret_cast<int *>(&c->o_work.as<RunWork>()[1].max_npad);
+            const bool ranked = q->hit_order != JB_ORDER_CANONICAL;
+            if (ranked) CU(cudaMemsetAsync(flag, 0, sizeof(int), st));
+            k_hits_small<<<1, 256, 0, st>>>(h0, (int)nh, c->hit_stride, HB, DB, nullptr, flag);
+            if (res->coords)
+                k_hit_coords<<<(unsigned)((nh * 32 + 255) / 256), 256, 0, st>>>(h0, h1, c->hit_stride, slice_base + r.m0, MT, DB, xyz);
+            CU(cudaGetLastError());
+            S.launches += res->coords ? 2 : 1;
+            int multi = 0;
+            if (ranked) {                                   // with one hit per pair at most the order inside a pair is moot
+                CU(cudaMemcpyAsync(&multi, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+            }
+            ordered = multi == 0;
+            if (ordered && to_host) res->direct = true;
+        }
+        if (hc.hits > hits_done && !ordered) {
             const long long h0 = (long long)hits_done, h1 = (long long)hc.hits, nh = h1 - h0;
             const int n_tiles = (int)((pairs + 1 + kScanTile - 1) / kScanTile);
             CU(c->o_off.ensure((size_t)(pairs + 1) * sizeof(unsigned), st));
@@ -1271,6 +1421,15 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
             FB.c1 = c->f_c1.as<double>();
             k_hit_gather<<<(unsigned)((nh * 32 + 255) / 256), 256, 0, st>>>(h0, h1, c->hit_stride, OA.order, HB, FB);
             CU(cudaGetLastError());
+            if (res->coords) {
+                // Hit.atoms(transform=True) for every ordered hit of the chunk, while its structures are resident
+                CU(c->f_xyz.ensure((size_t)c->hit_cap * c->hit_stride * 3 * sizeof(double), st,
+                                   (size_t)h0 * c->hit_stride * 3 * sizeof(double)));
+                k_hit_coords<<<(unsigned)((nh * 32 + 255) / 256), 256, 0, st>>>(h0, h1, c->hit_stride, slice_base + r.m0, MT, FB,
+                                                                              c->f_xyz.as<double>());
+                CU(cudaGetLastError());
+                S.launches++;
+            }
         }
         hits_done = hc.hits;
         S.chunks++;
@@ -1332,13 +1491,41 @@ static int query_run_once(jb_context *c, const jb_templates *t, const jb_molecul
     res->best_match = q->all_tuples ? 0 : q->best_match;
     res->n_templates = t->T;
     res->trim_epoch = c->trim_epoch;
-    const int rc = query_run_impl(c, t, mol, q, res);
+    res->coords = (q->flags & JB_QUERY_COORDS) ? 1 : 0;
+    const int rc = query_run_impl(c, t, mol, q, res, 0, true);
     if (rc != JB_OK) { delete res; return rc; }
     *out = res;
     return JB_OK;
 }
 
 static size_t align64(size_t v) { return (v + 63) & ~(size_t)63; }
+
+// A page-locked result block goes back to the context's pool (caller holds pool_mu).  The pool keeps the
+// kPinPool LARGEST blocks: pinning memory costs ~0.2 ms per MiB, so a workload with large hit volumes must
+// find its blocks again even after many small queries went through the same context (a pool that refused
+// newcomers when full made every cfg 4 call page-lock and release a fresh 1.3 GB block: 230 -> 450 ms).
+// Blocks of at most kPinSmall bytes (single-structure queries: every block is allocated at least that large, so
+// they are interchangeable) are pooled apart, so that neither kind evicts the other.
+constexpr size_t kPinPool = 8, kPinSmall = (size_t)1 << 16;
+static void pool_put(jb_context *c, void *block, size_t bytes)
+{
+    size_t n_small = 0, n_large = 0;
+    for (auto &b : c->pin_pool) (b.second <= kPinSmall ? n_small : n_large)++;
+    if (bytes <= kPinSmall) {
+        if (n_small < kPinPool) c->pin_pool.emplace_back(block, bytes);
+        else cudaFreeHost(block);
+        return;
+    }
+    c->pin_pool.emplace_back(block, bytes);
+    if (n_large + 1 > kPinPool) {
+        size_t small = c->pin_pool.size();
+        for (size_t i = 0; i < c->pin_pool.size(); i++)
+            if (c->pin_pool[i].second > kPinSmall && (small == c->pin_pool.size() || c->pin_pool[i].second < c->pin_pool[small].second))
+                small = i;
+        cudaFreeHost(c->pin_pool[small].first);
+        c->pin_pool.erase(c->pin_pool.begin() + small);
+    }
+}
 
 // One page-locked block for the seven hit arrays, laid out for `cap` records and recycled
 // through the context's pool.
@@ -1348,23 +1535,25 @@ static int result_alloc_block(jb_result *r, size_t cap)
     const size_t stride = (size_t)r->stride;
     const size_t o_mol = 0, o_tpl = o_mol + align64(cap * 4), o_atoms = o_tpl + align64(cap * 4),
                  o_rmsd = o_atoms + align64(cap * stride * 4), o_rot = o_rmsd + align64(cap * 8),
-                 o_c0 = o_rot + align64(cap * 72), o_c1 = o_c0 + align64(cap * 24), total = o_c1 + align64(cap * 24) + 64;
+                 o_c0 = o_rot + align64(cap * 72), o_c1 = o_c0 + align64(cap * 24), o_xyz = o_c1 + align64(cap * 24),
+                 total = o_xyz + (r->coords ? align64(cap * stride * 24) : 0) + 64;
     {
         std::lock_guard<std::mutex> g(c->pool_mu);
         if (r->block) {   // a smaller block from the pipelined path: back to the pool
-            if (c->pin_pool.size() < 4) c->pin_pool.emplace_back(r->block, r->block_bytes);
-            else cudaFreeHost(r->block);
+            pool_put(c, r->block, r->block_bytes);
             r->block = nullptr;
         }
+        size_t best = c->pin_pool.size();                // smallest block that fits
         for (size_t i = 0; i < c->pin_pool.size(); i++)
-            if (c->pin_pool[i].second >= total) {
-                r->block = c->pin_pool[i].first; r->block_bytes = c->pin_pool[i].second;
-                c->pin_pool.erase(c->pin_pool.begin() + i);
-                break;
-            }
+            if (c->pin_pool[i].second >= total && (best == c->pin_pool.size() || c->pin_pool[i].second < c->pin_pool[best].second))
+                best = i;
+        if (best < c->pin_pool.size()) {
+            r->block = c->pin_pool[best].first; r->block_bytes = c->pin_pool[best].second;
+            c->pin_pool.erase(c->pin_pool.begin() + best);
+        }
     }
     if (!r->block) {
-        const size_t want = total + total / 4;
+        const size_t want = std::max(total + total / 4, kPinSmall);
         CU(cudaMallocHost(&r->block, want));
         r->block_bytes = want;
     }
@@ -1373,6 +1562,7 @@ static int result_alloc_block(jb_result *r, size_t cap)
     r->atoms = reinterpret_cast<int32_t *>(base + o_atoms); r->rmsd = reinterpret_cast<double *>(base + o_rmsd);
     r->rot = reinterpret_cast<double *>(base + o_rot); r->c0 = reinterpret_cast<double *>(base + o_c0);
     r->c1 = reinterpret_cast<double *>(base + o_c1);
+    r->xyz = r->coords ? reinterpret_cast<double *>(base + o_xyz) : nullptr;
     r->block_cap = cap;
     return JB_OK;
 }
@@ -1391,6 +1581,7 @@ static int result_copy_range(jb_result *r, size_t from, size_t to, cudaStream_t 
     D2H(r->rot, c->f_rot, double, 9);
     D2H(r->c0, c->f_c0, double, 3);
     D2H(r->c1, c->f_c1, double, 3);
+    if (r->coords) D2H(r->xyz, c->f_xyz, double, stride * 3);
 #undef D2H
     return JB_OK;
 }
@@ -1414,6 +1605,7 @@ static void result_finalize(jb_result *r)
             memmove(&r->rot[w * 9], &r->rot[best * 9], 9 * sizeof(double));
             memmove(&r->c0[w * 3], &r->c0[best * 3], 3 * sizeof(double));
             memmove(&r->c1[w * 3], &r->c1[best * 3], 3 * sizeof(double));
+            if (r->coords) memmove(&r->xyz[w * stride * 3], &r->xyz[best * stride * 3], stride * 3 * sizeof(double));
             w++;
             i = j;
         }
@@ -1427,6 +1619,10 @@ extern "C" int jb_result_fetch(jb_result *r, jb_hits *out)
     if (!r || !out) return fail(JB_ERR_INVALID, "jb_result_fetch: NULL argument");
     jb_context *c = r->ctx;
     CU(cudaSetDevice(c->device));
+    if (!r->fetched && r->direct) {                       // the records are in the host block already (k_hits_small)
+        CU(cudaStreamSynchronize(c->stream));
+        result_finalize(r);
+    }
     if (!r->fetched) {
         if (r->trim_epoch != c->trim_epoch)
             return fail(JB_ERR_INVALID, "jb_result_fetch: the hits of this run were discarded by jb_context_trim");
@@ -1448,6 +1644,7 @@ extern "C" int jb_result_fetch(jb_result *r, jb_hits *out)
     out->reserved = 0;
     out->molecule = r->mol; out->template_index = r->tpl; out->atoms = r->atoms;
     out->rmsd = r->rmsd; out->rotation = r->rot; out->centre0 = r->c0; out->centre1 = r->c1;
+    out->coords = r->coords ? r->xyz : nullptr;
     return JB_OK;
 }
 
@@ -1463,8 +1660,7 @@ extern "C" void jb_result_free(jb_result *r)
     if (!r) return;
     if (r->block) {   // recycled by the next fetch (bounded pool); may run while another thread queries
         std::lock_guard<std::mutex> g(r->ctx->pool_mu);
-        if (r->ctx->pin_pool.size() < 4) r->ctx->pin_pool.emplace_back(r->block, r->block_bytes);
-        else cudaFreeHost(r->block);
+        pool_put(r->ctx, r->block, r->block_bytes);
     }
     delete r;
 }
@@ -1473,7 +1669,7 @@ extern "C" void jb_result_free(jb_result *r)
 // device copy of slice k+1 (copy stream, double-buffered staging) and the device -> host copy of
 // slice k-1's hits overlap the kernels of slice k (compute stream).  Record order is unchanged:
 // slices are ascending runs of structures.
-static int query_host_pipelined(jb_context *c, const jb_templates *t, const jb_molecule_batch *b,
+static int query_host_pipelined(jb_context *c, const jb_templates *t, const HostSource &src,
                                 const jb_query_params *q, int n_slices, jb_result **out, jb_hits *hits)
 {
     if (!c->copy_stream) {
@@ -1483,12 +1679,14 @@ static int query_host_pipelined(jb_context *c, const jb_templates *t, const jb_m
     for (int i = 0; i < 2; i++)
         if (!c->slice_mol[i]) c->slice_mol[i] = new jb_molecules();
     // slice boundaries: equal shares of the atoms
-    const int M = b->n_molecules;
-    const long long NA = b->atom_offset[M];
+    const int M = src.M;
+    const int64_t *aoff = src.offsets();
+    const long long NA = aoff[M];
     std::vector<int> cut{ 0 };
     for (int k = 1; k < n_slices; k++) {
-        const long long want = NA * k / n_slices;
-        int m = (int)(std::lower_bound(b->atom_offset, b->atom_offset + M + 1, want) - b->atom_offset);
+        // records mode: the packing of the FIRST slice is the only one nothing hides -- keep it half as large
+        const int64_t want = src.soa ? NA * k / n_slices : NA * (2 * k - 1) / (2 * n_slices - 1);
+        int m = (int)(std::lower_bound(aoff, aoff + M + 1, want) - aoff);
         m = std::min(std::max(m, cut.back() + 1), M - (n_slices - k));
         cut.push_back(m);
     }
@@ -1499,28 +1697,54 @@ static int query_host_pipelined(jb_context *c, const jb_templates *t, const jb_m
     res->best_match = q->all_tuples ? 0 : q->best_match;
     res->n_templates = t->T;
     res->trim_epoch = c->trim_epoch;
+    res->coords = (q->flags & JB_QUERY_COORDS) ? 1 : 0;
     int rc = result_alloc_block(res, (size_t)std::max<long long>(c->last_hits + c->last_hits / 8, 1 << 16));
     bool direct = rc == JB_OK;                        // hits still fit the block laid out above
     size_t copied = 0;
-    if (rc == JB_OK) rc = stage_molecules(c, c->slice_mol[0], b, cut[0], cut[1], c->copy_stream);
-    if (rc == JB_OK) CU(cudaEventRecord(c->ev_up[0], c->copy_stream));
+    // Slice k + 1 is staged (records mode: packed on host threads, then copied) by a helper thread while this thread
+    // drives the kernels of slice k.  Both the device image slice_mol[(k + 1) & 1] and the host block host_stage[(k + 1) & 1]
+    // were last used by slice k - 1, whose upload and kernels are complete when iteration k starts.
+    const double t_begin = now_ms();
+    auto stage = [&](int k) -> std::pair<int, std::string> {
+        cudaSetDevice(c->device);
+        const double t_0 = now_ms();
+        int r = stage_source(c, c->slice_mol[k & 1], src, cut[k], cut[k + 1], c->copy_stream, c->host_stage[k & 1]);
+        if (c->debug >= 2) fprintf(stderr, "[jb]   slice %d staged (structures [%d, %d)): %.2f - %.2f ms\n", k, cut[k], cut[k + 1],
+                                   t_0 - t_begin, now_ms() - t_begin);
+        if (r == JB_OK && cudaEventRecord(c->ev_up[k & 1], c->copy_stream) != cudaSuccess) r = fail(JB_ERR_CUDA, "cudaEventRecord failed");
+        return { r, r == JB_OK ? std::string() : std::string(g_err) };
+    };
+    if (rc == JB_OK) rc = stage(0).first;
     for (int k = 0; k < n_slices && rc == JB_OK; k++) {
         jb_molecules *cur = c->slice_mol[k & 1];
+        std::future<std::pair<int, std::string>> next;
         if (k + 1 < n_slices) {
-            rc = stage_molecules(c, c->slice_mol[(k + 1) & 1], b, cut[k + 1], cut[k + 2], c->copy_stream);
-            if (rc != JB_OK) break;
-            CU(cudaEventRecord(c->ev_up[(k + 1) & 1], c->copy_stream));
+            if (src.soa) {                               // copies only: enqueue them right here
+                rc = stage(k + 1).first;
+                if (rc != JB_OK) break;
+            } else next = std::async(std::launch::async, stage, k + 1);
         }
-        CU(cudaStreamWaitEvent(c->stream, c->ev_up[k & 1], 0));
-        rc = prepare_molecules(c, cur, c->stream);
-        if (rc == JB_OK) rc = query_run_impl(c, t, cur, q, res, cut[k]);       // returns with the slice's kernels done
-        if (rc != JB_OK) break;
-        if (direct && (size_t)res->count <= res->block_cap) {
-            rc = result_copy_range(res, copied, (size_t)res->count, c->copy_stream);
-            copied = (size_t)res->count;
-        } else direct = false;
+        int rk = JB_OK;
+        const double t_run = now_ms();
+        if (cudaStreamWaitEvent(c->stream, c->ev_up[k & 1], 0) != cudaSuccess) rk = fail(JB_ERR_CUDA, "cudaStreamWaitEvent failed");
+        if (rk == JB_OK) rk = prepare_molecules(c, cur, c->stream);
+        if (rk == JB_OK) rk = query_run_impl(c, t, cur, q, res, cut[k]);       // returns with the slice's kernels done
+        if (c->debug >= 2) fprintf(stderr, "[jb]   slice %d searched: %.2f - %.2f ms, %lld hits so far, retries %lld\n", k,
+                                   t_run - t_begin, now_ms() - t_begin, res->count, (long long)res->stats.retries);
+        if (rk == JB_OK) {
+            if (direct && (size_t)res->count <= res->block_cap) {
+                rk = result_copy_range(res, copied, (size_t)res->count, c->copy_stream);
+                copied = (size_t)res->count;
+            } else direct = false;
+        }
+        if (next.valid()) {                              // always joined: the helper references this frame
+            const std::pair<int, std::string> r = next.get();
+            if (r.first != JB_OK && rk == JB_OK) rk = fail(r.first, "%s", r.second.c_str());
+        }
+        rc = rk;
     }
     if (rc == JB_OK) CU(cudaStreamSynchronize(c->copy_stream));
+    if (c->debug >= 2) fprintf(stderr, "[jb]   copies done: %.2f ms (direct %d)\n", now_ms() - t_begin, (int)direct);
     if (rc == JB_OK && !direct) {                     // more hits than expected: one plain fetch of everything
         rc = result_alloc_block(res, (size_t)res->count);
         if (rc == JB_OK) rc = result_copy_range(res, 0, (size_t)res->count, c->stream);
@@ -1539,33 +1763,62 @@ static int query_host_pipelined(jb_context *c, const jb_templates *t, const jb_m
     return jb_result_fetch(res, hits);
 }
 
-static int query_host_once(jb_context *c, const jb_templates *t, const jb_molecule_batch *b, const jb_query_params *q,
+static int query_host_once(jb_context *c, const jb_templates *t, const HostSource &src, const jb_query_params *q,
                            jb_result **out, jb_hits *hits);
 
 extern "C" int jb_query_host(jb_context *c, const jb_templates *t, const jb_molecule_batch *b, const jb_query_params *q,
                              jb_result **out, jb_hits *hits)
 {
-    if (c) context_decay(c);
-    int rc = query_host_once(c, t, b, q, out, hits);
-    if (rc == JB_ERR_NOMEM && c) {                    // same policy as jb_query_run
+    if (!c || !b || !out || !hits) return fail(JB_ERR_INVALID, "jb_query_host: NULL argument");
+    if (b->n_molecules < 0) return fail(JB_ERR_INVALID, "negative molecule count");
+    HostSource src;
+    src.soa = b;
+    src.M = b->n_molecules;
+    context_decay(c);
+    int rc = query_host_once(c, t, src, q, out, hits);
+    if (rc == JB_ERR_NOMEM) {                         // same policy as jb_query_run
         context_trim(c);
-        rc = query_host_once(c, t, b, q, out, hits);
+        rc = query_host_once(c, t, src, q, out, hits);
     }
     return rc;
 }
 
-static int query_host_once(jb_context *c, const jb_templates *t, const jb_molecule_batch *b, const jb_query_params *q,
+extern "C" int jb_query_records(jb_context *c, const jb_templates *t, const jb_atom_record *const *molecules,
+                                const int64_t *counts, int32_t n_molecules, const jb_query_params *q, jb_result **out,
+                                jb_hits *hits)
+{
+    if (!c || !out || !hits || n_molecules < 0 || (n_molecules > 0 && (!molecules || !counts)))
+        return fail(JB_ERR_INVALID, "jb_query_records: bad argument");
+    HostSource src;
+    src.recs = molecules;
+    src.counts = counts;
+    src.M = n_molecules;
+    src.serial = q && q->hit_order != JB_ORDER_CANONICAL;   // Atom.serial only orders the residue index of the reference
+    src.off.assign((size_t)n_molecules + 1, 0);
+    for (int m = 0; m < n_molecules; m++) {
+        if (counts[m] < 0 || (counts[m] > 0 && !molecules[m])) return fail(JB_ERR_INVALID, "jb_query_records: structure %d", m);
+        src.off[m + 1] = src.off[m] + counts[m];
+    }
+    context_decay(c);
+    int rc = query_host_once(c, t, src, q, out, hits);
+    if (rc == JB_ERR_NOMEM) {
+        context_trim(c);
+        rc = query_host_once(c, t, src, q, out, hits);
+    }
+    return rc;
+}
+
+static int query_host_once(jb_context *c, const jb_templates *t, const HostSource &src, const jb_query_params *q,
                            jb_result **out, jb_hits *hits)
 {
-    if (!c || !b || !out || !hits) return fail(JB_ERR_INVALID, "jb_query_host: NULL argument");
     *out = nullptr;
     if (!t || !q || t->ctx != c) return fail(JB_ERR_INVALID, "jb_query_host: bad templates/params");
     if (q->ignore_chain < 0 || q->ignore_chain > 2) return fail(JB_ERR_INVALID, "invalid ignore_chain %d", q->ignore_chain);
     if (q->reorder < 0 || q->reorder > 2) return fail(JB_ERR_INVALID, "invalid reorder %d", q->reorder);
     if (q->hit_order < 0 || q->hit_order > 2) return fail(JB_ERR_INVALID, "invalid hit_order %d", q->hit_order);
     CU(cudaSetDevice(c->device));
-    if (b->n_molecules > 0 && t->T > 0 && t->TA > 0 && c->pipeline_slices != 1) {
-        const long long NA = b->atom_offset[b->n_molecules];
+    if (src.M > 0 && t->T > 0 && t->TA > 0 && c->pipeline_slices != 1) {
+        const long long NA = src.offsets()[src.M];
         // auto: slicing costs launches and host syncs per slice (measured on cfg3: 4 slices +1.0 ms,
         // 2 slices -0.25 ms), so only the copies worth hiding are pipelined: 2 slices for a large
         // upload, 4 when the previous call on this context returned a large hit volume
@@ -1573,11 +1826,17 @@ static int query_host_once(jb_context *c, const jb_templates *t, const jb_molecu
         int n_slices = c->pipeline_slices > 1 ? c->pipeline_slices
                        : out_bytes >= (256ll << 20) ? 4 : (NA >= 1000000 && q->hit_order == JB_ORDER_CANONICAL) ? 2 : 1;
         // (the rank tables of the reference hit order are rebuilt per slice: not worth two slices)
-        n_slices = std::min(n_slices, b->n_molecules / 16);
-        if (n_slices >= 2) return query_host_pipelined(c, t, b, q, n_slices, out, hits);
+        // records mode: the first slice's packing is the only one the engine does not hide -- more, smaller slices
+        if (!src.soa && c->pipeline_slices <= 1 && NA >= 1000000)
+            n_slices = std::max(n_slices, (int)std::min<long long>(8, std::max<long long>(2, NA / 2000000)));
+        n_slices = std::min(n_slices, src.M / 16);
+        if (n_slices >= 2) return query_host_pipelined(c, t, src, q, n_slices, out, hits);
     }
     if (!c->scratch_mol) c->scratch_mol = new jb_molecules();
-    int rc = fill_molecules(c, c->scratch_mol, b);      // grow-only device staging owned by the context
+    // grow-only device staging owned by the context
+    int rc = stage_source(c, c->scratch_mol, src, 0, src.M, c->stream, c->host_stage[0]);
+    if (rc == JB_OK) rc = prepare_molecules(c, c->scratch_mol, c->stream);
+    if (rc == JB_OK) CU(cudaStreamSynchronize(c->stream));   // the caller's (or our) staging may be reused from here on
     if (rc != JB_OK) return rc;
     rc = query_run_once(c, t, c->scratch_mol, q, out);
     if (rc == JB_OK) c->last_hits = (*out)->count;

@@ -39,6 +39,9 @@ __device__ __forceinline__ int nth_set_bit(unsigned x, int k)
     return pos;
 }
 
+constexpr int kGridQueue = 512;                         // survivors per window of the per-warp queue
+static_assert(kBinRecs <= 128, "queue entries hold 7 position bits");
+
 template <int L, int G> struct alignas(16) GridWarp {   // per-warp shared memory
     static constexpr int IPW = 32 / G;                  // partial matches per batch
     // placed atoms + shells towards the new atom, one array per field and [atom][partial match].  The FP32
@@ -53,6 +56,7 @@ template <int L, int G> struct alignas(16) GridWarp {   // per-warp shared memor
                                       // records in the candidate list
     int chain_atom[L][IPW];
     int stage[kStageItems * (L + 2)];                   // accepted extensions awaiting the flush
+    unsigned short queue[kGridQueue];                   // box survivors of the current window: (owner lane << 7) | position in its bin
 };
 
 template <int L, int G> constexpr size_t expand_grid_smem() { return sizeof(GridWarp<L, G>) * kExpandWarps; }
@@ -175,10 +179,14 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_grid(const ExpandA
 
     // Hand the survivors of the batch's current bins -- the set bits of the masks held by the first
     // lane of every group -- to the exact test, 32 per round.  A loose box passes a whole bin, a tight
-    // one nothing: one lane extracting its own bits ran 65-90 rounds per batch at 4 active lanes
-    // (gpurun_out/r2d-r2f).  Instead survivor s = 32 r + t belongs to the last lane o whose exclusive
-    // prefix sum E_o is <= s, and is the (s - E_o)-th set bit of that lane's mask.
-    auto deal = [&](const BinMask &m, const int posbase) {
+    // one nothing: one lane testing its own bits ran 65-90 rounds per batch at 4 active lanes
+    // (gpurun_out/r2d-r2f), and a per-round owner search by shuffles cost ~55 instructions per 32
+    // survivors (30 % of the kernel, profiles/r2i).  Instead every lane only UNPACKS its bits -- a
+    // few instructions per survivor -- into a per-warp queue of (owner lane, position) entries at
+    // the slots a warp prefix sum assigns, and the rounds read the queue: survivor s of a window is
+    // queue[s], whoever owns it.  A window holds kGridQueue survivors; lanes whose slots lie beyond
+    // it keep their remaining bits for the next window.
+    auto deal = [&](BinMask &m, const int posbase) {
         int c = 0;
 #pragma unroll
         for (int h = 0; h < kMaskWords; h++) c += __popc(m.w[h]);
@@ -189,29 +197,29 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_grid(const ExpandA
             if (lane >= o) inc += t;
         }
         const int total = __shfl_sync(FULL, inc, 31);
-        const int excl = inc - c;
-        for (int s0 = 0; s0 < total; s0 += 32) {
-            const int s = s0 + lane;
-            int o = 0;
+        int idx = inc - c;                                   // slot of this lane's next survivor
+        for (int w0 = 0; w0 < total; w0 += kGridQueue) {
+            const int w1 = min(total, w0 + kGridQueue);
 #pragma unroll
-            for (int step = 16; step > 0; step >>= 1) {
-                const int e = __shfl_sync(FULL, excl, o + step);
-                if (e <= s) o += step;
-            }
-            int k = s - __shfl_sync(FULL, excl, o);
-            unsigned w = __shfl_sync(FULL, m.w[0], o);
-            const unsigned x1 = __shfl_sync(FULL, m.w[1], o), x2 = __shfl_sync(FULL, m.w[2], o),
-                           x3 = __shfl_sync(FULL, m.w[3], o);
-            const int pb = __shfl_sync(FULL, posbase, o);
-            int h = 0, t = __popc(w);
-            if (k >= t) {
-                k -= t; w = x1; h = 1; t = __popc(x1);
-                if (k >= t) {
-                    k -= t; w = x2; h = 2; t = __popc(x2);
-                    if (k >= t) { k -= t; w = x3; h = 3; }
+            for (int h = 0; h < kMaskWords; h++) {
+                unsigned w = m.w[h];
+                while (w != 0u && idx < w1) {
+                    const int b = __ffs(w) - 1;
+                    w &= w - 1u;
+                    W.queue[idx - w0] = (unsigned short)((lane << 7) | (32 * h + b));
+                    idx++;
                 }
+                m.w[h] = w;
             }
-            drain(s < total, pb + 32 * h + nth_set_bit(w, k), o / G);
+            __syncwarp();
+            for (int s0 = w0; s0 < w1; s0 += 32) {
+                const int s = s0 + lane;
+                const int e = s < w1 ? (int)W.queue[s - w0] : 0;
+                const int o = e >> 7;
+                const int pb = __shfl_sync(FULL, posbase, o);
+                drain(s < w1, pb + (e & 127), o / G);
+            }
+            __syncwarp();                                    // the next window overwrites the queue
         }
     };
 

@@ -371,4 +371,124 @@ __global__ void __launch_bounds__(256) k_hit_gather(long long h0, long long h1, 
     else if (lane < 15) dst.c1[q * 3 + lane - 12] = src.c1[s * 3 + lane - 12];
 }
 
+// ---- small results: order + gather in ONE launch -------------------------------------------------
+// A single-structure query returns a handful of hits; the general ordering path above spends ~10
+// launches (+ a device radix sort) on them.  One CTA sorts up to kSmallHits hit indices by (structure,
+// template, atom tuple) -- a bitonic network over shared memory, tuples compared in place -- and writes
+// the records in that order to `dst`, which may be page-locked HOST memory (the result block itself:
+// no device->host copies afterwards).  *multi is set when some (structure, template) holds more than
+// one hit: the caller then knows whether the order INSIDE a pair matters (reference hit order).
+constexpr int kSmallHits = 1024;
+
+__global__ void __launch_bounds__(256) k_hits_small(long long h0, int nh, int stride, HitBuf src, HitBuf dst, double *dst_xyz_unused,
+                                                    int *multi)
+{
+    __shared__ int s_mol[kSmallHits], s_tpl[kSmallHits], s_idx[kSmallHits];
+    (void)dst_xyz_unused;
+    int npad = 1;
+    while (npad < nh) npad <<= 1;
+    for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+        s_idx[i] = i < nh ? i : -1;
+        s_mol[i] = i < nh ? src.mol[h0 + i] : 0x7fffffff;
+        s_tpl[i] = i < nh ? src.tpl[h0 + i] : 0x7fffffff;
+    }
+    __syncthreads();
+    auto less = [&](int a, int b) {                       // hit a before hit b (padding last)
+        if (a < 0 || b < 0) return b < 0 && a >= 0;
+        if (s_mol[a] != s_mol[b]) return s_mol[a] < s_mol[b];
+        if (s_tpl[a] != s_tpl[b]) return s_tpl[a] < s_tpl[b];
+        const int *pa = src.atoms + (h0 + a) * stride, *pb = src.atoms + (h0 + b) * stride;
+        for (int k = 0; k < stride; k++)
+            if (pa[k] != pb[k]) return pa[k] < pb[k];
+        return a < b;
+    };
+    for (int k = 2; k <= npad; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const int x = s_idx[i], y = s_idx[p];
+                    const bool up = (i & k) == 0;
+                    if (up ? less(y, x) : less(x, y)) { s_idx[i] = y; s_idx[p] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int q = threadIdx.x; q < nh; q += blockDim.x) {
+        const int a = s_idx[q];
+        if (q > 0) {
+            const int b = s_idx[q - 1];
+            if (s_mol[a] == s_mol[b] && s_tpl[a] == s_tpl[b]) *multi = 1;
+        }
+        const long long s_ = h0 + a, d = h0 + q;
+        dst.mol[d] = s_mol[a]; dst.tpl[d] = s_tpl[a]; dst.rmsd[d] = src.rmsd[s_];
+        for (int k = 0; k < stride; k++) dst.atoms[d * stride + k] = src.atoms[s_ * stride + k];
+        for (int k = 0; k < 9; k++) dst.rot[d * 9 + k] = src.rot[s_ * 9 + k];
+        for (int k = 0; k < 3; k++) { dst.c0[d * 3 + k] = src.c0[s_ * 3 + k]; dst.c1[d * 3 + k] = src.c1[s_ * 3 + k]; }
+    }
+}
+
+// ---- transformed coordinates of the matched atoms -------------------------------
+// Hit.atoms(transform=True) (_jess.pyx:2454-2482) builds Hit.transformation = Mv @ Mr @ Mc
+// (translation to centre1, rotation, translation by -centre0; :2343-2377) with Mat4.__matmul__
+// (:225-240: res[i][j] += a[i][k] * b[k][j], k ascending, from 0) and applies it with
+// Atom._transform (:1293-1307: x'[i] = sum_j M[i][j] * (x, 1)[j], j ascending, from 0).  One warp
+// per ORDERED hit replays exactly those operations (explicit round-to-nearest, no FMA) on the FP64
+// atom records, lane k on the atom matched to template atom k: xyz[(q * stride + k) * 3 ..].
+__global__ void __launch_bounds__(256) k_hit_coords(long long h0, long long h1, int stride, int mol_base, MolTable M,
+                                                    HitBuf f, double *xyz)
+{
+    const long long q = h0 + ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+    const int lane = threadIdx.x & 31;
+    if (q >= h1) return;
+    double Mv[4][4], Mr[4][4], Mc[4][4], A[4][4], T[3][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) Mv[i][j] = Mr[i][j] = Mc[i][j] = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        Mc[i][3] = -f.c0[q * 3 + i];
+        Mv[i][3] = f.c1[q * 3 + i];
+#pragma unroll
+        for (int j = 0; j < 3; j++) Mr[i][j] = f.rot[q * 9 + 3 * i + j];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            double r = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) r = __dadd_rn(r, __dmul_rn(Mv[i][k], Mr[k][j]));
+            A[i][j] = r;
+        }
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            double r = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) r = __dadd_rn(r, __dmul_rn(A[i][k], Mc[k][j]));
+            T[i][j] = r;
+        }
+    const long long a0 = M.atom_off[f.mol[q] - mol_base];
+    for (int k = lane; k < stride; k += 32) {
+        const int a = f.atoms[q * stride + k];
+        double out[3] = { 0.0, 0.0, 0.0 };
+        if (a >= 0) {
+            const AtomRec ar = M.atoms[a0 + a];
+            const double v[4] = { ar.x, ar.y, ar.z, 1.0 };
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                double r = 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) r = __dadd_rn(r, __dmul_rn(T[i][j], v[j]));
+                out[i] = r;
+            }
+        }
+        double *dst = xyz + (q * stride + k) * 3;
+        dst[0] = out[0]; dst[1] = out[1]; dst[2] = out[2];
+    }
+}
+
 }  // namespace jb

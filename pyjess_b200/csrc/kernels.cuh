@@ -304,10 +304,16 @@ __device__ __forceinline__ uint32_t float_orderable(float f)
 
 constexpr int kSortThreads = 512;
 
-__global__ void __launch_bounds__(kSortThreads) k_sort_atoms(const long long *atom_off, const AtomRec *atoms,
+struct RawAtoms {              // SoA upload image; x == nullptr: the 32-byte records exist already (k_pack_atoms)
+    const double *x, *y, *z;
+    const int *resseq;
+    const unsigned char *chain;
+};
+
+__global__ void __launch_bounds__(kSortThreads) k_sort_atoms(const long long *atom_off, AtomRec *atoms,
                                                              const uint32_t *name, const uint32_t *res, MolExt *ext,
                                                              float4 *srec, uint32_t *sname, uint32_t *sres,
-                                                             u64 *scratch, int smem_keys)
+                                                             u64 *scratch, int smem_keys, RawAtoms raw)
 {
     extern __shared__ __align__(16) unsigned char sort_smem[];
     __shared__ double sh_ext[kSortThreads / 32];
@@ -315,6 +321,16 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_atoms(const long long *at
     const long long a0 = atom_off[m], a1 = atom_off[m + 1];
     const int na = (int)(a1 - a0);
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (raw.x) {               // small batches: K0 fused in (one launch less on the latency path)
+        for (int i = tid; i < na; i += kSortThreads) {
+            AtomRec r;
+            r.x = raw.x[a0 + i]; r.y = raw.y[a0 + i]; r.z = raw.z[a0 + i];
+            r.resseq = raw.resseq[a0 + i];
+            r.chain = (int)raw.chain[a0 + i];
+            atoms[a0 + i] = r;
+        }
+        __syncthreads();       // the records of this structure are read back below, by other threads of the CTA
+    }
     double ox = 0.0, oy = 0.0, oz = 0.0, e = 0.0;
     if (na > 0) { const AtomRec o = atoms[a0]; ox = o.x; oy = o.y; oz = o.z; }
     for (int i = tid; i < na; i += kSortThreads) {
@@ -435,6 +451,8 @@ __device__ __forceinline__ unsigned class_hash(uint32_t name, uint32_t res_up)
 {
     return ((name * 0x9E3779B1u) ^ (res_up * 0x85EBCA6Bu) ^ (name >> 15)) & (kClassSlots - 1);
 }
+
+__device__ __forceinline__ void xindex_list(const long long L, const int lane, const CandTable &C);
 
 __global__ void __launch_bounds__(256) k_classify(MolTable M, SpecTable S, CandTable C, Counters *ctr, int class_words)
 {
@@ -569,6 +587,9 @@ __global__ void __launch_bounds__(256) k_classify(MolTable M, SpecTable S, CandT
             __syncthreads();
         }
     }
+    // K1b fused in: the x-bucket index of this structure's lists (its records were written by this CTA)
+    __syncthreads();
+    for (int s = w; s < ns; s += nw) xindex_list((long long)m * ns + s, lane, C);
 }
 
 // ---- K1b: x-bucket index of every candidate list ---------------------------------------
@@ -576,11 +597,8 @@ __global__ void __launch_bounds__(256) k_classify(MolTable M, SpecTable S, CandT
 // x lies inside the join box.  Instead of two binary searches (5-6 DEPENDENT scattered loads
 // each, 9 % of the sweep's stall samples in profiles/r1g) every list gets a table of
 // kXBuckets uniform x buckets: tab[b] = first record with bucket >= b.  One warp per list.
-__global__ void __launch_bounds__(256) k_xindex(long long n_lists, CandTable C)
+__device__ __forceinline__ void xindex_list(const long long L, const int lane, const CandTable &C)
 {
-    const long long L = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (L >= n_lists) return;
     CandHead hd = C.head[L];
     unsigned short *tab = C.xtab + L * kXBuckets;
     if (hd.cnt <= 0 || hd.off + hd.cnt > C.cap) return;        // empty, or the chunk is being re-run larger
@@ -598,6 +616,13 @@ __global__ void __launch_bounds__(256) k_xindex(long long n_lists, CandTable C)
     }
     const int bl = x_bucket(x1, x0, inv_w);
     for (int q = bl + 1 + lane; q < kXBuckets; q += 32) tab[q] = (unsigned short)hd.cnt;
+}
+
+__global__ void __launch_bounds__(256) k_xindex(long long n_lists, CandTable C)
+{
+    const long long L = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (L >= n_lists) return;
+    xindex_list(L, threadIdx.x & 31, C);
 }
 
 // ---- K1c: cell grid of every bin --------------------------------------------------------

@@ -172,35 +172,61 @@ def _protein_group(args):
     return ids, out
 
 
+def protein_groups(count: int, length, seed: int, first: int = 0):
+    """The independent generation units of a ranged-length set: groups of 64 chains of similar
+    length, each with its own RNG stream -- so ANY subset of the groups can be generated (by any
+    process) and yields the same structures.  Returns [(job, ids, lengths)]: `ids` = positions of
+    the group's structures in the set of `count`, `job` = argument of `_protein_group`."""
+    rng = np.random.default_rng([seed, first, count])
+    lengths = rng.integers(length[0], length[1] + 1, size=count)
+    order = np.argsort(lengths, kind="stable")
+    group = 64 if lengths.max() > 600 else 256
+    out = []
+    for g0 in range(0, count, group):
+        ids = order[g0:g0 + group]
+        out.append(((seed, first, count, g0, lengths[ids], ids), ids, lengths[ids]))
+    return out
+
+
+def proteins_of_groups(groups, first: int = 0, workers=None):
+    """Generate the structures of `groups` (entries of `protein_groups`) on a process pool.
+    Returns (ids, molecules), group by group."""
+    jobs = [g[0] for g in groups]
+    if workers is None:
+        workers = min(len(jobs), len(os.sched_getaffinity(0)))
+    n = sum(len(g[1]) for g in groups)
+    if n >= 512 and workers > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(workers) as pool:
+            results = pool.map(_protein_group, jobs, chunksize=1)
+    else:
+        results = list(map(_protein_group, jobs))
+    ids, mols = [], []
+    for gi, arrs in results:
+        for i, arr in zip(gi, arrs):
+            ids.append(int(i))
+            mols.append(Molecule._from_records(arr, id=f"S{(first + int(i)) % 1000:03d}"))
+    return np.asarray(ids, dtype=np.int64), mols
+
+
 def proteins(count: int, length=300, seed: int = 1000, first: int = 0) -> List[Molecule]:
     """`count` single-chain proteins; `length` is an int or a (lo, hi) range
     (cfg 3: 300; cfg 4: (300, 1500)).  Ranged lengths are generated group by group from
     independent RNG streams (deterministic whatever the worker count), on a process pool
     when the set is large (cfg 4: 6,250 structures per GPU)."""
-    rng = np.random.default_rng([seed, first, count])
     ranged = isinstance(length, (tuple, list))
     if ranged:
-        lengths = rng.integers(length[0], length[1] + 1, size=count)
-    else:
-        lengths = np.full(count, int(length))
-    out: List[Molecule] = [None] * count
+        ids, mols = proteins_of_groups(protein_groups(count, length, seed, first), first)
+        out: List[Molecule] = [None] * count
+        for i, m in zip(ids.tolist(), mols):
+            out[i] = m
+        return out
+    rng = np.random.default_rng([seed, first, count])
+    lengths = np.full(count, int(length))
+    out = [None] * count
     order = np.argsort(lengths, kind="stable")
     # walk chains of similar length together to bound the (P, trials, L) temporaries
     group = 64 if lengths.max() > 600 else 256
-    if ranged:
-        jobs = [(seed, first, count, g0, lengths[order[g0:g0 + group]], order[g0:g0 + group])
-                for g0 in range(0, count, group)]
-        workers = min(len(jobs), len(os.sched_getaffinity(0)))
-        if count >= 512 and workers > 1:
-            import multiprocessing as mp
-            with mp.get_context("fork").Pool(workers) as pool:
-                results = pool.map(_protein_group, jobs, chunksize=1)
-        else:
-            results = map(_protein_group, jobs)
-        for ids, arrs in results:
-            for i, arr in zip(ids, arrs):
-                out[i] = Molecule._from_records(arr, id=f"S{(first + i) % 1000:03d}")
-        return out
     for g0 in range(0, count, group):
         ids = order[g0:g0 + group]
         ca = _ca_walks(rng, lengths[ids])

@@ -165,6 +165,14 @@ def main():
     add("single_mixed_lnb", ["single_his.qry", "template_01.qry", "single_glu_asp.qry"], "pdb1lnb.ent",
         (2.0, 5.0, 5.0), {})
     cases[-1]["single_atom"] = True
+    # ... with best_match: every single-atom tuple has RMSD 0, so the reference keeps the FIRST candidate it
+    # reports -- its candidate #1, candidate #0 being the one it never reports
+    for fname in singles:
+        add(f"{fname[:-4]}_pdb1lnb_best", [fname], "pdb1lnb.ent", (2.0, 2.0, 2.0), {"best_match": True})
+        cases[-1]["single_atom"] = True
+    add("single_mixed_lnb_best", ["single_his.qry", "template_01.qry", "single_glu_asp.qry"], "pdb1lnb.ent",
+        (2.0, 5.0, 5.0), {"best_match": True})
+    cases[-1]["single_atom"] = True
 
     # cfg 2: the three example templates against all 132 structures
     cfg2 = []

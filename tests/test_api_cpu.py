@@ -124,9 +124,9 @@ def test_batch_run_slices_with_a_stubbed_engine(monkeypatch):
     table = types.SimpleNamespace(count=n, molecule=mol, template=t, atoms=np.zeros((n, 18), np.int32),
                                   rmsd=rng.uniform(0, 2, n), rotation=np.zeros((n, 3, 3)), centre0=np.zeros((n, 3)),
                                   centre1=np.zeros((n, 3)))
-    monkeypatch.setattr(_capi, "default_context", lambda: None)
+    monkeypatch.setattr(_capi, "default_context", lambda device=None: None)
     monkeypatch.setattr(Jess, "_device_templates", lambda self, ctx: None)
-    monkeypatch.setattr(_capi, "query_host", lambda ctx, dev, batch, params: (table, {"nan_dropped": 0}))
+    monkeypatch.setattr(_capi, "query_records", lambda ctx, dev, molecules, params: (table, {"nan_dropped": 0}))
     jess = Jess(tpl)
     single = len(tpl) - 1
     seen = 0
@@ -189,3 +189,163 @@ def test_every_public_member_of_the_reference_classes_exists():
     for cls, members in REFERENCE_SURFACE.items():
         missing = [m for m in members if not hasattr(getattr(pyjess_b200, cls), m)]
         assert not missing, (cls, missing)
+
+
+def _stub_engine(monkeypatch, mols, table, calls=None, delay=0.0):
+    """`_capi.query_records` answered from a global hit table (numbered by position in `mols`): the
+    call's own structures are looked up by identity and the rows re-numbered to the call."""
+    import time
+    import types
+    import numpy as np
+    from pyjess_b200 import Jess, _capi
+    where = {id(m): i for i, m in enumerate(mols)}
+
+    def query_records(ctx, dev, molecules, params):
+        ids = np.asarray([where[id(m)] for m in molecules], dtype=np.int64)
+        local = np.full(len(mols), -1, dtype=np.int64)
+        local[ids] = np.arange(len(ids))
+        rows = np.nonzero(local[table.molecule] >= 0)[0]
+        rows = rows[np.argsort(local[table.molecule[rows]], kind="stable")]
+        if calls is not None:
+            calls.append((ctx, ids.tolist()))
+        if delay:
+            time.sleep(delay)
+        sub = types.SimpleNamespace(count=len(rows), molecule=local[table.molecule[rows]].astype(np.int32),
+                                    template=table.template[rows].copy(), atoms=table.atoms[rows].copy(),
+                                    rmsd=table.rmsd[rows].copy(), rotation=table.rotation[rows].copy(),
+                                    centre0=table.centre0[rows].copy(), centre1=table.centre1[rows].copy(), coords=None)
+        return sub, {"nan_dropped": 0, "hits": len(rows)}
+
+    monkeypatch.setattr(_capi, "default_context", lambda device=None: device)
+    monkeypatch.setattr(Jess, "_device_templates", lambda self, ctx: None)
+    monkeypatch.setattr(_capi, "query_records", query_records)
+
+
+def _random_table(n_mols, n_tpl, n, seed):
+    import types
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    mol = np.sort(rng.integers(0, n_mols, n)).astype(np.int32)
+    t = rng.integers(0, n_tpl, n).astype(np.int32)
+    order = np.lexsort((t, mol))
+    mol, t = mol[order], t[order]
+    return types.SimpleNamespace(count=n, molecule=mol, template=t,
+                                 atoms=rng.integers(0, 50, (n, 18)).astype(np.int32), rmsd=rng.uniform(0, 2, n),
+                                 rotation=np.zeros((n, 3, 3)), centre0=np.zeros((n, 3)), centre1=np.zeros((n, 3)))
+
+
+def test_sharded_runs_equal_the_single_run(monkeypatch):
+    """`query_many(devices=[...])`: structures dealt to the devices by atom count (LPT), one hit
+    table per device -- every Query must see exactly the records (and order) of the one-device
+    run.  Host logic only: the engine is stubbed."""
+    import numpy as np
+    from pyjess_b200 import Jess, synth
+    tpl, mols, thr, _ = synth.workload("cfg3", scale=0.04)
+    table = _random_table(len(mols), len(tpl), 4000, 5)
+    jess = Jess(tpl)
+    _stub_engine(monkeypatch, mols, table)
+    base = [(q.hit_table()[1].tolist(), [(h.rmsd, h.template()) for h in q]) for q in jess.query_many(mols, *thr)]
+    want = [([int(table.molecule[i]) for i in rows], [float(table.rmsd[i]) for i in rows]) for rows, _ in base]
+    for devices in ([0, 1, 2], [1, 0], [3], "2,5"):
+        calls = []
+        _stub_engine(monkeypatch, mols, table, calls)
+        queries = jess.query_many(mols, *thr, devices=devices)
+        if isinstance(devices, str):
+            devices = [2, 5]
+        for m, q in enumerate(queries):
+            t, rows = q.hit_table()
+            assert [int(v) for v in t.molecule[rows]] == want[m][0] == [m] * len(rows)   # caller's numbering
+            assert [float(v) for v in t.rmsd[rows]] == want[m][1]
+            assert [(h.rmsd, h.template()) for h in q] == base[m][1]
+        assert sorted(i for _, ids in calls for i in ids) == list(range(len(mols)))          # a partition
+        assert {c for c, _ in calls} == set(devices)
+        assert len(calls) == len(devices) and all(ids == sorted(ids) for _, ids in calls)
+        if len(devices) > 1:
+            atoms = {d: sum(len(mols[i]) for c, ids in calls if c == d for i in ids) for d in devices}
+            assert max(atoms.values()) - min(atoms.values()) <= max(len(m) for m in mols)    # LPT balance
+        assert queries[0].stats["hits"] == table.count
+
+
+def test_best_match_with_single_atom_templates_is_selected_after_the_first_candidate_drop(monkeypatch):
+    """every single-atom tuple has RMSD 0, so an engine-side best_match keeps the first
+    record of the run -- the candidate the reference never reports.  The host must drop that
+    record FIRST and select afterwards (first of equal RMSDs in reference order)."""
+    import numpy as np
+    from pyjess_b200 import Jess, Template, synth
+    tpl, mols, thr, _ = synth.workload("cfg3", scale=0.01)
+    tpl = [Template(list(tpl[0])[:1], id="single"), tpl[1], Template(list(tpl[2])[:1], id="single2")]
+    table = _random_table(len(mols), 3, 600, 9)
+    table.rmsd[np.isin(table.template, (0, 2))] = 0.0
+    seen = {}
+
+    def spy(ctx, dev, batch, params, orig=None):
+        seen["best"], seen["order"] = params.best_match, params.hit_order
+        return orig(ctx, dev, batch, params)
+
+    from pyjess_b200 import _capi
+    _stub_engine(monkeypatch, mols, table)
+    orig = _capi.query_records
+    monkeypatch.setattr(_capi, "query_records", lambda *a: spy(*a, orig=orig))
+    got = [[(jess_t, h.rmsd, h._row) for h in q for jess_t in [tpl.index(h.template())]]
+           for q in Jess(tpl).query_many(mols, *thr, best_match=True, hit_order="canonical")]
+    assert seen == {"best": 0, "order": 1}          # host-side selection, reference record order
+    for m, hits in enumerate(got):
+        want = []
+        for t in (2, 1, 0):                          # reverse insertion order
+            rows = [i for i in range(table.count) if table.molecule[i] == m and table.template[i] == t]
+            if t != 1:
+                rows = rows[1:]                      # the reference never reports its first candidate
+            if rows:
+                best = min(rows, key=lambda i: (table.rmsd[i], i))
+                want.append((t, float(table.rmsd[best]), best))
+        assert hits == want
+
+
+def test_queries_of_one_batch_consumed_from_several_threads(monkeypatch):
+    """`pool.map(list, jess.query_many(...))` -- the first thread runs the engine, the
+    others must wait for it (not see a half-initialised run); an engine error is re-raised by
+    every consumer, not replaced by a TypeError."""
+    from multiprocessing.pool import ThreadPool
+    import pytest
+    from pyjess_b200 import Jess, _capi, synth
+    tpl, mols, thr, _ = synth.workload("cfg3", scale=0.02)
+    table = _random_table(len(mols), len(tpl), 500, 3)
+    jess = Jess(tpl)
+    _stub_engine(monkeypatch, mols, table, delay=0.05)
+    with ThreadPool(8) as pool:
+        counts = pool.map(lambda q: len(list(q)), jess.query_many(mols, *thr))
+    assert sum(counts) == table.count
+
+    def broken(*a):
+        raise _capi.EngineError(-3, "out of memory")
+
+    monkeypatch.setattr(_capi, "query_records", broken)
+    queries = jess.query_many(mols, *thr)
+    for q in queries[:3]:
+        with pytest.raises(_capi.EngineError):
+            next(q)
+
+
+def test_query_properties_settable_only_while_they_can_be_honoured(monkeypatch):
+    import pytest
+    from pyjess_b200 import Jess, synth
+    tpl, mols, thr, _ = synth.workload("cfg3", scale=0.01)
+    table = _random_table(len(mols), len(tpl), 50, 1)
+    _stub_engine(monkeypatch, mols, table)
+    jess = Jess(tpl)
+    q = jess.query(mols[0], *thr)
+    q.ignore_chain = "atoms"                         # before the first next(): reaches the engine run
+    assert q._run.args[3] == "atoms"
+    list(q)
+    q.ignore_chain = "atoms"                         # unchanged value: fine
+    with pytest.raises(RuntimeError):
+        q.ignore_chain = None
+    with pytest.raises(RuntimeError):
+        q.max_candidates = 3
+    with pytest.raises(ValueError):
+        q.ignore_chain = "all"
+    many = jess.query_many(mols, *thr)
+    with pytest.raises(RuntimeError):
+        many[0].ignore_chain = "residues"            # one query of a shared batch
+    with pytest.raises(ValueError):
+        jess.query_many(mols, *thr, hit_order="random")

@@ -278,3 +278,104 @@ def test_best_sites_equals_the_filter_script_on_the_dumped_hits(workload, all_in
     assert len(hits) == n_want and n_want > 0
     assert got.getvalue() == want.getvalue()
     assert all(h.template().id != h.molecule().id for h in hits)
+
+
+def _hit_keys(queries):
+    return [[(h.template().id, tuple(a.serial for a in h.atoms(False)), h.rmsd) for h in q] for q in queries]
+
+
+def test_device_coordinates_equal_the_host_transform():
+    """`coordinates=True` returns, per hit, the matched atoms transformed into the
+    template frame by the device (k_hit_coords: Hit.transformation + Atom._transform operation by
+    operation).  They must equal the host transform of the same hit (1e-9: numpy's 4x4 product may
+    contract differently), and `Hit.atoms` / `Hit.dump` must read them."""
+    from pyjess_b200 import synth
+    templates, mols, thr, _ = synth.workload("cfg3dense", scale=0.03)
+    jess = Jess(templates)
+    plain = jess.query_many(mols, *thr)
+    rich = jess.query_many(mols, *thr, coordinates=True)
+    n = 0
+    for qp, qr in zip(plain, rich):
+        table, rows = qr.hit_table()
+        assert table.coords is not None and table.coords.shape == (table.count, table.stride, 3)
+        hp, hr = list(qp), list(qr)
+        assert len(hp) == len(hr) == len(rows)
+        for a, b in zip(hp[:40], hr[:40]):
+            assert a.rmsd == b.rmsd
+            xa = np.asarray([[t.x, t.y, t.z] for t in a.atoms(transform=True)])
+            xb = np.asarray([[t.x, t.y, t.z] for t in b.atoms(transform=True)])
+            assert np.abs(xa - xb).max() <= 1e-9
+            assert np.array_equal(xb, table.coords[b._row, :len(b.template())])
+            assert a.dumps() == b.dumps()
+            n += 1
+        # padding columns of shorter templates are zero
+        k = np.asarray([len(templates[t]) for t in table.template[rows]])
+        for r, kk in zip(rows[:20], k[:20]):
+            assert not table.coords[r, kk:].any()
+    assert n > 100
+    # best_match compacts the coordinates together with the other columns
+    for qp, qr in zip(jess.query_many(mols[:10], *thr, best_match=True),
+                      jess.query_many(mols[:10], *thr, best_match=True, coordinates=True)):
+        for a, b in zip(list(qp), list(qr)):
+            xa = np.asarray([[t.x, t.y, t.z] for t in a.atoms(transform=True)])
+            xb = np.asarray([[t.x, t.y, t.z] for t in b.atoms(transform=True)])
+            assert a.rmsd == b.rmsd and np.abs(xa - xb).max() <= 1e-9
+
+
+def test_canonical_hit_order_is_the_same_set_in_tuple_order():
+    from pyjess_b200 import synth
+    templates, mols, thr, _ = synth.workload("cfg3dense", scale=0.03)
+    jess = Jess(templates)
+    ref = _hit_keys(jess.query_many(mols, *thr))
+    can = _hit_keys(jess.query_many(mols, *thr, hit_order="canonical"))
+    assert sum(map(len, ref)) > 200
+    for a, b in zip(ref, can):
+        assert sorted(a) == sorted(b)
+        assert [k[0] for k in a] == [k[0] for k in b]          # same template runs, reverse insertion order
+    assert any(a != b for a, b in zip(ref, can))               # ... and the order inside a run does differ
+
+
+def test_records_call_equals_the_packed_call_sliced_or_not(monkeypatch):
+    """`jb_query_records` (the engine packs the atom records itself, slice by slice behind the
+    kernels) == `jb_query_host` on the batch packed by the caller, whatever the slicing."""
+    from pyjess_b200 import _capi, synth
+    from pyjess_b200._tables import MoleculeBatch, TemplateTable, query_params
+    templates, mols, thr, kw = synth.workload("cfg3", scale=0.1)
+    mols = mols + [Molecule()]
+    ctx = _capi.default_context()
+    dev = _capi.DeviceTemplates(ctx, TemplateTable(templates))
+    for order in ("canonical", "reference"):
+        qp = query_params(*thr, hit_order=order, **kw)
+        want, _ = _capi.query_host(ctx, dev, MoleculeBatch(mols, serial=True), qp)
+        assert want.count > 50
+        for slices in ("1", "2", "5"):
+            monkeypatch.setenv("JB_PIPELINE", slices)
+            ctx2 = _capi.Context(0)                       # JB_PIPELINE is read when a context is created
+            dev2 = _capi.DeviceTemplates(ctx2, TemplateTable(templates))
+            for _ in range(2):                            # second call: staging and result blocks are re-used
+                got, _ = _capi.query_records(ctx2, dev2, mols, qp)
+                assert got.count == want.count
+                for a, b in zip(got.arrays(), want.arrays()):
+                    assert np.array_equal(a, b)
+            del got
+            dev2.close()
+            ctx2.close()
+    empty, _ = _capi.query_records(ctx, dev, [], query_params(*thr))
+    assert empty.count == 0
+    dev.close()
+
+
+def test_query_many_over_several_devices_equals_one_device():
+    """SURVEY 8e behind the drop-in API: structures dealt to the GPUs by atom count, one engine
+    context and host thread per GPU, per-device hit tables (nothing merged)."""
+    from pyjess_b200 import _capi, synth
+    if _capi.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    templates, mols, thr, _ = synth.workload("cfg3", scale=0.2)
+    jess = Jess(templates)
+    one = _hit_keys(jess.query_many(mols, *thr, devices=[0]))
+    for devices in ([0, 1], "all"):
+        queries = jess.query_many(mols, *thr, devices=devices)
+        assert _hit_keys(queries) == one
+        assert len(queries[0]._run.tables) >= 2
+    assert sum(map(len, one)) > 100

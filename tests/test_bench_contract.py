@@ -22,7 +22,9 @@ def test_reference_arm_prints_the_contract_line(oracle_lib):
     assert line["impl"] == "reference" and line["metric"] == "template-structure pairs/sec" and line["unit"] == "pairs/s"
     assert line["n_gpus"] == 1 and line["steps"] == 1 and line["warmup"] == 0 and line["higher_is_better"] is True
     assert line["scaling"] == "weak" and line["vs_baseline"] is None and line["dtype"] == "f64" and line["data"] == "synthetic"
-    assert line["config"]["workload"] == "cfg3" and line["config"]["templates"] == 1000 and line["config"]["structures"] == 6
+    assert line["config"]["workload"] == "cfg3" and line["config"]["templates"] == 1000
+    assert line["config"]["structures_per_gpu"] == 1000 and line["sample_structures"] == 6   # the arm's config; the sample is stated
+    assert line["engine_library_mapped"] is False          # inputs packed with numpy: the product's .so never enters this process
     assert line["value"] > 0 and line["ms_per_step"] > 0
     assert abs(line["value"] - 6000 / (line["ms_per_step"] / 1e3)) / line["value"] < 1e-6
     base = line["cpu_baseline"]

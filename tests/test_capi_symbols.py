@@ -26,7 +26,7 @@ def test_library_exports_every_symbol():
     for name in declared_functions():
         assert hasattr(lib, name), name
     lib.jb_abi_version.restype = ctypes.c_int
-    assert lib.jb_abi_version() == 2
+    assert lib.jb_abi_version() == 3
 
 
 def test_no_cpu_fallback_without_gpu():

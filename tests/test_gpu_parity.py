@@ -184,12 +184,14 @@ def test_short_templates_match_oracle(engine, oracle_lib, size):
                     assert abs(mine[k] - ours.rmsd[i]) <= TOL
 
 
-def test_small_workspace_splits_chunks_and_fails_loudly(engine):
+def test_small_workspace_splits_chunks_and_fails_loudly(engine, monkeypatch):
     """The frontier workspace is bounded (`workspace_bytes`): an overflowing chunk is re-run with
     larger buffers or split into smaller runs of structures -- same table -- and a single
-    structure that cannot fit raises JB_ERR_CAPACITY instead of truncating."""
+    structure that cannot fit raises JB_ERR_CAPACITY instead of truncating.  (Level-synchronous
+    sweep: the depth-first sweep of small chunks keeps no frontier, JB_DFS_PAIRS=0 turns it off.)"""
     from pyjess_b200 import _capi, synth
     from pyjess_b200._tables import query_params
+    monkeypatch.setenv("JB_DFS_PAIRS", "0")
     tpl, mols, thr, kw = synth.workload("cfg3dense", scale=0.05)
     tpl, mols = tpl[:5], mols[:24]
     params = query_params(*thr, **kw)
@@ -251,7 +253,7 @@ def test_candidate_record_overflow_is_retried(engine, oracle_lib, monkeypatch):
         assert np.array_equal(a, b)
 
 
-def test_context_trim_releases_buffers_and_runs_again(engine):
+def test_context_trim_releases_buffers_and_runs_again(engine, monkeypatch):
     """jb_context_trim: the grow-only device buffers go back to the driver, the next run
     re-allocates them and returns the same table; hits of a run that was not fetched before the
     trim are refused instead of being read from freed memory."""
@@ -273,11 +275,25 @@ def test_context_trim_releases_buffers_and_runs_again(engine):
     dev = _capi.DeviceTemplates(engine, TemplateTable(tpl))
     dmol = _capi.DeviceMolecules(engine, MoleculeBatch(mols))
     try:
+        # a small result already sits in its page-locked host block (k_hits_small): it survives the trim
+        res = _capi.query_run(engine, dev, dmol, params)
+        engine.trim()
+        assert base.count <= 1024                                 # kSmallHits
+        kept = res.fetch()
+        assert kept.count == base.count and np.array_equal(kept.rmsd, base.rmsd)
+        res.close()
+        # ... a result that still lives in the device buffers does not: refused, never garbage
+        monkeypatch.setenv("JB_ORDER_GENERAL", "1")
         res = _capi.query_run(engine, dev, dmol, params)
         engine.trim()
         with pytest.raises(_capi.EngineError, match="jb_context_trim"):
             res.fetch()
         res.close()
+        later = _capi.query_run(engine, dev, dmol, params)
+        _capi.query_run(engine, dev, dmol, params).close()
+        with pytest.raises(_capi.EngineError, match="later run"):
+            later.fetch()                                       # overwritten by the run after it (run epoch)
+        later.close()
         fresh = _capi.query_run(engine, dev, dmol, params).fetch()
         assert fresh.count == base.count
     finally:
@@ -365,3 +381,35 @@ def test_shell_boundary_candidates_take_the_exact_path(engine, oracle_lib, shift
             assert stats[key] == ostats[key], key
         mine = {k for k in table.keys() if k[1] == 3}
         assert mine == {k for k in ours.keys() if k[1] == 3} and len(mine) > 0
+
+
+@pytest.mark.parametrize("workload,scale", [("cfg3", 0.05), ("cfg3dense", 0.04), ("cfg5", 0.012)])
+def test_depth_first_sweep_equals_level_sweep(workload, scale, monkeypatch):
+    """Small chunks take ONE depth-first launch (expand_dfs.cuh) instead of one launch per level:
+    same hit table, same algorithm-independent work counters, all three ignore_chain modes and
+    both scan orders; with single-atom templates in the set (a root is a complete tuple)."""
+    from pyjess_b200 import Template, _capi, synth
+    from pyjess_b200._tables import query_params
+    tpl, mols, thr, kw = synth.workload(workload, scale=scale)
+    tpl = list(tpl)[:40] + [Template(list(tpl[0])[:1], id="single"), Template(list(tpl[1])[:2], id="pair")]
+    mols = mols[:3]
+    ctxs = {}
+    for name, pairs in (("bfs", "0"), ("dfs", "1000000")):
+        monkeypatch.setenv("JB_DFS_PAIRS", pairs)
+        ctxs[name] = _capi.Context(0)
+    try:
+        for ignore in (None, "residues", "atoms"):
+            for reorder in (2, 0):
+                kw2 = dict(kw, ignore_chain=ignore)
+                params = query_params(*thr, reorder=reorder, all_tuples=True, **kw2)
+                got = {name: run_engine(c, tpl, mols, params) for name, c in ctxs.items()}
+                (ta, sa), (tb, sb) = got["bfs"], got["dfs"]
+                assert ta.count == tb.count > 0
+                for a, b in zip(ta.arrays(), tb.arrays()):       # (every tuple: rank-deficient ones carry NaN rotations)
+                    assert np.array_equal(a, b, equal_nan=a.dtype.kind == "f")
+                for key in ("live_pairs", "candidate_atoms", "candidate_tests", "frontier_items", "frontier_ints", "tuples", "hits"):
+                    assert sa[key] == sb[key], key
+                assert sb["launches"] < sa["launches"]
+    finally:
+        for c in ctxs.values():
+            c.close()

@@ -67,7 +67,13 @@ def _worker(rank, world, port, out):
         mols = cfg2_molecules()[:16]
         merged = sharding.query_sharded(lambda ms: _scan(templates, ms), mols, rank, world)
         if rank == 0:
-            _same(merged, _scan(templates, mols))
+            whole = _scan(templates, mols)
+            assert merged.count == whole.count and merged.checksum() == sharding.ShardedHits([whole], [np.arange(len(mols))]).checksum()
+            for m in range(len(mols)):                       # the per-structure index points at the right records
+                t, lo, hi = merged.of(m)
+                assert hi - lo == int((whole.molecule == m).sum())
+                assert np.array_equal(t.rmsd[lo:hi], whole.rmsd[whole.molecule == m])
+            _same(merged.merged(), whole)
             out.put(("ok", merged.count))
         else:
             assert merged is None

@@ -37,6 +37,10 @@ for step in "$@"; do
       ncu --set full --clock-control none --import-source on -k regex:$regex -s ${skip:-0} -c ${count:-3} -f -o gpurun_out/${TAG}_ncu_$n \
           python bench.py --steps 1 --warmup 3 --no-cpu-baseline ${args//,/ } > gpurun_out/${TAG}_ncu_$n.log 2>&1
       echo "[run] ncu rc=$?"; ls -la gpurun_out/${TAG}_ncu_$n.ncu-rep;;
+    nculist)   # nculist:SCRIPT[:ARGS]  per-launch durations of any probe script
+      script=${rest%%:*}; args=""; [[ "$rest" == *:* ]] && args=${rest#*:}
+      ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_nculist_$n.csv \
+          python $script ${args//,/ } > gpurun_out/${TAG}_nculist_$n.log 2>&1; echo "[run] nculist rc=$?"; wc -l gpurun_out/${TAG}_nculist_$n.csv;;
     py)
       script=${rest%%:*}; args=""; [[ "$rest" == *:* ]] && args=${rest#*:}
       python $script ${args//,/ } > gpurun_out/${TAG}_py_$n.log 2>&1; echo "[run] $script rc=$?"; tail -40 gpurun_out/${TAG}_py_$n.log;;

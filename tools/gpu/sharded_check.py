@@ -29,6 +29,7 @@ for name, tpl, mols, thr, kw in cases:
     run = lambda ms: _capi.query_host(ctx, dev, MoleculeBatch(ms), params)[0]      # noqa: E731
     merged = sharding.query_sharded(run, mols, rank, world)
     if rank == 0:
+        merged = merged.merged()
         whole = run(mols)
         same = merged.count == whole.count and all(np.array_equal(a, b) for a, b in zip(merged.arrays(), whole.arrays()))
         print(f"{name}: {world} ranks, merged {merged.count} hits, single GPU {whole.count} hits, identical={same}", flush=True)
