@@ -208,13 +208,43 @@ def parity_report(gpu, cpu, rmsd_threshold, templates, mols, gpu_rows=None):
     kc, oc = _sorted_view(cpu)
     out = {"against": "unmodified reference C library (oracle/_ref)", "hits_gpu": int(len(kg)), "hits_reference": int(len(kc)),
            "tolerance": TOL}
-    edge = int((np.abs(gpu.rmsd[og] - rmsd_threshold) <= TOL).sum() + (np.abs(cpu.rmsd[oc] - rmsd_threshold) <= TOL).sum())
-    out["threshold_edge"] = edge
-    if kg.shape != kc.shape or not np.array_equal(kg, kc):
-        sg, sc = {tuple(r) for r in kg.tolist()}, {tuple(r) for r in kc.tolist()}
-        out.update(keys="MISMATCH", only_gpu=len(sg - sc), only_reference=len(sc - sg))
-        return out
+    # north_star: "any hit lying within that tolerance of rmsd_threshold is listed separately" -- such a hit may
+    # legitimately sit on either side (the two math libraries differ in the last bits of atan2 / sin / cos)
+    eg, ec = np.abs(gpu.rmsd[og] - rmsd_threshold) <= TOL, np.abs(cpu.rmsd[oc] - rmsd_threshold) <= TOL
+    out["threshold_edge"] = int(eg.sum() + ec.sum())
+    if out["threshold_edge"]:
+        out["threshold_edge_hits"] = ([{"side": "gpu", "key": kg[i].tolist(), "rmsd": float(gpu.rmsd[og[i]])} for i in np.nonzero(eg)[0][:8]]
+                                      + [{"side": "reference", "key": kc[i].tolist(), "rmsd": float(cpu.rmsd[oc[i]])} for i in np.nonzero(ec)[0][:8]])
+        kg, og, kc, oc = kg[~eg], og[~eg], kc[~ec], oc[~ec]
     out["keys"] = "identical"
+    if kg.shape != kc.shape or not np.array_equal(kg, kc):
+        # One-sided hits are tolerated in ONE case, and counted: a rank-deficient superposition (sigma_min / sigma_max
+        # of the 3x3 covariance below 1e-7, i.e. the smallest eigenvalue of X^T X -- which Super.c:417-538 takes the
+        # square root of -- is rounding noise of either sign).  The reference then reports a garbage rotation
+        # (|det R| far from 1) or drops the hit for its NaN (_jess.pyx:2240-2251), whichever its libm's last bits
+        # decide; the engine enumerates the same tuple (the tuple counters are exact) and decides on ITS noise.
+        width = kg.shape[1]
+        vg = np.ascontiguousarray(kg).view([("", kg.dtype)] * width).reshape(-1)
+        vc = np.ascontiguousarray(kc).view([("", kc.dtype)] * width).reshape(-1)
+        in_c, in_g = np.isin(vg, vc), np.isin(vc, vg)
+        odd, deficient = [], 0
+        for side, keys_, mask in (("gpu", kg, ~in_c), ("reference", kc, ~in_g)):
+            for row in keys_[mask].tolist():
+                tpl = templates[row[1]]
+                n = len(tpl)
+                x = mols[row[0]]._atoms["x"][np.asarray(row[2:2 + n])]
+                y = np.array([a._pos for a in tpl], dtype=np.float64)
+                sv = np.linalg.svd((x - x.mean(0)).T @ (y - y.mean(0)), compute_uv=False)
+                if sv[-1] <= 1e-7 * sv[0]:
+                    deficient += 1
+                else:
+                    odd.append({"side": side, "key": row})
+        out.update(only_gpu=int((~in_c).sum()), only_reference=int((~in_g).sum()), rank_deficient_one_sided=deficient)
+        if odd:
+            out.update(keys="MISMATCH", unexplained=odd[:8])
+            return out
+        out["keys"] = "identical up to rank-deficient superpositions (listed: rank_deficient_one_sided)"
+        kg, og, kc, oc = kg[in_c], og[in_c], kc[in_g], oc[in_g]
     d_rmsd = np.abs(gpu.rmsd[og] - cpu.rmsd[oc])
     d_rot = np.abs(gpu.rotation[og] - cpu.rotation[oc]).reshape(len(og), -1).max(axis=1) if len(og) else np.zeros(0)
     d_cen = max(float(np.abs(gpu.centre0[og] - cpu.centre0[oc]).max(initial=0.0)),
@@ -487,6 +517,70 @@ def run_single_gpu_config(args, env, name, cpu_structures):
     return out
 
 
+def run_latency_configs(args, env):
+    """BASELINE configs 1 and 2 (LATENCY datapoints, N=1 line only): the reference's README example
+    (3 vendor templates x pdb1a0p, 3 pairs) through `Jess.query`, and the 3 templates x the 132 vendor
+    structures through `Jess.query_many` -- wall clock per call, next to the reference C library on the
+    same inputs (one thread and all host cores)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _util import cfg2_molecules, golden_cases, load_molecule, load_template
+    from pyjess_b200 import Jess
+    from pyjess_b200._tables import TemplateTable, query_params
+    tpl = [load_template(f"template_0{i}.qry") for i in (1, 2, 3)]
+    jess = Jess(tpl)
+    thr = (2.0, 3.0, 3.0)
+    out = {}
+
+    def wall(fn, reps):
+        for _ in range(70):      # past the context's buffer-decay check (every 64 calls): the big buffers of the
+            fn()                 # earlier workloads are released once, not inside the timed repetitions
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return (time.perf_counter() - t0) / reps * 1e3
+
+    def cpu(mols, threads, reps):
+        import oracle
+        kind, fn = reference_fn()
+        tt, mb, qp = TemplateTable(tpl), oracle.numpy_batch(mols), query_params(*thr)
+        best, hits = 1e30, None
+        for _ in range(reps):
+            hits, st = fn(tt, mb, qp, threads=threads)
+            best = min(best, st["kernel_ms"]) if kind == "reference" else best
+        return best, int(hits.count), kind
+
+    mol = load_molecule("pdb1a0p.ent")
+    hits = list(jess.query(mol, *thr))
+    gold = golden_cases()["cfg1_examples_1a0p"]
+    ok = len(hits) == gold["n_hits"] and all(abs(h.rmsd - g["rmsd"]) <= TOL for h, g in zip(hits, gold["hits"]))
+    run = jess.query(mol, *thr)
+    list(run)
+    c1 = {"workload": "cfg1: 3 vendor templates x pdb1a0p (README example), 3 pairs", "thresholds": list(thr),
+          "call": "list(Jess(templates).query(molecule, 2.0, 3.0, 3.0))",
+          "wall_ms_per_query": wall(lambda: list(jess.query(mol, *thr)), 300),
+          "wall_ms_per_query_canonical_order": wall(lambda: list(jess.query(mol, *thr, hit_order="canonical")), 300),
+          "kernel_launches_per_query": int(run._run.stats["launches"]), "hits": len(hits),
+          "parity": "identical to the reference's golden hit (RMSD within 1e-6)" if ok else "MISMATCH"}
+    mols = list(cfg2_molecules())
+    tables = jess.query_many(mols, *thr)
+    n2 = sum(len(q.hit_table()[1]) for q in tables)
+    c2 = {"workload": "cfg2: 3 vendor templates x the 132 vendor structures, 396 pairs", "thresholds": list(thr),
+          "call": "Jess(templates).query_many(molecules, 2.0, 3.0, 3.0)[0].hit_table()",
+          "wall_ms_per_batch": wall(lambda: jess.query_many(mols, *thr)[0].hit_table(), 50),
+          "wall_ms_per_batch_canonical_order": wall(lambda: jess.query_many(mols, *thr, hit_order="canonical")[0].hit_table(), 50),
+          "hits": n2, "parity": "97 hits as the reference" if n2 == golden_cases()["cfg2_examples_all"]["n_hits"] else "MISMATCH"}
+    if not args.no_cpu_baseline:
+        ms1, h1, kind = cpu([mol], 1, 20)
+        c1["cpu_baseline"] = {"wall_ms_per_query": ms1, "cores": 1, "kind": kind, "hits": h1,
+                              "sample": "the same 3 pairs, query loops only, best of 20"}
+        ms2, h2, kind = cpu(mols, 1, 3)
+        ms2n, _, _ = cpu(mols, host_cores(), 3)
+        c2["cpu_baseline"] = {"wall_ms_per_batch_1_core": ms2, "wall_ms_per_batch_all_cores": ms2n, "cores": host_cores(),
+                              "kind": kind, "hits": h2, "sample": "the same 396 pairs, query loops only, best of 3"}
+    out["cfg1"], out["cfg2"] = c1, c2
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -501,8 +595,9 @@ def main():
                     help="--impl reference: host seconds the (steps + warmup) steps may take in total")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--configs", default="auto",
-                    help="further BASELINE configs reported in the line's `configs` object: comma list of cfg4,cfg5, "
-                         "`none`, or `auto` (cfg4 strong-scaled over the ranks + cfg5 at N=1 when --workload is cfg3)")
+                    help="further BASELINE configs reported in the line's `configs` object: comma list of cfg4,cfg5,latency, "
+                         "`none`, or `auto` (cfg4 strong-scaled over the ranks; at N=1 also cfg5 and the cfg1/cfg2 latencies; "
+                         "when --workload is cfg3)")
     ap.add_argument("--cfg4-structures", type=int, default=6250, help="size of the fixed cfg 4 set that is strong-scaled")
     ap.add_argument("--cfg4-cpu-structures", type=int, default=150)
     ap.add_argument("--config-steps", type=int, default=3)
@@ -519,7 +614,7 @@ def main():
     if args.cpu_structures <= 0:
         args.cpu_structures = {"cfg2": 132, "cfg3": 1000, "cfg3dense": 1000, "cfg4shard": 300, "cfg5": 60}.get(args.workload, 100)
     if args.configs == "auto":
-        extra = ["cfg4", "cfg5"] if (args.workload == "cfg3" and args.scale == 1.0) else []
+        extra = ["cfg4", "cfg5", "latency"] if (args.workload == "cfg3" and args.scale == 1.0) else []
     else:
         extra = [c for c in args.configs.split(",") if c and c != "none"]
 
@@ -717,6 +812,8 @@ def main():
             configs["cfg4"] = configs_cfg4
     if "cfg5" in pre and rank == 0:
         configs["cfg5"] = run_single_gpu_config(args, env, "cfg5", 6)
+    if "latency" in extra and rank == 0 and world == 1:
+        configs.update(run_latency_configs(args, env))
     if rank == 0:
         if configs:
             out["configs"] = configs

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libjess_b200.so")
 SOURCES = ["capi.cu", "ingest.cu"]
-HEADERS = ["kernels.cuh", "expand_lv.cuh", "expand_grid.cuh", "expand_dfs.cuh", "hits.cuh", "order.cuh", os.path.join("..", "..", "include", "jess_b200.h")]
+HEADERS = ["kernels.cuh", "expand_lv.cuh", "expand_grid.cuh", "expand_dfs.cuh", "prepare_small.cuh", "hits.cuh", "order.cuh", os.path.join("..", "..", "include", "jess_b200.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",

@@ -29,7 +29,7 @@ from typing import Iterable, List, Optional, Sequence
 import numpy as np
 
 from ._model import Atom, Mat4, Molecule, Template, _format_atom, _transform_points
-from ._tables import HitTable, MoleculeBatch, TemplateTable, query_params
+from ._tables import JB_MAX_TEMPLATE_ATOMS, HitTable, TemplateTable, query_params
 
 __all__ = ["Jess", "Query", "Hit"]
 
@@ -574,6 +574,14 @@ class Jess:
         # the engine works on its own packed copy: later edits of the Template
         # objects cannot affect it (the reference deep-copies, _jess.pyx:2703-2707)
         self._table = TemplateTable(self._templates)
+        # The one documented limit of the GPU path (include/jess_b200.h: JB_MAX_TEMPLATE_ATOMS): the scan
+        # order and spec list of a (structure, template) pair live in one 128-byte record.  The reference
+        # has no limit (Template.__init__, _jess.pyx:1825-1912); M-CSA / EnzyMM catalytic-site templates
+        # hold 3 atoms x 3-8 residues.  Refused here, loudly, rather than at the first next().
+        if self._table.max_atoms > JB_MAX_TEMPLATE_ATOMS:
+            big = next(i for i, t in enumerate(self._templates) if len(t) > JB_MAX_TEMPLATE_ATOMS)
+            raise ValueError(f"template {big} has {len(self._templates[big])} atoms; the B200 engine supports at most "
+                             f"{JB_MAX_TEMPLATE_ATOMS} atoms per template")
         self._device = {}
         self._device_lock = threading.Lock()
 

@@ -25,6 +25,7 @@
 #include "expand_dfs.cuh"
 #include "hits.cuh"
 #include "order.cuh"
+#include "prepare_small.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <nvtx3/nvToolsExt.h>   // header-only: ranges are no-ops unless a profiler is attached
 
@@ -605,6 +606,7 @@ static int prepare_molecules(jb_context *c, jb_molecules *m, cudaStream_t st)
     for (int i = 0; i < M; i++) amax_all = std::max(amax_all, m->atom_off[i + 1] - m->atom_off[i]);
     // small batches: the sort kernel builds the 32-byte records of its structure itself (one launch less)
     const bool fused_pack = M > 0 && M <= 64 && amax_all <= 16384;
+    const bool radix_small = fused_pack && amax_all <= 8 * kPrepThreads && !getenv("JB_NO_SMALL_PREPARE");
     if (e == cudaSuccess && m->NA > 0 && !fused_pack) {
         k_pack_atoms<<<(unsigned)((m->NA + 255) / 256), 256, 0, st>>>(m->NA, m->x.as<double>(), m->y.as<double>(),
                                                                      m->z.as<double>(), m->resseq.as<int>(),
@@ -616,7 +618,19 @@ static int prepare_molecules(jb_context *c, jb_molecules *m, cudaStream_t st)
     if (e == cudaSuccess) e = m->sname.ensure(std::max<size_t>((size_t)m->NA, 1) * sizeof(uint32_t), st);
     if (e == cudaSuccess) e = m->sres.ensure(std::max<size_t>((size_t)m->NA, 1) * sizeof(uint32_t), st);
     if (e == cudaSuccess) e = m->ext.ensure(std::max<size_t>((size_t)M, 1) * sizeof(MolExt), st);
-    if (e == cudaSuccess && M > 0) {
+    if (e == cudaSuccess && radix_small) {
+        // latency path: records + frame + x-sorted view by one block radix sort per structure (prepare_small.cuh)
+        const RawAtoms raw{ m->x.as<double>(), m->y.as<double>(), m->z.as<double>(), m->resseq.as<int>(), m->chain.as<unsigned char>() };
+        if (amax_all <= 4 * kPrepThreads)
+            k_prepare_small<4><<<M, kPrepThreads, 0, st>>>(m->d_off.as<long long>(), m->atoms.as<AtomRec>(), m->name.as<uint32_t>(),
+                                                          m->res.as<uint32_t>(), m->ext.as<MolExt>(), m->srec.as<float4>(),
+                                                          m->sname.as<uint32_t>(), m->sres.as<uint32_t>(), raw);
+        else
+            k_prepare_small<8><<<M, kPrepThreads, 0, st>>>(m->d_off.as<long long>(), m->atoms.as<AtomRec>(), m->name.as<uint32_t>(),
+                                                          m->res.as<uint32_t>(), m->ext.as<MolExt>(), m->srec.as<float4>(),
+                                                          m->sname.as<uint32_t>(), m->sres.as<uint32_t>(), raw);
+        e = cudaGetLastError();
+    } else if (e == cudaSuccess && M > 0) {
         long long amax = 0;
         for (int i = 0; i < M; i++) amax = std::max(amax, m->atom_off[i + 1] - m->atom_off[i]);
         if (amax > 16384 && m->NA < (1ll << 32)) {
@@ -958,7 +972,12 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
 
     const int tuple_stride = t->nmax + 1;
     // k_classify: [warps][S] counters + (when it fits) the class set and its spec masks
-    const size_t cnt_bytes = ((size_t)8 * t->S + 1) / 2 * 2 * sizeof(int);
+    // (a handful of structures: 32 warps per CTA instead of 8 -- the (class, spec) evaluations of ONE structure are the
+    // critical path of a single-structure query, 66 -> ~20 us)
+    int classify_threads = 256;
+    if (mol->M <= 32 && ((size_t)32 * t->S + 2) * sizeof(int) + (size_t)kClassSlots * (sizeof(u64) + (size_t)((t->S + 31) / 32) * sizeof(unsigned)) <= 96 * 1024)
+        classify_threads = 1024;
+    const size_t cnt_bytes = ((size_t)(classify_threads / 32) * t->S + 1) / 2 * 2 * sizeof(int);
     if (cnt_bytes > 200 * 1024 || t->S > 65535)
         return fail(JB_ERR_INVALID, "%d distinct atom specs exceed the classify kernel's shared memory", t->S);
     int class_words = (t->S + 31) / 32;
@@ -1039,7 +1058,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
 
         CU(cudaEventRecord(c->evs[0], st));
         nvtxRangePushA("jb:candidate lists (k_classify, k_xindex, k_binindex)");
-        k_classify<<<Mc, 256, classify_smem, st>>>(MT, ST, CT, dc, class_words);   // + the x index of its lists (K1b)
+        k_classify<<<Mc, classify_threads, classify_smem, st>>>(MT, ST, CT, dc, class_words);   // + the x index of its lists (K1b)
         // small chunks: ONE depth-first launch instead of one launch per level (expand_dfs.cuh); it reads the lists directly
         const bool dfs = !c->legacy && pairs <= c->dfs_pairs;
         if (c->sweep && !dfs) k_binindex<<<c->sm_count * 8, 256, 0, st>>>(CT, dc);
@@ -1047,16 +1066,24 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         CU(cudaEventRecord(c->evs[1], st));
         nvtxRangePop();
         nvtxRangePushA("jb:pair set-up (k_order, k_pairs)");
-        if (q->reorder == 2) {
+        const bool pairs_small = dfs && !getenv("JB_NO_SMALL_PREPARE");
+        if (pairs_small) {
+            // latency path: scan order + pair record by one warp per pair (prepare_small.cuh)
+            k_pairs_small<<<(unsigned)((pairs + kPairWarps - 1) / kPairWarps), kPairWarps * 32, 0, st>>>(
+                Mc, TT, t->S, CT.head, MT.atom_off, q->reorder, c->recs.as<PairRec>(), dc);
+            CU(cudaGetLastError());
+        } else if (q->reorder == 2) {
             CU(c->ordbuf.ensure((size_t)pairs * kMaxN, st));
             k_order<<<dim3((unsigned)t->T, (unsigned)((Mc + 127) / 128)), 128, 0, st>>>(
                 Mc, TT, t->S, CT.head, MT.atom_off, c->ordbuf.as<unsigned char>());
             CU(cudaGetLastError());
             S.launches++;
         }
-        k_pairs<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(Mc, TT, t->S, CT.head, MT.atom_off, q->reorder,
-                                                                 c->ordbuf.as<unsigned char>(), c->recs.as<PairRec>(), dc);
-        CU(cudaGetLastError());
+        if (!pairs_small) {
+            k_pairs<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(Mc, TT, t->S, CT.head, MT.atom_off, q->reorder,
+                                                                     c->ordbuf.as<unsigned char>(), c->recs.as<PairRec>(), dc);
+            CU(cudaGetLastError());
+        }
         CU(cudaEventRecord(c->evs[2], st));
         nvtxRangePop();
         nvtxRangePushA("jb:frontier sweep (k_expand_grid per level) + k_superpose");

@@ -454,7 +454,7 @@ __device__ __forceinline__ unsigned class_hash(uint32_t name, uint32_t res_up)
 
 __device__ __forceinline__ void xindex_list(const long long L, const int lane, const CandTable &C);
 
-__global__ void __launch_bounds__(256) k_classify(MolTable M, SpecTable S, CandTable C, Counters *ctr, int class_words)
+__global__ void __launch_bounds__(1024) k_classify(MolTable M, SpecTable S, CandTable C, Counters *ctr, int class_words)
 {
     extern __shared__ int sh_cnt[];                 // [warps][S], then the class set and its masks
     __shared__ int sh_fill;

@@ -349,3 +349,16 @@ def test_query_properties_settable_only_while_they_can_be_honoured(monkeypatch):
         many[0].ignore_chain = "residues"            # one query of a shared batch
     with pytest.raises(ValueError):
         jess.query_many(mols, *thr, hit_order="random")
+
+
+def test_templates_beyond_the_engine_limit_are_refused_at_construction():
+    """the reference accepts templates of any size; the engine's pair record holds
+    32 atoms (JB_MAX_TEMPLATE_ATOMS).  n = 32 is accepted, n = 33 raises when the Jess is built --
+    with the template's index and size in the message -- never silently truncated."""
+    import pytest
+    from pyjess_b200 import Jess, Template, TemplateAtom
+    atoms = [TemplateAtom(chain_id="A", residue_number=1 + k // 3, x=1.5 * k, y=0.3 * k, z=0.0, residue_names=["GLY"],
+                          atom_names=["CA"], distance_weight=0.0, match_mode=0) for k in range(33)]
+    assert len(Jess([Template(atoms[:32], id="ok")])) == 1
+    with pytest.raises(ValueError, match="template 1 has 33 atoms.*at most 32"):
+        Jess([Template(atoms[:5], id="small"), Template(atoms, id="big")])

@@ -1,6 +1,8 @@
 """GPU parity tests proper: the CUDA engine, called through the C ABI, against
 (a) the reference's golden vectors and (b) the CPU oracle on the same inputs.
 Hit key sets must be bit-exact; RMSD / rotation / centroids within TOL = 1e-6."""
+import os
+
 import numpy as np
 import pytest
 
@@ -399,7 +401,7 @@ def test_depth_first_sweep_equals_level_sweep(workload, scale, monkeypatch):
         ctxs[name] = _capi.Context(0)
     try:
         for ignore in (None, "residues", "atoms"):
-            for reorder in (2, 0):
+            for reorder in (2, 1, 0):
                 kw2 = dict(kw, ignore_chain=ignore)
                 params = query_params(*thr, reorder=reorder, all_tuples=True, **kw2)
                 got = {name: run_engine(c, tpl, mols, params) for name, c in ctxs.items()}
@@ -413,3 +415,41 @@ def test_depth_first_sweep_equals_level_sweep(workload, scale, monkeypatch):
     finally:
         for c in ctxs.values():
             c.close()
+
+
+@pytest.mark.parametrize("workload,scale,kwargs", [
+    ("cfg3dense", 0.5, {}),                       # 50 templates x 500 structures, dense-hit thresholds: 2.2 M hits
+    ("cfg4shard", 0.2, {}),                       # 200 templates x 1,250 structures of 300-1,500 residues
+    ("cfg5", 0.2, {"ignore_chain": None}),        # 200 24-atom weighted templates x 50 tetramers
+    ("cfg5", 0.1, {"ignore_chain": "residues"}),
+    ("cfg5", 0.1, {"ignore_chain": "atoms"}),
+])
+def test_large_samples_match_the_unmodified_reference_library(engine, workload, scale, kwargs):
+    """VERDICT r1 (parity, item 1): the BASELINE shapes at the largest scale the reference's CPU path
+    finishes in ~10-30 s, against oracle/_ref (the UNMODIFIED reference C library, not the port):
+    hit key sets bit-exact, RMSD / rotation / centroids within 1e-6, ill-conditioned superpositions
+    and threshold-edge hits counted separately (bench.parity_report -- the same check the bench line
+    carries for its timed result)."""
+    import oracle
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref/libjess_ref.so not built")
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import parity_report
+    from pyjess_b200 import synth
+    from pyjess_b200._tables import query_params
+    tpl, mols, thr, kw = synth.workload(workload, scale=scale)
+    kw = dict(kw, **kwargs)
+    params = query_params(*thr, **kw)
+    got, _ = run_engine(engine, tpl, mols, params)
+    want, _ = oracle.ref_query(TemplateTable(tpl), oracle.numpy_batch(mols), params, threads=len(os.sched_getaffinity(0)))
+    rep = parity_report(got, want, thr[0], tpl, mols)
+    print(rep)
+    assert rep["keys"].startswith("identical") and rep["values"] == "within tolerance", rep
+    assert rep["hits_reference"] > 1000
+    # listed separately, and rare: one-sided rank-deficient superpositions (found by this very test at scale 1.0: 1 of 8,953,863
+    # cfg3dense hits, sigma_min / sigma_max = 4e-9, the reference's own rotation there has det R = 4.07),
+    # ill-conditioned rotations, hits within 1e-6 of the RMSD threshold
+    assert rep.get("rank_deficient_one_sided", 0) <= 1e-5 * rep["hits_reference"] + 1, rep
+    assert rep["ill_conditioned"] <= 0.01 * rep["hits_gpu"], rep
+    assert rep["threshold_edge"] <= 1e-5 * rep["hits_reference"] + 2, rep

@@ -41,6 +41,8 @@ for step in "$@"; do
       script=${rest%%:*}; args=""; [[ "$rest" == *:* ]] && args=${rest#*:}
       ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_nculist_$n.csv \
           python $script ${args//,/ } > gpurun_out/${TAG}_nculist_$n.log 2>&1; echo "[run] nculist rc=$?"; wc -l gpurun_out/${TAG}_nculist_$n.csv;;
+    fp64)      # measured FP64 throughput (roofline denominator of k_superpose)
+      nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o /tmp/fp64_peak tools/gpu/fp64_peak.cu && /tmp/fp64_peak | tee gpurun_out/${TAG}_fp64.json;;
     py)
       script=${rest%%:*}; args=""; [[ "$rest" == *:* ]] && args=${rest#*:}
       python $script ${args//,/ } > gpurun_out/${TAG}_py_$n.log 2>&1; echo "[run] $script rc=$?"; tail -40 gpurun_out/${TAG}_py_$n.log;;
