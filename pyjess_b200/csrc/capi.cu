@@ -141,6 +141,7 @@ struct jb_context {
     DevBuf k_key, k_key2, k_iota, k_runid, k_scan;             // keyed hit ordering (hits.cuh)
     DevBuf h_pair, h_keys;                                     // reference-order mode: pair of each hit, rank vectors
     DevBuf q_ocnt, q_keyA, q_keyA2, q_keyB, q_keyB2, q_iota, q_perm, q_setpos, q_kdrank, q_coords, q_kdidx, q_cub;
+    DevBuf q_need, q_pairhits;                                 // reference order: lists whose ranks are read, hits per pair
     RunWork *host_work = nullptr;                              // pinned
     std::vector<std::pair<void *, size_t>> pin_pool;           // page-locked result blocks, recycled
     std::mutex pool_mu;                                        // jb_result_free may run on another thread than a query
@@ -308,7 +309,7 @@ static std::vector<DevBuf *> context_buffers(jb_context *c)
              &c->o_off, &c->o_fill, &c->o_grouped, &c->o_order, &c->o_tiles, &c->o_runs,
              &c->k_key, &c->k_key2, &c->k_iota, &c->k_runid, &c->k_scan, &c->h_pair, &c->h_keys, &c->q_ocnt, &c->q_keyA,
              &c->q_keyA2, &c->q_keyB, &c->q_keyB2, &c->q_iota, &c->q_perm, &c->q_setpos, &c->q_kdrank, &c->q_coords,
-             &c->q_kdidx, &c->q_cub };
+             &c->q_kdidx, &c->q_cub, &c->q_need, &c->q_pairhits };
 }
 
 static void context_trim(jb_context *c)
@@ -856,7 +857,20 @@ static int build_reference_keys(jb_context *c, const jb_templates *t, const jb_m
     CU(c->q_ocnt.ensure((size_t)(nl + 1) * sizeof(unsigned), st));
     CU(c->o_tiles.ensure((size_t)n_tiles * sizeof(unsigned), st));
     unsigned *ooff = c->q_ocnt.as<unsigned>();
-    k_olist_count<<<(unsigned)((nl + 1 + 255) / 256), 256, 0, st>>>(Mc, O, t->S, CT.head, ooff);
+    // only the lists of pairs holding two or more hits (order.cuh)
+    const long long n_pairs = (long long)Mc * t->T;
+    CU(c->q_need.ensure((size_t)(nl + 1), st));
+    CU(c->q_pairhits.ensure((size_t)n_pairs * sizeof(unsigned), st));
+    CU(cudaMemsetAsync(c->q_need.p, 0, (size_t)(nl + 1), st));
+    CU(cudaMemsetAsync(c->q_pairhits.p, 0, (size_t)n_pairs * sizeof(unsigned), st));
+    {
+        const unsigned hb = (unsigned)((h1 - h0 + 255) / 256);
+        k_pair_hits<<<hb, 256, 0, st>>>(h0, h1, c->h_pair.as<int>(), c->q_pairhits.as<unsigned>());
+        k_mark_lists<<<hb, 256, 0, st>>>(h0, h1, c->h_pair.as<int>(), c->q_pairhits.as<unsigned>(), c->recs.as<PairRec>(), O,
+                                         c->q_need.as<unsigned char>());
+        S.launches += 2;
+    }
+    k_olist_count<<<(unsigned)((nl + 1 + 255) / 256), 256, 0, st>>>(Mc, O, t->S, CT.head, c->q_need.as<unsigned char>(), ooff);
     k_scan_tiles<<<n_tiles, kScanThreads, 0, st>>>(ooff, nl + 1, c->o_tiles.as<unsigned>());
     k_scan_totals<<<1, kScanThreads, 0, st>>>(c->o_tiles.as<unsigned>(), n_tiles);
     k_scan_add<<<n_tiles, kScanThreads, 0, st>>>(ooff, nl + 1, c->o_tiles.as<unsigned>());
@@ -874,7 +888,8 @@ static int build_reference_keys(jb_context *c, const jb_templates *t, const jb_m
         CU(c->q_coords.ensure(n * 3 * sizeof(double), st)); CU(c->q_kdidx.ensure(n * sizeof(int), st));
         k_olist_fill<<<(unsigned)((nl * 32 + 255) / 256), 256, 0, st>>>(
             Mc, O, t->S, CT.head, CT.rec, MT.atom_off, mol->res.as<uint32_t>(),
-            mol->has_serial ? mol->serial.as<int>() : nullptr, ooff, c->q_keyA.as<u64>(), c->q_keyB.as<u64>());
+            mol->has_serial ? mol->serial.as<int>() : nullptr, ooff, c->q_need.as<unsigned char>(), c->q_keyA.as<u64>(),
+            c->q_keyB.as<u64>());
         CU(cudaGetLastError());
         int list_bits = 1;
         while ((1ll << list_bits) < nl) list_bits++;

@@ -56,14 +56,33 @@ __global__ void __launch_bounds__(256) k_iota(unsigned *v, long long n)
     if (i < n) v[i] = (unsigned)i;
 }
 
+// The rank tables are only read for hits that SHARE their (structure, template) pair with another hit -- alone in its
+// pair a hit needs no order.  k_pair_hits counts the hits of every pair, k_mark_lists flags the lists of the pairs with
+// two or more; the lists nobody asks for stay empty (sparse results -- BASELINE config 2: 97 hits, a 58,870-atom
+// structure -- spent 10 of their 14 ms replaying k-d trees whose ranks were never read).
+__global__ void __launch_bounds__(256) k_pair_hits(long long h0, long long h1, const int *pair, unsigned *pair_hits)
+{
+    const long long h = h0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h < h1) atomicAdd(&pair_hits[pair[h]], 1u);
+}
+
+__global__ void __launch_bounds__(256) k_mark_lists(long long h0, long long h1, const int *pair, const unsigned *pair_hits,
+                                                    const PairRec *recs, OrderSpecs O, unsigned char *needed)
+{
+    const long long h = h0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= h1 || pair_hits[pair[h]] < 2u) return;
+    const PairRec *rec = recs + pair[h];
+    for (int k = 0; k < rec->n; k++) needed[(long long)rec->m * O.n_ospecs + O.atom_ospec[rec->ta0 + k]] = 1;
+}
+
 __global__ void __launch_bounds__(256) k_olist_count(int Mc, OrderSpecs O, int n_specs, const CandHead *head,
-                                                     unsigned *ocnt)
+                                                     const unsigned char *needed, unsigned *ocnt)
 {
     const long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nl = (long long)Mc * O.n_ospecs;
     if (L > nl) return;
     unsigned c = 0;
-    if (L < nl) {
+    if (L < nl && needed[L]) {
         const int m = (int)(L / O.n_ospecs), os = (int)(L % O.n_ospecs);
         c = (unsigned)head[(long long)m * n_specs + O.spec[os]].cnt;
     }
@@ -74,11 +93,11 @@ __global__ void __launch_bounds__(256) k_olist_count(int Mc, OrderSpecs O, int n
 __global__ void __launch_bounds__(256) k_olist_fill(int Mc, OrderSpecs O, int n_specs, const CandHead *head,
                                                     const float4 *cand, const long long *atom_off,
                                                     const uint32_t *res, const int *serial, const unsigned *ooff,
-                                                    u64 *key_atom, u64 *key_set)
+                                                    const unsigned char *needed, u64 *key_atom, u64 *key_set)
 {
     const long long L = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (L >= (long long)Mc * O.n_ospecs) return;
+    if (L >= (long long)Mc * O.n_ospecs || !needed[L]) return;
     const int m = (int)(L / O.n_ospecs), os = (int)(L % O.n_ospecs);
     const CandHead hd = head[(long long)m * n_specs + O.spec[os]];
     const long long a0 = atom_off[m];
@@ -251,12 +270,14 @@ __global__ void __launch_bounds__(128) k_hit_keys(HitKeyArgs A)
             const int k = ro[l];
             const long long L = (long long)m * A.O.n_ospecs + A.O.atom_ospec[ta0 + k];
             const u64 want = ((u64)L << 32) | (u64)(uint32_t)at[k];
-            unsigned lo = A.ooff[L], hi = A.ooff[L + 1];
+            const unsigned end = A.ooff[L + 1];
+            unsigned lo = A.ooff[L], hi = end;
             while (lo < hi) {
                 const unsigned mid = (lo + hi) >> 1;
                 if (A.atom_sorted[mid] < want) lo = mid + 1; else hi = mid;
             }
-            v = (int)(l == 0 ? A.set_pos[lo] : A.kd_rank[lo]);
+            // (a list that was not built belongs to a pair with this single hit: any key will do)
+            if (lo < end) v = (int)(l == 0 ? A.set_pos[lo] : A.kd_rank[lo]);
         }
         key[l] = v;
     }
