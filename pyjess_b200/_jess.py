@@ -252,7 +252,7 @@ class _BatchRun:
     which rows belong to its structure -- and puts them into iteration order when it is first read."""
 
     __slots__ = ("jess", "molecules", "args", "all_tuples", "devices", "hit_order", "coords", "tables", "stats",
-                 "item_stats", "_slices", "_where", "_lo", "_hi", "_keep", "done", "_lock", "_error")
+                 "item_stats", "_slices", "_where", "_lo", "_hi", "_keep", "done", "_lock", "_error", "_served")
 
     def __init__(self, jess, molecules, args, all_tuples, devices=None, hit_order="reference", coords=False):
         self.jess = jess
@@ -271,6 +271,7 @@ class _BatchRun:
         self.done = False                 # set once tables and slices are in place (or the run has failed)
         self._lock = threading.Lock()     # the Query objects of one batch may be consumed from several threads
         self._error = None
+        self._served = False              # combined single-structure runs: results (or the error) are in place
 
     # single-table view (one work item): kept for callers and tests that predate sharded runs
     @property
@@ -291,13 +292,60 @@ class _BatchRun:
             with self._lock:
                 if not self.done:
                     try:
-                        self._run_locked()
+                        if len(self.molecules) == 1 and self.devices is None:
+                            self._run_combined()
+                        else:
+                            self._run_locked()
                     except BaseException as exc:      # every later next() re-raises the real error
                         self._error = exc
                         raise
                     finally:
                         self.done = True
                     return
+        if self._error is not None:
+            raise self._error
+
+    # -- single-structure queries arriving from several threads -----------------------------------
+    # The reference's recipe for many structures is a pool of threads, each calling `jess.query(molecule, ...)`
+    # (README.md:147-162): its C scanner releases the GIL and the calls run side by side.  Here they all
+    # meet at ONE engine context, and a GPU query of one structure costs ~0.3 ms however small it is: the
+    # calls would queue and the pool would run at the speed of a serial loop.  Instead the calls COMBINE:
+    # a thread that finds the engine busy leaves its run in `jess._pending` and waits; when the engine is
+    # free, ONE of the waiting threads (the leader of the round) takes everything that has piled up, runs
+    # the runs with equal parameters as one batch -- one upload, one set of launches -- and hands every
+    # run its block of the shared hit table.  A lone call takes the same path with a batch of one.
+    def _combine_key(self):
+        return (self.args, self.all_tuples, self.hit_order, self.coords)
+
+    def _run_combined(self):
+        jess = self.jess
+        cv = jess._combine
+        with cv:
+            jess._pending.append(self)
+            while True:
+                if self._served:
+                    if self._error is not None:
+                        raise self._error
+                    return
+                if not jess._leader:
+                    jess._leader = True
+                    batch, jess._pending = jess._pending, []
+                    break
+                cv.wait()
+        try:
+            groups: dict = {}
+            for r in batch:
+                groups.setdefault(r._combine_key(), []).append(r)
+            for group in groups.values():
+                _serve_group(group)
+        finally:
+            with cv:
+                for r in batch:
+                    if not r._served:             # the leader failed outside an engine call
+                        r._error = r._error or RuntimeError("combined query failed")
+                        r._served = True
+                jess._leader = False
+                cv.notify_all()
         if self._error is not None:
             raise self._error
 
@@ -322,7 +370,7 @@ class _BatchRun:
         sub = mols if len(idx) == len(mols) else [mols[int(i)] for i in idx]
         out.append((idx,) + _capi.query_records(ctx, dev_tpl, sub, params))
 
-    def _run_locked(self):
+    def _run_locked(self, warn: bool = True):
         jess, mols = self.jess, self.molecules
         n_mol = len(mols)
         if len(jess) == 0 or not mols or all(len(m) == 0 for m in mols) or jess._table.max_atoms == 0:
@@ -401,7 +449,7 @@ class _BatchRun:
                 self._keep.append(keep)
         self._where = where.tolist()
         self.stats = total
-        if total.get("nan_dropped"):
+        if warn and total.get("nan_dropped"):
             warnings.warn("Jess returned a superposition matrix with NaN values", UserWarning, stacklevel=5)
 
     def indices(self, m: int) -> np.ndarray:
@@ -417,6 +465,36 @@ class _BatchRun:
                 block = keep[block]
             rows = self._slices[m] = _iteration_rows(t.molecule, t.template, block)
         return rows
+
+
+def _serve_group(group: List[_BatchRun]) -> None:
+    """Run single-structure runs with equal parameters as ONE engine batch and give each its block of the shared
+    hit table.  A batch whose engine run dropped NaN superpositions is re-run structure by structure, so that the
+    reference's warning reaches the caller whose structure it concerns."""
+    first = group[0]
+    if len(group) > 1:
+        big = _BatchRun(first.jess, [r.molecules[0] for r in group], first.args, first.all_tuples, None,
+                        first.hit_order, first.coords)
+        try:
+            big._run_locked(warn=False)
+        except BaseException:
+            big = None                            # e.g. out of memory: every run gets its own attempt (and its own error)
+        if big is not None and not (big.stats or {}).get("nan_dropped"):
+            for j, r in enumerate(group):
+                r.tables, r.item_stats, r.stats = big.tables, big.item_stats, big.stats
+                r._keep = big._keep if big._keep is not None else []
+                r._where = [big._where[j]] if big._where else [0]
+                r._slices = [big._slices[j]] if big._lo is None else [None]
+                if big._lo is not None:
+                    r._lo, r._hi = big._lo[j:j + 1], big._hi[j:j + 1]
+                r._served = True
+            return
+    for r in group:
+        try:
+            r._run_locked()
+        except BaseException as exc:
+            r._error = exc
+        r._served = True
 
 
 class Query:
@@ -584,6 +662,10 @@ class Jess:
                              f"{JB_MAX_TEMPLATE_ATOMS} atoms per template")
         self._device = {}
         self._device_lock = threading.Lock()
+        # single-structure queries from several threads combine into one engine batch (_BatchRun._run_combined)
+        self._combine = threading.Condition()
+        self._pending: List[_BatchRun] = []
+        self._leader = False
 
     def _device_templates(self, ctx):
         from . import _capi

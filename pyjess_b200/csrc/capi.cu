@@ -602,6 +602,8 @@ static int prepare_molecules(jb_context *c, jb_molecules *m, cudaStream_t st)
 {
     (void)c;
     const int M = m->M;
+    // the sweep addresses atoms and candidate records with 32-bit offsets (expand_grid.cuh: GridWarp)
+    if (m->NA >= (1ll << 32)) return fail(JB_ERR_INVALID, "an upload holds %lld atoms; the engine takes fewer than 2^32 per upload", m->NA);
     cudaError_t e = m->atoms.ensure(std::max<size_t>((size_t)m->NA, 1) * sizeof(AtomRec), st);
     long long amax_all = 0;
     for (int i = 0; i < M; i++) amax_all = std::max(amax_all, m->atom_off[i + 1] - m->atom_off[i]);
@@ -817,7 +819,7 @@ static cudaError_t launch_expand_grid(int sm_count, cudaStream_t st, const Expan
         cudaError_t e = cudaFuncSetAttribute(k_expand_grid<L, G, ROOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / (smem + 1024)));   // 227 KB per SM, 1 KB reserved per CTA
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (228 * 1024) / (smem + 1024)));   // 228 KB per SM, 1 KB reserved per CTA
     k_expand_grid<L, G, ROOT><<<sm_count * per_sm, kExpandThreads, smem, st>>>(a, b, stats);
     return cudaGetLastError();
 }
@@ -911,9 +913,34 @@ static int build_reference_keys(jb_context *c, const jb_templates *t, const jb_m
             MT.atoms, c->q_setpos.as<unsigned>(), c->q_coords.as<double>(), c->q_kdidx.as<int>());
         // one thread per list, lists in memory order (a length-sorted schedule was measured 40 % slower:
         // the threads of a warp then walk lists of different structures and lose their shared cache lines)
+        // lists of up to 32 records: one thread each; longer ones: one warp each, index array in shared memory
+        // (order.cuh: k_kd_order_team, three size classes); beyond 16,384 records the thread kernel again (global memory,
+        // slow but complete)
+        constexpr int kTeamMid = 256, kTeamLong = 2048, kTeamHuge = 16384;
+        const bool team = !getenv("JB_NO_KD_TEAM");
         k_kd_order<<<(unsigned)((nl + 127) / 128), 128, 0, st>>>(nl, nullptr, ooff, c->q_coords.as<double>(), c->q_kdidx.as<int>(),
-                                                                 c->q_perm.as<unsigned>(), c->q_kdrank.as<unsigned>());
+                                                                 c->q_perm.as<unsigned>(), c->q_kdrank.as<unsigned>(),
+                                                                 team ? (unsigned)kKdThreadMax : ~0u, team ? (unsigned)kTeamHuge : ~0u);
         CU(cudaGetLastError());
+        if (team) {
+            constexpr size_t smem_mid = 8 * 2 * kTeamMid * sizeof(int), smem_long = 8 * 2 * kTeamLong * sizeof(int),
+                             smem_huge = 2 * kTeamHuge * sizeof(int);
+            const double *co = c->q_coords.as<double>();
+            const unsigned *pm = c->q_perm.as<unsigned>();
+            unsigned *kr = c->q_kdrank.as<unsigned>();
+            k_kd_order_team<kTeamMid, 8><<<(unsigned)std::min<long long>((nl + 7) / 8, (long long)c->sm_count * 8), 256, smem_mid, st>>>(
+                nl, kKdThreadMax, ooff, co, pm, kr);
+            CU(cudaGetLastError());
+            CU(cudaFuncSetAttribute(k_kd_order_team<kTeamLong, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_long));
+            k_kd_order_team<kTeamLong, 8><<<(unsigned)std::min<long long>((nl + 7) / 8, c->sm_count), 256, smem_long, st>>>(
+                nl, kTeamMid, ooff, co, pm, kr);
+            CU(cudaGetLastError());
+            CU(cudaFuncSetAttribute(k_kd_order_team<kTeamHuge, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_huge));
+            k_kd_order_team<kTeamHuge, 1><<<(unsigned)std::min<long long>(nl, c->sm_count), 32, smem_huge, st>>>(
+                nl, kTeamLong, ooff, co, pm, kr);
+            CU(cudaGetLastError());
+            S.launches += 3;
+        }
         S.launches += 6;   // + the radix sort passes (library kernels)
     }
     HitKeyArgs K;
@@ -1061,7 +1088,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         MT.ext = mol->ext.as<MolExt>() + r.m0;
         CandTable CT;
         CT.head = c->chead.as<CandHead>(); CT.rec = c->crec.as<float4>(); CT.xtab = c->cxtab.as<unsigned short>();
-        CT.cap = (long long)(c->crec.bytes / sizeof(float4));
+        CT.cap = std::min<long long>((long long)(c->crec.bytes / sizeof(float4)), (1ll << 32) - 1);   // 32-bit record offsets in the sweep
         CT.bins = c->cbin.as<BinTab>(); CT.binlist = c->cbinlist.as<int>();
         CT.bin_cap = (long long)(c->cbin.bytes / sizeof(BinTab));
         Counters *dc = c->ctr.as<Counters>();
@@ -1878,11 +1905,15 @@ static int query_host_once(jb_context *c, const jb_templates *t, const HostSourc
     // grow-only device staging owned by the context
     int rc = stage_source(c, c->scratch_mol, src, 0, src.M, c->stream, c->host_stage[0]);
     if (rc == JB_OK) rc = prepare_molecules(c, c->scratch_mol, c->stream);
-    if (rc == JB_OK) CU(cudaStreamSynchronize(c->stream));   // the caller's (or our) staging may be reused from here on
+    // (no synchronisation here: the run below waits for its own kernels, which follow the copies on the same stream, before
+    //  it returns -- the caller's staging is free again by then; a round trip less on the latency path)
     if (rc != JB_OK) return rc;
     rc = query_run_once(c, t, c->scratch_mol, q, out);
     if (rc == JB_OK) c->last_hits = (*out)->count;
     if (rc == JB_OK) rc = jb_result_fetch(*out, hits);
-    if (rc != JB_OK && *out) { jb_result_free(*out); *out = nullptr; }
+    if (rc != JB_OK) {
+        cudaStreamSynchronize(c->stream);             // the uploads may still be reading the caller's staging
+        if (*out) { jb_result_free(*out); *out = nullptr; }
+    }
     return rc;
 }

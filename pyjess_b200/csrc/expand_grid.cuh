@@ -48,10 +48,11 @@ template <int L, int G> struct alignas(16) GridWarp {   // per-warp shared memor
     // image decides all but the borderline cases (see the drain), the FP64 radii serve those.
     float4 cf[L][IPW];                                  // centre relative to the structure origin (FP32), lo_reject
     float4 th[L][IPW];                                  // lo_certain, hi_certain, hi_reject of the squared distance
-    double clo2[L][IPW], chi2[L][IPW];
+    // (the FP64 radii are NOT staged: the few records per million inside the error band read them from the shell
+    //  table again -- 16 bytes per placed atom less, which is what lets level 3 keep four CTAs per SM)
     int cres[L][IPW], cflag[L][IPW];
-    long long cbase[IPW];                               // first record of the candidate list
-    long long abase[IPW];                               // first atom of the structure
+    unsigned cbase[IPW];                                // first record of the candidate list (capi.cu bounds both tables by 2^32)
+    unsigned abase[IPW];                                // first atom of the structure
     int2 meta[IPW];                                     // pair index, "this level completes the template"
                                       // records in the candidate list
     int chain_atom[L][IPW];
@@ -82,7 +83,6 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_grid(const ExpandA
 
     u64 n_in = *A.in_count;
     if ((long long)n_in > A.in_cap) n_in = (u64)A.in_cap;
-    const long long total_warps = (long long)gridDim.x * kExpandWarps;
     u64 n_cand = 0;                                   // per-lane partial sums
     unsigned n_scan = 0, n_box = 0;                   // per-lane partial sums (diagnostics)
     const float INF = __int_as_float(0x7f800000);
@@ -93,9 +93,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_grid(const ExpandA
     // e = 2^-20 rb (ext + rb), more than twice the worst case: DESIGN.md "FP32 first") settles every
     // survivor whose s lies outside [lo2 - e, lo2 + e] and [hi2 - e, hi2 + e]; the others -- a few per
     // million -- take the FP64 operations of the reference on the FP64 atom records.
-    auto drain = [&](bool ok, const int pos, const int g) {
-        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok) r = __ldg(&A.cand[W.cbase[g] + pos]);
+    auto drain = [&](bool ok, const float4 r, const int g) {
         const int a = __float_as_int(r.w);
         const int2 mt = W.meta[g];
         bool unsure = false;
@@ -112,12 +110,15 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_grid(const ExpandA
         if (__any_sync(FULL, ok && unsure)) {
             if (ok && unsure) {
                 const AtomRec p = A.atoms[W.abase[g] + a];
+                const PairRec *rec = A.recs + mt.x;
+                const int n = rec->n, k = rec->order[L];
 #pragma unroll
                 for (int j = 0; j < L; j++) {
                     const AtomRec q = A.atoms[W.abase[g] + W.chain_atom[j][g]];
+                    const ShellRec *sh = A.shell + rec->shell0 + (long long)rec->order[j] * n + k;
                     const double t0 = __dsub_rn(q.x, p.x), t1 = __dsub_rn(q.y, p.y), t2 = __dsub_rn(q.z, p.z);
                     const double s = __dadd_rn(__dadd_rn(__dmul_rn(t0, t0), __dmul_rn(t1, t1)), __dmul_rn(t2, t2));
-                    if (s < W.clo2[j][g] || s > W.chi2[j][g]) { ok = false; break; }
+                    if (s < sh->lo2 || s > sh->hi2) { ok = false; break; }
                 }
             }
         }
@@ -214,22 +215,48 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_grid(const ExpandA
             __syncwarp();
             for (int s0 = w0; s0 < w1; s0 += 32) {
                 const int s = s0 + lane;
-                const int e = s < w1 ? (int)W.queue[s - w0] : 0;
+                const bool ok = s < w1;
+                const int e = ok ? (int)W.queue[s - w0] : 0;
                 const int o = e >> 7;
                 const int pb = __shfl_sync(FULL, posbase, o);
-                drain(s < w1, pb + (e & 127), o / G);
+                const int g = o / G;
+                // (prefetching the record of round r + 1 while round r is tested measured neutral: 8.01 -> 8.00 ms, r3c)
+                float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok) r = __ldg(&A.cand[W.cbase[g] + pb + (e & 127)]);
+                drain(ok, r, g);
             }
             __syncwarp();                                    // the next window overwrites the queue
         }
     };
 
-    long long my_pair = (long long)blockIdx.x * kExpandWarps + warp;      // ROOT: next pair of this warp
+    // Work is CLAIMED, not dealt: a warp takes the next kGrab batches (pairs in root mode) off a device counter when it
+    // runs dry.  The static round-robin deal of round 1 left the SMs idle for 10-24 % of a launch -- partial matches of
+    // large structures cost several times the average, and the warps that drew them finished last (profiles/r2_sweep_ncu.md:
+    // sm__cycles_active 76 / 87 / 90 % of the elapsed cycles at levels 1 / 2 / 3).
+    // (a claim is 2 batches / 4 pairs; one when the level holds too little work to keep every warp busy that way)
+    const int grab = (ROOT ? 1 : IPW) * ((long long)n_in >= (long long)gridDim.x * kExpandWarps * (ROOT ? 8 : 4 * IPW) ? (ROOT ? 4 : 2) : 1);
+    u64 *const sched = &A.ctr->sched[L];
+    long long claim = 0, claim_end = 0;                                   // warp uniform
+    auto claim_more = [&]() {
+        u64 g0 = 0;
+        if (lane == 0) g0 = atomicAdd(sched, (u64)grab);
+        claim = (long long)__shfl_sync(FULL, g0, 0);
+        claim_end = claim + grab;
+    };
+    claim_more();
+    long long my_pair = claim;                                            // ROOT: next pair of this warp
     int root_j = 0, root_cnt = 0;
     long long root_off = 0;
     bool pair_loaded = false;
     unsigned n_roots = 0;
-    for (long long base_item = ((long long)blockIdx.x * kExpandWarps + warp) * IPW; ROOT || base_item < (long long)n_in;
-         base_item += total_warps * IPW) {
+    for (;;) {
+        long long base_item = 0;
+        if (!ROOT) {
+            if (claim >= claim_end) claim_more();
+            base_item = claim;
+            claim += IPW;
+            if (base_item >= (long long)n_in) break;
+        }
         const long long item = base_item + grp;
         bool valid = item < (long long)n_in;
         int root_lp = 0, root_a = 0;
@@ -252,7 +279,10 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_grid(const ExpandA
                 }
                 filled += take;
                 root_j += take;
-                if (root_j >= root_cnt) { my_pair += total_warps; pair_loaded = false; }
+                if (root_j >= root_cnt) {
+                    pair_loaded = false;
+                    if (++my_pair >= claim_end) { claim_more(); my_pair = claim; }
+                }
             }
             if (filled == 0) break;
             if (valid && gl == 0) n_roots++;
@@ -278,8 +308,8 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_grid(const ExpandA
             hx0 = hd.x0; hinv = hd.inv_w;
             if (gl == 0) {
                 W.meta[grp] = make_int2(lp, (L + 1 == n) ? 1 : 0);
-                W.abase[grp] = h1.x;
-                W.cbase[grp] = coff;
+                W.abase[grp] = (unsigned)h1.x;
+                W.cbase[grp] = (unsigned)coff;
             }
             const MolExt me = A.ext[h0.x];
             const float err = __double2float_ru(me.ext * 2.4e-7 + 1e-30);    // > ext * 2^-22: record rounding
@@ -291,7 +321,6 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_grid(const ExpandA
                     const int a = ROOT ? root_a : it[1 + j];
                     const AtomRec ar = A.atoms[h1.x + a];
                     const ShellRec sh = A.shell[h1.y + (long long)rec->order[j] * n + k];
-                    W.clo2[j][grp] = sh.lo2; W.chi2[j][grp] = sh.hi2;
                     W.cres[j][grp] = ar.resseq; W.cflag[j][grp] = ar.chain | (sh.flags << 8);
                     W.chain_atom[j][grp] = a;
                     const double dx = __dsub_rn(ar.x, me.ox), dy = __dsub_rn(ar.y, me.oy), dz = __dsub_rn(ar.z, me.oz);

@@ -189,6 +189,7 @@ struct Counters {              // device counters of one chunk attempt
     u64 hits;                  // hits written (absolute, across chunks)
     u64 nan_dropped;
     u64 level[kMaxN + 1];      // level[l] = items with l atoms (l>=1)
+    u64 sched[kMaxN + 1];      // sched[l] = next unclaimed item (pair in root mode) of the level-l sweep: warps claim work here
 };
 
 // ---- tokens ------------------------------------------------------------------

@@ -189,13 +189,14 @@ __device__ void kd_qselect(int *idx, int n, int k, const double *u, int axis)
 // the next axis.  The final index array is the left-to-right leaf order; KdTreeQuery_next
 // visits leaves right to left, so rank = count - 1 - leaf position.
 __global__ void __launch_bounds__(128) k_kd_order(long long n_lists, const unsigned *schedule, const unsigned *ooff,
-                                                  const double *coords, int *kd_idx, const unsigned *perm, unsigned *kd_rank)
+                                                  const double *coords, int *kd_idx, const unsigned *perm, unsigned *kd_rank,
+                                                  unsigned skip_lo, unsigned skip_hi)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_lists) return;
     const long long L = schedule ? (long long)schedule[t] : t;
     const unsigned o0 = ooff[L], cnt = ooff[L + 1] - o0;
-    if (cnt == 0) return;
+    if (cnt == 0 || (cnt > skip_lo && cnt <= skip_hi)) return;   // (skip_lo, skip_hi]: lists of the team kernels
     int *idx = kd_idx + o0;
     const double *u = coords + 3ll * o0;
     int st_s[40], st_n[40];
@@ -213,6 +214,93 @@ __global__ void __launch_bounds__(128) k_kd_order(long long n_lists, const unsig
         st_s[sp] = s; st_n[sp] = split; st_d[sp] = (unsigned char)(d + 1); sp++;
     }
     for (unsigned q = 0; q < cnt; q++) kd_rank[perm[o0 + idx[q]]] = cnt - 1 - q;
+}
+
+// One WARP per list of kd_team_lo < cnt <= CAP records.  A thread walking a 1,000-record list alone (n log n dependent
+// gathers from global memory) was the whole cost of the thread-per-list kernel: 3.6 ms per launch on BASELINE config 3,
+// 100 ms on config 4's large structures (profiles/r2_launches.md).  Here the index array lives in shared memory and the
+// tree is built LEVEL BY LEVEL: the segments of one level are disjoint, so lane t replays qselect on segment t -- the same
+// comparisons on the same FP64 values in the same order as KdTreeNode_create, whatever the order the segments are taken
+// in.  The top levels (1, 2, 4 ... segments) still run on few lanes, but against shared memory and the L1-resident
+// coordinates of ONE list instead of 128 lists per CTA.
+constexpr int kKdThreadMax = 32;                 // lists up to here stay with the thread-per-list kernel
+
+__device__ __forceinline__ void kd_qselect_sm(int *idx, int n, int k, const double *u, int axis)
+{
+    int left = 0, right = n - 1;
+    while (left != right) {
+        const int mid = (left + right + 1) / 2;
+        int pivot;
+        if ((kd_cmp(u, idx[left], idx[mid], axis) > 0) != (kd_cmp(u, idx[left], idx[right], axis) > 0)) pivot = left;
+        else if ((kd_cmp(u, idx[mid], idx[left], axis) < 0) != (kd_cmp(u, idx[mid], idx[right], axis) < 0)) pivot = mid;
+        else pivot = right;
+        kd_swap(idx, right, pivot);
+        int store = left;
+        const double pv = __ldg(&u[3 * idx[right] + axis]);
+        // the element of step i + 1 is never touched by the swap of step i (store <= i): fetch it one step ahead
+        int v = idx[left];
+        double c = __ldg(&u[3 * v + axis]);
+        for (int i = left; i < right; i++) {
+            const int vn = idx[i + 1];                                       // (i + 1 == right: the pivot, unused)
+            const double cn = __ldg(&u[3 * vn + axis]);
+            if (!(c > pv)) {
+                idx[i] = idx[store];
+                idx[store] = v;
+                store++;
+            }
+            v = vn; c = cn;
+        }
+        kd_swap(idx, store, right);
+        if (store == k) return;
+        if (k < store) right = store - 1; else left = store + 1;
+    }
+}
+
+template <int CAP, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_kd_order_team(long long n_lists, int lo, const unsigned *ooff, const double *coords,
+                                                              const unsigned *perm, unsigned *kd_rank)
+{
+    extern __shared__ int kd_sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int *idx = kd_sm + warp * (2 * CAP);                                     // [CAP]
+    static_assert(CAP <= 16384, "segments are packed into 32 bits");
+    unsigned *qa = reinterpret_cast<unsigned *>(idx + CAP), *qb = qa + CAP / 2;   // segment queues of the current / next level
+    const unsigned lt = (1u << lane) - 1;
+    for (long long L = (long long)blockIdx.x * WARPS + warp; L < n_lists; L += (long long)gridDim.x * WARPS) {
+        const unsigned o0 = ooff[L], cnt = ooff[L + 1] - o0;
+        if ((int)cnt <= lo || cnt > (unsigned)CAP) continue;                  // warp uniform
+        const double *u = coords + 3ll * o0;
+        for (int j = lane; j < (int)cnt; j += 32) idx[j] = j;
+        // a segment is (start << 16) | n with n >= 2 (CAP <= 16,384)
+        if (lane == 0) qa[0] = cnt;
+        int n_cur = 1;
+        __syncwarp();
+        for (int depth = 0; n_cur > 0; depth++) {
+            int n_next = 0;
+            for (int i0 = 0; i0 < n_cur; i0 += 32) {
+                const int i = i0 + lane;
+                unsigned left = 0, right = 0;                                 // children worth another split
+                if (i < n_cur) {
+                    const unsigned seg = qa[i];
+                    const int s = (int)(seg >> 16), n = (int)(seg & 0xffffu);
+                    const int split = n / 2;
+                    kd_qselect_sm(idx + s, n, split, u, depth % 3);
+                    if (split >= 2) left = ((unsigned)s << 16) | (unsigned)split;
+                    if (n - split >= 2) right = ((unsigned)(s + split) << 16) | (unsigned)(n - split);
+                }
+                const unsigned bl = __ballot_sync(0xffffffffu, left != 0), br = __ballot_sync(0xffffffffu, right != 0);
+                if (left) qb[n_next + __popc(bl & lt)] = left;
+                n_next += __popc(bl);
+                if (right) qb[n_next + __popc(br & lt)] = right;
+                n_next += __popc(br);
+            }
+            __syncwarp();
+            unsigned *t = qa; qa = qb; qb = t;
+            n_cur = n_next;
+        }
+        for (int q = lane; q < (int)cnt; q += 32) kd_rank[perm[o0 + idx[q]]] = cnt - 1 - q;
+        __syncwarp();
+    }
 }
 
 // Small sparse results: does any (structure, template) pair own more than one hit?  If not, the

@@ -326,6 +326,49 @@ def test_queries_of_one_batch_consumed_from_several_threads(monkeypatch):
             next(q)
 
 
+def test_single_structure_queries_from_a_thread_pool_combine_into_batches(monkeypatch):
+    """The reference's recipe for many structures (README.md:147-162): `pool.map(lambda m: list(jess.query(m, ...)))`.
+    Calls that find the engine busy are combined into ONE engine batch by the next free thread; every caller must
+    still see exactly its structure's records, in order, and an engine error must reach every caller."""
+    from multiprocessing.pool import ThreadPool
+    import pytest
+    from pyjess_b200 import Jess, _capi, synth
+    tpl, mols, thr, _ = synth.workload("cfg3", scale=0.03)
+    table = _random_table(len(mols), len(tpl), 900, 11)
+    jess = Jess(tpl)
+    _stub_engine(monkeypatch, mols, table)
+    want = [[(h.rmsd, tpl.index(h.template()), h.atoms(transform=False)[0].serial) for h in jess.query(m, *thr)] for m in mols]
+    assert sum(len(w) for w in want) == table.count
+    calls = []
+    _stub_engine(monkeypatch, mols, table, calls, delay=0.02)
+    with ThreadPool(8) as pool:
+        got = pool.map(lambda m: [(h.rmsd, tpl.index(h.template()), h.atoms(transform=False)[0].serial)
+                                  for h in jess.query(m, *thr)], mols)
+        # different parameters never share a batch
+        mixed = pool.map(lambda im: len(list(jess.query(im[1], *thr, best_match=bool(im[0] % 2)))), list(enumerate(mols)))
+    assert got == want
+    served = [ids for _, ids in calls]
+    assert any(len(ids) > 1 for ids in served), "no calls were combined"
+    assert len(served) < 2 * len(mols)                                        # far fewer engine calls than the 2 x len(mols) queries
+    assert sorted(i for ids in served for i in ids) == sorted(2 * list(range(len(mols))))   # every query served exactly once
+    assert mixed == [len(w) for w in want]            # (the stub ignores best_match; the runs must not have been mixed up)
+
+    def broken(*a):
+        raise _capi.EngineError(-3, "out of memory")
+
+    monkeypatch.setattr(_capi, "query_records", broken)
+    with ThreadPool(4) as pool:
+        def attempt(m):
+            with pytest.raises(_capi.EngineError):
+                next(jess.query(m, *thr))
+            return True
+        assert all(pool.map(attempt, mols[:12]))
+    # the engine works again: nothing is left behind by the failed rounds
+    _stub_engine(monkeypatch, mols, table)
+    assert [(h.rmsd, tpl.index(h.template()), h.atoms(transform=False)[0].serial) for h in jess.query(mols[3], *thr)] == want[3]
+    assert not jess._pending and not jess._leader
+
+
 def test_query_properties_settable_only_while_they_can_be_honoured(monkeypatch):
     import pytest
     from pyjess_b200 import Jess, synth
