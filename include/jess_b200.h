@@ -225,7 +225,9 @@ int jb_templates_spec_count(const jb_templates *tpl);
 
 /* ---- molecules: replaces Molecule_* (molecule.pxd:17-21) and
  * ResIndex_create (res_index.pxd:13, eff:ResIndex.c:28-113).  Copies the SoA
- * host image (pinned or pageable) to HBM on the context stream.              */
+ * host image (pinned or pageable) to HBM on the context stream.  One upload
+ * (and one jb_query_host / jb_query_records batch) holds fewer than 2^32 atoms:
+ * the sweep addresses atoms with 32-bit offsets; JB_ERR_INVALID beyond.     */
 int jb_molecules_upload(jb_context *ctx, const jb_molecule_batch *batch,
                         jb_molecules **out);
 void jb_molecules_free(jb_molecules *mol);

@@ -500,6 +500,10 @@ def _serve_group(group: List[_BatchRun]) -> None:
 class Query:
     """Iterator over the hits of one structure (_jess.pyx:2090-2283)."""
 
+    # (a `query_many` over 1,000 structures creates 1,000 of these: no per-object dict, a third of the allocations)
+    __slots__ = ("_run", "_index", "_pos", "_ignore_chain", "_max_candidates", "_jess", "_molecule", "_rmsd_threshold",
+                 "_best_match", "_partial", "_candidates", "_skip_template", "__weakref__")
+
     def __init__(self, jess, molecule, rmsd_threshold, best_match, ignore_chain, max_candidates, run: _BatchRun,
                  index: int):
         self._run = run

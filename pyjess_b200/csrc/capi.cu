@@ -916,30 +916,44 @@ static int build_reference_keys(jb_context *c, const jb_templates *t, const jb_m
         // lists of up to 32 records: one thread each; longer ones: one warp each, index array in shared memory
         // (order.cuh: k_kd_order_team, three size classes); beyond 16,384 records the thread kernel again (global memory,
         // slow but complete)
-        constexpr int kTeamMid = 256, kTeamLong = 2048, kTeamHuge = 16384;
+        constexpr int kTeamMid = 256, kTeamLong = 1024, kTeamXl = 4096, kTeamHuge = 16384;
         const bool team = !getenv("JB_NO_KD_TEAM");
+        // upper list sizes of the thread / mid / long / xl kernels (the capacities above are their limits); tests lower them
+        // with JB_KD_CLASSES=a,b,c,d so that small inputs drive every size class
+        int lim[4] = { kKdThreadMax, kTeamMid, kTeamLong, kTeamXl };
+        if (const char *g = getenv("JB_KD_CLASSES")) {
+            int v[4];
+            if (sscanf(g, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]) == 4 && v[0] >= 1 && v[0] <= v[1] && v[1] <= v[2] && v[2] <= v[3] &&
+                v[1] <= kTeamMid && v[2] <= kTeamLong && v[3] <= kTeamXl)
+                for (int i = 0; i < 4; i++) lim[i] = v[i];
+        }
         k_kd_order<<<(unsigned)((nl + 127) / 128), 128, 0, st>>>(nl, nullptr, ooff, c->q_coords.as<double>(), c->q_kdidx.as<int>(),
                                                                  c->q_perm.as<unsigned>(), c->q_kdrank.as<unsigned>(),
-                                                                 team ? (unsigned)kKdThreadMax : ~0u, team ? (unsigned)kTeamHuge : ~0u);
+                                                                 team ? (unsigned)lim[0] : ~0u, team ? (unsigned)kTeamHuge : ~0u);
         CU(cudaGetLastError());
         if (team) {
+            // shared memory per warp: 8 bytes per record of the class's capacity (index array + two segment queues)
             constexpr size_t smem_mid = 8 * 2 * kTeamMid * sizeof(int), smem_long = 8 * 2 * kTeamLong * sizeof(int),
-                             smem_huge = 2 * kTeamHuge * sizeof(int);
+                             smem_xl = 4 * 2 * kTeamXl * sizeof(int), smem_huge = 2 * kTeamHuge * sizeof(int);
             const double *co = c->q_coords.as<double>();
             const unsigned *pm = c->q_perm.as<unsigned>();
             unsigned *kr = c->q_kdrank.as<unsigned>();
             k_kd_order_team<kTeamMid, 8><<<(unsigned)std::min<long long>((nl + 7) / 8, (long long)c->sm_count * 8), 256, smem_mid, st>>>(
-                nl, kKdThreadMax, ooff, co, pm, kr);
+                nl, lim[0], lim[1], ooff, co, pm, kr);
             CU(cudaGetLastError());
             CU(cudaFuncSetAttribute(k_kd_order_team<kTeamLong, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_long));
-            k_kd_order_team<kTeamLong, 8><<<(unsigned)std::min<long long>((nl + 7) / 8, c->sm_count), 256, smem_long, st>>>(
-                nl, kTeamMid, ooff, co, pm, kr);
+            k_kd_order_team<kTeamLong, 8><<<(unsigned)std::min<long long>((nl + 7) / 8, (long long)c->sm_count * 3), 256, smem_long, st>>>(
+                nl, lim[1], lim[2], ooff, co, pm, kr);
+            CU(cudaGetLastError());
+            CU(cudaFuncSetAttribute(k_kd_order_team<kTeamXl, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_xl));
+            k_kd_order_team<kTeamXl, 4><<<(unsigned)std::min<long long>((nl + 3) / 4, c->sm_count), 128, smem_xl, st>>>(
+                nl, lim[2], lim[3], ooff, co, pm, kr);
             CU(cudaGetLastError());
             CU(cudaFuncSetAttribute(k_kd_order_team<kTeamHuge, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_huge));
             k_kd_order_team<kTeamHuge, 1><<<(unsigned)std::min<long long>(nl, c->sm_count), 32, smem_huge, st>>>(
-                nl, kTeamLong, ooff, co, pm, kr);
+                nl, lim[3], kTeamHuge, ooff, co, pm, kr);
             CU(cudaGetLastError());
-            S.launches += 3;
+            S.launches += 4;
         }
         S.launches += 6;   // + the radix sort passes (library kernels)
     }
@@ -1023,7 +1037,8 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
     if (cnt_bytes > 200 * 1024 || t->S > 65535)
         return fail(JB_ERR_INVALID, "%d distinct atom specs exceed the classify kernel's shared memory", t->S);
     int class_words = (t->S + 31) / 32;
-    size_t classify_smem = cnt_bytes + (size_t)kClassSlots * (sizeof(u64) + (size_t)class_words * sizeof(unsigned));
+    size_t classify_smem = cnt_bytes + (size_t)kClassSlots * (sizeof(u64) + (size_t)class_words * sizeof(unsigned)) +
+                           (size_t)t->S * sizeof(long long) + (size_t)classify_threads * sizeof(unsigned);   // + list offsets, transposed masks
     if (classify_smem > 200 * 1024) { class_words = 0; classify_smem = cnt_bytes; }
     if (getenv("JB_CLASSIFY_PLAIN")) { class_words = 0; classify_smem = cnt_bytes; }
     if (classify_smem > 48 * 1024)

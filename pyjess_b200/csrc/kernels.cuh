@@ -455,6 +455,21 @@ __device__ __forceinline__ unsigned class_hash(uint32_t name, uint32_t res_up)
 
 __device__ __forceinline__ void xindex_list(const long long L, const int lane, const CandTable &C);
 
+// 32 x 32 bit transpose across the lanes of a warp: lane b returns the word whose bit a is bit b of lane a's `x`
+// (five butterfly exchanges; checked against the definition in tests/test_bit_transpose.py's model of this code).
+__device__ __forceinline__ unsigned warp_transpose32(unsigned x, const int lane)
+{
+    unsigned m = 0x0000ffffu;
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        const unsigned y = __shfl_xor_sync(0xffffffffu, x, j);
+        if ((lane & j) == 0) x ^= (((x >> j) ^ y) & m) << j;       // keep my low halves, take the partner's into the high ones
+        else x ^= ((y >> j) ^ x) & m;                               // keep my high halves, take the partner's into the low ones
+        m ^= m << (j >> 1);
+    }
+    return x;
+}
+
 __global__ void __launch_bounds__(1024) k_classify(MolTable M, SpecTable S, CandTable C, Counters *ctr, int class_words)
 {
     extern __shared__ int sh_cnt[];                 // [warps][S], then the class set and its masks
@@ -466,6 +481,9 @@ __global__ void __launch_bounds__(1024) k_classify(MolTable M, SpecTable S, Cand
     const int na = (int)(a1 - a0);
     u64 *ckey = reinterpret_cast<u64 *>(sh_cnt + ((nw * ns + 1) & ~1));          // [kClassSlots]
     unsigned *cmask = reinterpret_cast<unsigned *>(ckey + kClassSlots);           // [kClassSlots][class_words]
+    long long *sh_off = reinterpret_cast<long long *>(cmask + (size_t)kClassSlots * class_words);   // [ns] first record of each list (fast path)
+    unsigned *tb = reinterpret_cast<unsigned *>(sh_off + ns) + w * 32;            // [warps][32] transposed match masks of the current group
+    const unsigned lt = (1u << lane) - 1;
     constexpr u64 EMPTY = ~0ull;
     bool fast = class_words > 0;
     if (fast) {
@@ -551,14 +569,30 @@ __global__ void __launch_bounds__(1024) k_classify(MolTable M, SpecTable S, Cand
                     while (ckey[h] != key) h = (h + 1) & (kClassSlots - 1);
                     mymask = cmask + h * class_words;
                 }
+                // Per 32 atoms and 32 specs ONE bit transpose instead of one ballot per spec some atom matches (40-100 of
+                // them, most matched by one or two lanes: 88 warp instructions per atom, 0.46 ms per cfg 3 step, 15 % of a
+                // cfg 4 step): lane b then owns spec 32 word + b and holds the lanes that match it -- all 32 counters move
+                // in one instruction, and an atom finds its slot in each of ITS specs' lists (a handful) from that table.
                 for (int word = 0; word < class_words; word++) {
                     const unsigned bits = valid ? mymask[word] : 0u;
-                    unsigned any = __reduce_or_sync(0xffffffffu, bits);
-                    while (any) {
-                        const int bit = __ffs(any) - 1;
-                        any &= any - 1;
-                        visit(word * 32 + bit, (bits >> bit) & 1u);
+                    if (__reduce_or_sync(0xffffffffu, bits) == 0u) continue;          // warp uniform
+                    const unsigned bal = warp_transpose32(bits, lane);
+                    const int sp = word * 32 + lane;                                  // (bal == 0 beyond the last spec)
+                    if (pass == 1) {
+                        tb[lane] = bal;
+                        __syncwarp();
+                        unsigned mybits = bits;
+                        while (mybits) {
+                            const int bit = __ffs(mybits) - 1;
+                            mybits &= mybits - 1;
+                            const int s = word * 32 + bit;
+                            const long long dst = sh_off[s] + mine[s] + __popc(tb[bit] & lt);
+                            if (dst < C.cap) C.rec[dst] = rec;
+                        }
+                        __syncwarp();
                     }
+                    if (bal) mine[sp] += __popc(bal);
+                    __syncwarp();
                 }
             } else {
                 for (int s = 0; s < ns; s++) visit(s, valid && spec_match(S, s, name, name_up, res_up));
@@ -584,6 +618,7 @@ __global__ void __launch_bounds__(1024) k_classify(MolTable M, SpecTable S, Cand
                         if (b0 + b < C.bin_cap) C.binlist[b0 + b] = m * ns + s;
                 }
                 C.head[(long long)m * ns + s] = h;
+                if (class_words > 0) sh_off[s] = h.off;
             }
             __syncthreads();
         }
@@ -746,6 +781,9 @@ __global__ void k_shells(TemplateTable T, double cutoff, double max_dyn)
 // One CTA = one template x 128 structures, so the n x n volume table is staged once in
 // shared memory and read as warp-uniform broadcasts.  The arithmetic mirrors
 // oracle/jess_oracle.c operation by operation (explicit RN ops): same order, same counters.
+// (Round 2 tried the per-thread arrays -- counts, running minimum volumes, the order -- in dynamic shared memory instead of
+//  local memory, which removes 436 MB of DRAM write-back per cfg 3 step: 0.50 -> 0.67 ms, slower -- the kernel is bound by
+//  the issue slots of its O(n^2) loops, not by the local-memory traffic; gpurun_out/r3g.)
 __global__ void __launch_bounds__(128) k_order(int n_mol, TemplateTable T, int n_specs, const CandHead *heads,
                                                const long long *atom_off, unsigned char *ordbuf)
 {

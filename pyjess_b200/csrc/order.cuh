@@ -237,18 +237,18 @@ __device__ __forceinline__ void kd_qselect_sm(int *idx, int n, int k, const doub
         kd_swap(idx, right, pivot);
         int store = left;
         const double pv = __ldg(&u[3 * idx[right] + axis]);
-        // the element of step i + 1 is never touched by the swap of step i (store <= i): fetch it one step ahead
-        int v = idx[left];
-        double c = __ldg(&u[3 * v + axis]);
+        // the elements of steps i + 1 and i + 2 are never touched by the swap of step i (store <= i): fetch them ahead
+        int v = idx[left], v1 = idx[min(left + 1, right)];
+        double c = __ldg(&u[3 * v + axis]), c1 = __ldg(&u[3 * v1 + axis]);
         for (int i = left; i < right; i++) {
-            const int vn = idx[i + 1];                                       // (i + 1 == right: the pivot, unused)
-            const double cn = __ldg(&u[3 * vn + axis]);
+            const int v2 = idx[min(i + 2, right)];                           // (>= right: the pivot, unused)
+            const double c2 = __ldg(&u[3 * v2 + axis]);
             if (!(c > pv)) {
                 idx[i] = idx[store];
                 idx[store] = v;
                 store++;
             }
-            v = vn; c = cn;
+            v = v1; c = c1; v1 = v2; c1 = c2;
         }
         kd_swap(idx, store, right);
         if (store == k) return;
@@ -257,8 +257,8 @@ __device__ __forceinline__ void kd_qselect_sm(int *idx, int n, int k, const doub
 }
 
 template <int CAP, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_kd_order_team(long long n_lists, int lo, const unsigned *ooff, const double *coords,
-                                                              const unsigned *perm, unsigned *kd_rank)
+__global__ void __launch_bounds__(WARPS * 32) k_kd_order_team(long long n_lists, int lo, int hi, const unsigned *ooff,
+                                                              const double *coords, const unsigned *perm, unsigned *kd_rank)
 {
     extern __shared__ int kd_sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_kd_order_team(long long n_lists,
     const unsigned lt = (1u << lane) - 1;
     for (long long L = (long long)blockIdx.x * WARPS + warp; L < n_lists; L += (long long)gridDim.x * WARPS) {
         const unsigned o0 = ooff[L], cnt = ooff[L + 1] - o0;
-        if ((int)cnt <= lo || cnt > (unsigned)CAP) continue;                  // warp uniform
+        if ((int)cnt <= lo || (int)cnt > hi || cnt > (unsigned)CAP) continue;   // warp uniform: lists of (lo, hi] are this launch's
         const double *u = coords + 3ll * o0;
         for (int j = lane; j < (int)cnt; j += 32) idx[j] = j;
         // a segment is (start << 16) | n with n >= 2 (CAP <= 16,384)

@@ -5,6 +5,7 @@
 #   tests            python -m pytest tests -m gpu -q
 #   tests:EXPR       ... restricted with -k EXPR
 #   bench[:ARGS]     python bench.py ARGS                 -> TAG_bench[_n].json  (ARGS: comma separated, e.g. --workload,cfg5)
+#   benchn:N[:ARGS]  the same under torchrun on N GPUs (gpurun --gpus N)
 #   ref[:ARGS]       python bench.py --impl reference ARGS
 #   launches[:ARGS]  ncu launch list (gpu__time_duration + dram bytes) of a short bench run
 #   ncu:REGEX[:SKIP[:COUNT[:ARGS]]]  ncu --set full of the kernels matching REGEX
@@ -25,6 +26,11 @@ for step in "$@"; do
     bench)
       out=gpurun_out/${TAG}_bench_$n.json
       python bench.py ${rest//,/ } > $out 2> gpurun_out/${TAG}_bench_$n.err; echo "[run] bench $rest rc=$?"; cut -c1-1500 $out; tail -3 gpurun_out/${TAG}_bench_$n.err;;
+    benchn)    # benchn:N[:ARGS]  the bench under torchrun on N GPUs (use with gpurun --gpus N)
+      ng=${rest%%:*}; args=""; [[ "$rest" == *:* ]] && args=${rest#*:}
+      out=gpurun_out/${TAG}_bench_n${ng}.json
+      python -m torch.distributed.run --nnodes=1 --nproc-per-node $ng --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $ng ${args//,/ } \
+          > $out 2> gpurun_out/${TAG}_bench_n${ng}.err; echo "[run] bench x$ng $args rc=$?"; grep '^{' $out | cut -c1-600; tail -3 gpurun_out/${TAG}_bench_n${ng}.err;;
     ref)
       out=gpurun_out/${TAG}_ref_$n.json
       python bench.py --impl reference ${rest//,/ } > $out 2>/dev/null; cut -c1-400 $out;;
