@@ -533,11 +533,11 @@ def run_latency_configs(args, env):
     thr = (2.0, 3.0, 3.0)
     out = {}
 
-    def wall(fns, reps):
+    def wall(fns, reps, warm=70):
         """ms per call of every variant: blocks of `reps` calls, the variants alternating, best block of three."""
         for fn in fns:
-            for _ in range(70):  # past the context's buffer-decay check (every 64 calls): the big buffers of the
-                fn()             # earlier workloads are released once, not inside the timed repetitions
+            for _ in range(warm):  # past the context's buffer-decay check (every 64 calls): the big buffers of the
+                fn()               # earlier workloads are released once, not inside the timed repetitions
         best = [1e30] * len(fns)
         for _ in range(3):
             for i, fn in enumerate(fns):
@@ -583,8 +583,8 @@ def run_latency_configs(args, env):
     from multiprocessing.pool import ThreadPool
     with ThreadPool(min(16, host_cores())) as pool:
         n_pool = sum(pool.map(lambda m: len(list(jess.query(m, *thr))), mols))
-        w_pool, = wall([lambda: pool.map(lambda m: list(jess.query(m, *thr)), mols)], 10)
-    w_loop, = wall([lambda: [list(jess.query(m, *thr)) for m in mols]], 2)
+        w_pool, = wall([lambda: pool.map(lambda m: list(jess.query(m, *thr)), mols)], 10, warm=5)
+    w_loop, = wall([lambda: [list(jess.query(m, *thr)) for m in mols]], 2, warm=2)
     c2["thread_pool_recipe"] = {"call": "ThreadPool(16).map(lambda m: list(jess.query(m, 2.0, 3.0, 3.0)), molecules)",
                                 "wall_ms_per_batch": w_pool, "hits": n_pool, "serial_loop_wall_ms": w_loop}
     if not args.no_cpu_baseline:

@@ -130,6 +130,7 @@ struct jb_context {
     int debug = 0;                // JB_DEBUG: per-level counts and times on stderr
     int legacy = 0;               // JB_LEGACY: run-time-level k_expand at every level (A/B comparisons)
     int sweep = 1;                // JB_SWEEP: 1 cell-grid sweep (expand_grid.cuh), 0 x-range stream (expand_lv.cuh)
+    int compact_bins = 0;         // JB_COMPACT_BINS: one-word cell masks for bins of <= 32 records
     long long dfs_pairs = 4096;   // JB_DFS_PAIRS: chunks of at most that many pairs take the one-launch depth-first sweep
     cudaEvent_t lev[kMaxN + 1] = {};
     // workspace (grow only)
@@ -284,6 +285,7 @@ extern "C" int jb_context_create(int device, void *stream, int64_t workspace_byt
     if (const char *g = getenv("JB_DEBUG")) c->debug = atoi(g);
     if (const char *g = getenv("JB_LEGACY")) c->legacy = atoi(g);
     if (const char *g = getenv("JB_SWEEP")) c->sweep = atoi(g);
+    if (const char *g = getenv("JB_COMPACT_BINS")) c->compact_bins = atoi(g);
     if (const char *g = getenv("JB_DFS_PAIRS")) c->dfs_pairs = atoll(g);
     if (const char *g = getenv("JB_PIPELINE")) c->pipeline_slices = atoi(g);
     if (c->debug) for (int i = 0; i <= kMaxN; i++) CU(cudaEventCreate(&c->lev[i]));
@@ -1118,7 +1120,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         k_classify<<<Mc, classify_threads, classify_smem, st>>>(MT, ST, CT, dc, class_words);   // + the x index of its lists (K1b)
         // small chunks: ONE depth-first launch instead of one launch per level (expand_dfs.cuh); it reads the lists directly
         const bool dfs = !c->legacy && pairs <= c->dfs_pairs;
-        if (c->sweep && !dfs) k_binindex<<<c->sm_count * 8, 256, 0, st>>>(CT, dc);
+        if (c->sweep && !dfs) k_binindex<<<c->sm_count * 8, 256, 0, st>>>(CT, dc, c->compact_bins);
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->evs[1], st));
         nvtxRangePop();
@@ -1174,7 +1176,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
             A.tuples = c->tuples.as<int>(); A.tuple_cap = tuple_cap;
             A.ctr = dc;
             GridArgs GA;
-            GA.bins = CT.bins; GA.bin_cap = CT.bin_cap;
+            GA.bins = CT.bins; GA.bin_cap = CT.bin_cap; GA.compact = c->compact_bins;
             if (c->debug) {
                 CU(cudaEventRecord(c->lev[l], st));
                 CU(cudaMemcpyAsync(c->host_lv + 2 * l, &dc->scan_tests, 2 * sizeof(u64), cudaMemcpyDeviceToHost, st));

@@ -665,7 +665,12 @@ __global__ void __launch_bounds__(256) k_xindex(long long n_lists, CandTable C)
 // One warp per bin: bounding box (warp min / max), cell of every record along the three axes,
 // 32 ballots per axis and 32 records of the bin.  Records with a NaN coordinate enter no mask (the box
 // test they replace -- r.x >= lo && r.x <= hi ... -- never accepted them either).
-__global__ void __launch_bounds__(256) k_binindex(CandTable C, const Counters *ctr)
+// compact != 0: a bin of at most 32 records keeps ONE word per cell, all 32 cells of an axis in one 128-byte line
+// (bin_compact_masks below): the two look-ups of an axis then share a line, 3 lines per (partial match, bin) instead of 6.
+__device__ __forceinline__ unsigned *bin_compact_masks(BinTab *T) { return reinterpret_cast<unsigned *>(T->upto); }
+__device__ __forceinline__ const unsigned *bin_compact_masks(const BinTab *T) { return reinterpret_cast<const unsigned *>(T->upto); }
+
+__global__ void __launch_bounds__(256) k_binindex(CandTable C, const Counters *ctr, const int compact)
 {
     const int lane = threadIdx.x & 31;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -732,7 +737,8 @@ __global__ void __launch_bounds__(256) k_binindex(CandTable C, const Counters *c
                     if (lane == b) mine.w[h] = mb;
                 }
             }
-            T->upto[a][lane] = mine;
+            if (compact && n <= 32) bin_compact_masks(T)[a * kMaskBuckets + lane] = mine.w[0];
+            else T->upto[a][lane] = mine;
             if (lane == 0) T->frame[a] = fr;
         }
         if (lane == 0) T->frame[3] = make_float2(0.f, 0.f);

@@ -95,6 +95,39 @@ def test_scan_order_and_group_invariance_full_cfg3(engine):
     assert np.abs(tables[0].rmsd - tables[1].rmsd).max() <= TOL
 
 
+@pytest.mark.parametrize("mode", ["masks", "plain", "overflow"])
+def test_every_classify_path_builds_the_same_candidate_lists(engine, oracle_lib, monkeypatch, mode):
+    """k_classify has three ways to the candidate lists: the class-mask path (one 32 x 32 bit transpose per 32 atoms and
+    32 specs), the plain loop over all specs (JB_CLASSIFY_PLAIN, or a template set whose masks do not fit), and the plain
+    loop a structure falls back to at run time when it holds more distinct (atom name, residue name) pairs than the
+    shared-memory class set (here: 900 made-up residue names on atoms no template matches).  Same hits, same work
+    counters as the oracle on all three -- the counters see every list's length."""
+    from pyjess_b200 import synth
+    from pyjess_b200._tables import query_params
+    tpl, mols, thr, kw = synth.workload("cfg3", scale=0.03)
+    mols = [m.copy() for m in mols]
+    if mode == "plain":
+        monkeypatch.setenv("JB_CLASSIFY_PLAIN", "1")
+    if mode == "overflow":
+        rng = np.random.default_rng(3)
+        letters = np.frombuffer(b"QWXZJ0123456789", dtype=np.uint8)
+        for m in mols[::2]:
+            at = m._atoms
+            pick = rng.choice(len(at), size=min(900, len(at) // 2), replace=False)
+            # residue names no template lists (digits / rare letters), all different: > 768 classes in one structure
+            at["resName"][pick] = np.array([letters[[i % 15, (i // 15) % 15, (i // 225) % 15]].tobytes()
+                                            for i in range(len(pick))], dtype="S3")
+            m._pack = None
+    params = query_params(*thr, reorder=2, **kw)
+    table, stats = run_engine(engine, tpl, mols, params)
+    ours, ostats = oracle_lib.query(TemplateTable(tpl), MoleculeBatch(mols), params, threads=8)
+    assert table.count > 0
+    ill = []
+    assert compare_tables(table, ours, params.rmsd_threshold, tpl, mols, ill) == []
+    for key in COUNTERS:
+        assert stats[key] == ostats[key], key
+
+
 @pytest.mark.parametrize("env", ["JB_ORDER_LSD", "JB_ORDER_NO_LSD", "JB_ORDER_COUNTING"])
 @pytest.mark.parametrize("hit_order", ["canonical", "reference"])
 def test_every_hit_ordering_path_gives_the_same_records(engine, monkeypatch, env, hit_order):
