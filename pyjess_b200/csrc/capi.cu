@@ -130,8 +130,8 @@ struct jb_context {
     int debug = 0;                // JB_DEBUG: per-level counts and times on stderr
     int legacy = 0;               // JB_LEGACY: run-time-level k_expand at every level (A/B comparisons)
     int sweep = 1;                // JB_SWEEP: 1 cell-grid sweep (expand_grid.cuh), 0 x-range stream (expand_lv.cuh)
-    int compact_bins = 0;         // JB_COMPACT_BINS: one-word cell masks for bins of <= 32 records
     long long dfs_pairs = 4096;   // JB_DFS_PAIRS: chunks of at most that many pairs take the one-launch depth-first sweep
+    long long tail_items = 0;     // JB_TAIL_ITEMS: a frontier of at most that many partial matches is finished depth first (k_expand_tail); 0 = off
     cudaEvent_t lev[kMaxN + 1] = {};
     // workspace (grow only)
     DevBuf crec, chead, cxtab, cbin, cbinlist, recs, ordbuf, fr[2], tuples, ctr;
@@ -285,8 +285,8 @@ extern "C" int jb_context_create(int device, void *stream, int64_t workspace_byt
     if (const char *g = getenv("JB_DEBUG")) c->debug = atoi(g);
     if (const char *g = getenv("JB_LEGACY")) c->legacy = atoi(g);
     if (const char *g = getenv("JB_SWEEP")) c->sweep = atoi(g);
-    if (const char *g = getenv("JB_COMPACT_BINS")) c->compact_bins = atoi(g);
     if (const char *g = getenv("JB_DFS_PAIRS")) c->dfs_pairs = atoll(g);
+    if (const char *g = getenv("JB_TAIL_ITEMS")) c->tail_items = atoll(g);
     if (const char *g = getenv("JB_PIPELINE")) c->pipeline_slices = atoi(g);
     if (c->debug) for (int i = 0; i <= kMaxN; i++) CU(cudaEventCreate(&c->lev[i]));
     CU(cudaMallocHost(&c->host_ctr, sizeof(Counters)));
@@ -1120,7 +1120,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         k_classify<<<Mc, classify_threads, classify_smem, st>>>(MT, ST, CT, dc, class_words);   // + the x index of its lists (K1b)
         // small chunks: ONE depth-first launch instead of one launch per level (expand_dfs.cuh); it reads the lists directly
         const bool dfs = !c->legacy && pairs <= c->dfs_pairs;
-        if (c->sweep && !dfs) k_binindex<<<c->sm_count * 8, 256, 0, st>>>(CT, dc, c->compact_bins);
+        if (c->sweep && !dfs) k_binindex<<<c->sm_count * 8, 256, 0, st>>>(CT, dc);
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->evs[1], st));
         nvtxRangePop();
@@ -1159,7 +1159,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
             A.tuples = c->tuples.as<int>(); A.tuple_cap = tuple_cap;
             A.ctr = dc;
             const long long want = (pairs * kRootSlices + kDfsWarps - 1) / kDfsWarps;
-            k_expand_dfs<<<(unsigned)std::max<long long>(1, std::min<long long>(want, (long long)c->sm_count * 16)), kDfsThreads, 0, st>>>(A);
+            k_expand_dfs_t<false><<<(unsigned)std::max<long long>(1, std::min<long long>(want, (long long)c->sm_count * 16)), kDfsThreads, 0, st>>>(A, 0, 0);
             CU(cudaGetLastError());
         }
         for (int l = 0; l < t->nmax && !dfs; l++) {
@@ -1176,7 +1176,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
             A.tuples = c->tuples.as<int>(); A.tuple_cap = tuple_cap;
             A.ctr = dc;
             GridArgs GA;
-            GA.bins = CT.bins; GA.bin_cap = CT.bin_cap; GA.compact = c->compact_bins;
+            GA.bins = CT.bins; GA.bin_cap = CT.bin_cap;
             if (c->debug) {
                 CU(cudaEventRecord(c->lev[l], st));
                 CU(cudaMemcpyAsync(c->host_lv + 2 * l, &dc->scan_tests, 2 * sizeof(u64), cudaMemcpyDeviceToHost, st));
@@ -1201,6 +1201,13 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
                 else if (g == 2) CU((launch_expand_lv<1, 2, true>(c->sm_count, st, A, stats)));
                 else CU((launch_expand_lv<1, 4, true>(c->sm_count, st, A, stats)));
                 continue;
+            }
+            // a small frontier is finished depth first in one launch (expand_dfs.cuh: TAIL); the level kernels below and
+            // of the deeper levels then return at once
+            if (l >= 3 && c->sweep && !c->legacy && c->tail_items > 0) {
+                k_expand_dfs_t<true><<<(unsigned)c->sm_count * 4, kDfsThreads, 0, st>>>(A, l, c->tail_items);
+                CU(cudaGetLastError());
+                S.launches++;
             }
             if (l >= 1 && l <= kMaxLv && !c->legacy) {
                 if (c->sweep) CU(dispatch_expand_grid(l, g, c->sm_count, st, A, GA, c->debug != 0));
@@ -1266,7 +1273,9 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
             used(c->crec, (size_t)hc.cand_total * sizeof(float4));
             used(c->cbin, (size_t)hc.bin_total * sizeof(BinTab));
             used(c->cbinlist, (size_t)hc.bin_total * sizeof(int));
-            for (int l = 0; l < t->nmax; l++) used(c->fr[l & 1], (size_t)hc.level[l + 1] * (l + 2) * sizeof(int));
+            // (levels from tail_level on were finished depth first: their counters are work counters, no frontier was written)
+            const int fr_levels = hc.tail_level ? std::min<int>(t->nmax, (int)hc.tail_level) : t->nmax;
+            for (int l = 0; l < fr_levels; l++) used(c->fr[l & 1], (size_t)hc.level[l + 1] * (l + 2) * sizeof(int));
             used(c->tuples, (size_t)hc.tuples * tuple_stride * sizeof(int));
             const size_t nhits = (size_t)std::min<u64>(hc.hits, (u64)c->hit_cap);   // cumulative over the run
             DevBuf *hb[] = { &c->h_mol, &c->h_tpl, &c->h_atoms, &c->h_rmsd, &c->h_rot, &c->h_c0, &c->h_c1, &c->f_mol, &c->f_tpl,
@@ -1289,7 +1298,8 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         }
         if (!retry) {
             long long need_ints[2] = { 0, 0 };
-            for (int l = 0; l < t->nmax && !dfs; l++)        // (the depth-first sweep keeps no frontier)
+            const int fr_levels = hc.tail_level ? std::min<int>(t->nmax, (int)hc.tail_level) : t->nmax;
+            for (int l = 0; l < fr_levels && !dfs; l++)      // (the depth-first sweeps keep no frontier)
                 need_ints[l & 1] = std::max(need_ints[l & 1], (long long)hc.level[l + 1] * (l + 2));
             for (int b = 0; b < 2; b++)
                 if (need_ints[b] > fr_ints[b]) {

@@ -35,7 +35,15 @@ struct alignas(16) DfsWarp {                 // per-warp shared memory
     unsigned count[kMaxN + 2];               // accepted partial matches per size (work counters), [kMaxN + 1]: unused
 };
 
-__global__ void __launch_bounds__(kDfsThreads) k_expand_dfs(const ExpandArgs A)
+// TAIL = false: the whole tree of every live pair (small chunks, above).
+// TAIL = true (k_expand_tail): the level-synchronous sweep hands over its frontier of level l0 -- items
+// [pair, a_0 .. a_{l0-1}] -- once that frontier is small: the last levels of a large batch hold a few thousand partial
+// matches each (cfg 3: 4,655 at level 9 of 17) and cost ~40 us of launch + dependent-load latency per level whatever
+// their size.  One warp per item finishes its subtree depth first; the level kernels of levels >= l0 then return at once
+// (Counters::tail_level).  Every block takes the same decision from the same final counter; the flag only tells LATER
+// kernels.
+template <bool TAIL>
+__global__ void __launch_bounds__(kDfsThreads) k_expand_dfs_t(const ExpandArgs A, const int l0, const long long tail_max)
 {
     constexpr unsigned FULL = 0xffffffffu;
     __shared__ DfsWarp sh[kDfsWarps];
@@ -43,17 +51,22 @@ __global__ void __launch_bounds__(kDfsThreads) k_expand_dfs(const ExpandArgs A)
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1;
     const long long total_warps = (long long)gridDim.x * kDfsWarps;
-    u64 n_in = *A.in_count;                  // live pairs
+    u64 n_in = *A.in_count;                  // live pairs (TAIL: partial matches of l0 atoms)
+    if (TAIL) {
+        const u64 fired = A.ctr->tail_level;
+        if ((fired != 0 && fired < (u64)l0) || (long long)n_in > tail_max || (long long)n_in > A.in_cap) return;
+        if (blockIdx.x == 0 && threadIdx.x == 0) A.ctr->tail_level = (u64)l0;
+    }
     if ((long long)n_in > A.in_cap) n_in = (u64)A.in_cap;
     const float INF = __int_as_float(0x7f800000);
     u64 n_cand = 0;
     for (int i = lane; i < kMaxN + 2; i += 32) W.count[i] = 0u;
     __syncwarp();
 
-    for (long long item = (long long)blockIdx.x * kDfsWarps + (threadIdx.x >> 5); item < (long long)n_in * kRootSlices;
+    for (long long item = (long long)blockIdx.x * kDfsWarps + (threadIdx.x >> 5); item < (long long)n_in * (TAIL ? 1 : kRootSlices);
          item += total_warps) {
-        const long long lp = item / kRootSlices;
-        const int slice = (int)(item % kRootSlices);
+        const long long lp = TAIL ? (long long)A.in[item * (l0 + 1)] : item / kRootSlices;
+        const int slice = TAIL ? 0 : (int)(item % kRootSlices);
         const PairRec *rec = A.recs + lp;
         const int4 h0 = *reinterpret_cast<const int4 *>(rec);            // m, t, ta0, n
         const longlong2 h1 = *reinterpret_cast<const longlong2 *>(&rec->abase);
@@ -140,18 +153,10 @@ __global__ void __launch_bounds__(kDfsThreads) k_expand_dfs(const ExpandArgs A)
             __syncwarp();
         };
 
-        // the roots of this slice: records slice, slice + kRootSlices, ... of the first atom's list
-        const CandHead hd0 = A.head[(long long)h0.x * A.n_specs + rec->spec[0]];
-        int cnt0 = hd0.cnt;
-        if (hd0.off + cnt0 > A.cand_cap) cnt0 = (int)max(0ll, A.cand_cap - hd0.off);
-        for (int root = slice; root < cnt0; root += kRootSlices) {
-        const int a0 = __float_as_int(__ldg(&A.cand[hd0.off + root].w));
-        __syncwarp();
-        if (lane == 0) { W.atom[0] = a0; if (n > 1) W.count[1]++; }
-        __syncwarp();
-        if (n == 1) { emit(); continue; }
-        l = 1;
-        enter(1);
+        // depth-first walk of the subtree below the `base` placed atoms W.atom[0 .. base-1]
+        auto walk = [&](const int base) {
+        l = base;
+        enter(base);
         while (true) {
             if (W.qi[l] < W.qn[l]) {
                 // ---- descend into the next accepted record of this level ----
@@ -216,10 +221,30 @@ __global__ void __launch_bounds__(kDfsThreads) k_expand_dfs(const ExpandArgs A)
                 continue;
             }
             // ---- this level is exhausted: back to the previous one ----
-            if (l == 1) break;
+            if (l == base) break;
             l--;
         }
         __syncwarp();
+        };
+
+        if (TAIL) {
+            __syncwarp();
+            for (int j = lane; j < l0; j += 32) W.atom[j] = A.in[item * (l0 + 1) + 1 + j];
+            __syncwarp();
+            walk(l0);
+            continue;
+        }
+        // the roots of this slice: records slice, slice + kRootSlices, ... of the first atom's list
+        const CandHead hd0 = A.head[(long long)h0.x * A.n_specs + rec->spec[0]];
+        int cnt0 = hd0.cnt;
+        if (hd0.off + cnt0 > A.cand_cap) cnt0 = (int)max(0ll, A.cand_cap - hd0.off);
+        for (int root = slice; root < cnt0; root += kRootSlices) {
+            const int a0 = __float_as_int(__ldg(&A.cand[hd0.off + root].w));
+            __syncwarp();
+            if (lane == 0) { W.atom[0] = a0; if (n > 1) W.count[1]++; }
+            __syncwarp();
+            if (n == 1) { emit(); continue; }
+            walk(1);
         }
     }
     __syncwarp();

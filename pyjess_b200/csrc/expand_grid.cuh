@@ -65,7 +65,6 @@ template <int L, int G> constexpr size_t expand_grid_smem() { return sizeof(Grid
 struct GridArgs {
     const BinTab *bins;
     long long bin_cap;
-    int compact;                                        // bins of <= 32 records hold one-word masks (k_binindex)
 };
 
 template <int L, int G, bool ROOT = false>
@@ -82,6 +81,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_grid(const ExpandA
     const unsigned lt = (1u << lane) - 1;
     int fill = 0;
 
+    if (!ROOT && A.ctr->tail_level != 0 && A.ctr->tail_level <= (u64)L) return;   // finished depth first (k_expand_tail)
     u64 n_in = *A.in_count;
     if ((long long)n_in > A.in_cap) n_in = (u64)A.in_cap;
     u64 n_cand = 0;                                   // per-lane partial sums
@@ -383,21 +383,13 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_grid(const ExpandA
                         const float lo = ax == 0 ? bx0 : (ax == 1 ? by0 : bz0), hi = ax == 0 ? bx1 : (ax == 1 ? by1 : bz1);
                         const float2 fr = __ldg(&T->frame[ax]);
                         const int cl = axis_cell(lo, fr), ch = axis_cell(hi, fr);
-                        if (B.compact && cnt - (b_lo + bi) * kBinRecs <= 32) {      // a short bin: one word per cell
-                            const unsigned *U = bin_compact_masks(T) + ax * kMaskBuckets;
-                            const unsigned up = __ldg(U + ch), dn = cl > 0 ? __ldg(U + cl - 1) : 0u;
-                            m.w[0] &= up & ~dn;
+                        const BinMask up = ldg_mask(&T->upto[ax][ch]);
+                        BinMask dn;
 #pragma unroll
-                            for (int h = 1; h < kMaskWords; h++) m.w[h] = 0u;
-                        } else {
-                            const BinMask up = ldg_mask(&T->upto[ax][ch]);
-                            BinMask dn;
+                        for (int h = 0; h < kMaskWords; h++) dn.w[h] = 0u;
+                        if (cl > 0) dn = ldg_mask(&T->upto[ax][cl - 1]);
 #pragma unroll
-                            for (int h = 0; h < kMaskWords; h++) dn.w[h] = 0u;
-                            if (cl > 0) dn = ldg_mask(&T->upto[ax][cl - 1]);
-#pragma unroll
-                            for (int h = 0; h < kMaskWords; h++) m.w[h] &= up.w[h] & ~dn.w[h];
-                        }
+                        for (int h = 0; h < kMaskWords; h++) m.w[h] &= up.w[h] & ~dn.w[h];
                     }
                 }
             }

@@ -190,6 +190,8 @@ struct Counters {              // device counters of one chunk attempt
     u64 nan_dropped;
     u64 level[kMaxN + 1];      // level[l] = items with l atoms (l>=1)
     u64 sched[kMaxN + 1];      // sched[l] = next unclaimed item (pair in root mode) of the level-l sweep: warps claim work here
+    u64 tail_level;            // != 0: the frontier of that level was small enough to be finished depth first by
+                               // k_expand_tail (expand_dfs.cuh); the level kernels of that and of deeper levels return at once
 };
 
 // ---- tokens ------------------------------------------------------------------
@@ -512,16 +514,18 @@ __global__ void __launch_bounds__(1024) k_classify(MolTable M, SpecTable S, Cand
         if (fast) {
             for (int i = threadIdx.x; i < kClassSlots * class_words; i += blockDim.x) cmask[i] = 0u;
             __syncthreads();
-            // one (class, spec) evaluation per thread-iteration; a warp handles 32 specs of one class
-            for (int job = w; job < kClassSlots * class_words; job += nw) {
-                const int slot = job / class_words, word = job % class_words;
+            // one (class, spec) evaluation per thread-iteration; a warp takes a class and walks its specs 32 at a time
+            // (slot by slot: the flat loop over (slot, word) jobs spent 29 % of the kernel on its division and on empty slots)
+            for (int slot = w; slot < kClassSlots; slot += nw) {
                 const u64 key = ckey[slot];
                 if (key == EMPTY) continue;
-                const int sp = word * 32 + lane;
-                const uint32_t name = (uint32_t)(key >> 32), res_up = (uint32_t)key;
-                const bool ok = sp < ns && spec_match(S, sp, name, upper4(name), res_up);
-                const unsigned bits = __ballot_sync(0xffffffffu, ok);
-                if (lane == 0) cmask[job] = bits;
+                const uint32_t name = (uint32_t)(key >> 32), name_up = upper4(name), res_up = (uint32_t)key;
+                for (int word = 0; word < class_words; word++) {
+                    const int sp = word * 32 + lane;
+                    const bool ok = sp < ns && spec_match(S, sp, name, name_up, res_up);
+                    const unsigned bits = __ballot_sync(0xffffffffu, ok);
+                    if (lane == 0) cmask[slot * class_words + word] = bits;
+                }
             }
         }
         __syncthreads();
@@ -665,12 +669,9 @@ __global__ void __launch_bounds__(256) k_xindex(long long n_lists, CandTable C)
 // One warp per bin: bounding box (warp min / max), cell of every record along the three axes,
 // 32 ballots per axis and 32 records of the bin.  Records with a NaN coordinate enter no mask (the box
 // test they replace -- r.x >= lo && r.x <= hi ... -- never accepted them either).
-// compact != 0: a bin of at most 32 records keeps ONE word per cell, all 32 cells of an axis in one 128-byte line
-// (bin_compact_masks below): the two look-ups of an axis then share a line, 3 lines per (partial match, bin) instead of 6.
-__device__ __forceinline__ unsigned *bin_compact_masks(BinTab *T) { return reinterpret_cast<unsigned *>(T->upto); }
-__device__ __forceinline__ const unsigned *bin_compact_masks(const BinTab *T) { return reinterpret_cast<const unsigned *>(T->upto); }
-
-__global__ void __launch_bounds__(256) k_binindex(CandTable C, const Counters *ctr, const int compact)
+// (Round 2 tried ONE word per cell for bins of at most 32 records, the 32 cells of an axis in one 128-byte line -- 3 lines
+//  per (partial match, bin) instead of 6: 7.67 -> 7.74 ms on cfg 3, 12.83 -> 12.82 ms on cfg4shard/4, gpurun_out/r3j; dropped.)
+__global__ void __launch_bounds__(256) k_binindex(CandTable C, const Counters *ctr)
 {
     const int lane = threadIdx.x & 31;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -737,8 +738,7 @@ __global__ void __launch_bounds__(256) k_binindex(CandTable C, const Counters *c
                     if (lane == b) mine.w[h] = mb;
                 }
             }
-            if (compact && n <= 32) bin_compact_masks(T)[a * kMaskBuckets + lane] = mine.w[0];
-            else T->upto[a][lane] = mine;
+            T->upto[a][lane] = mine;
             if (lane == 0) T->frame[a] = fr;
         }
         if (lane == 0) T->frame[3] = make_float2(0.f, 0.f);
@@ -1048,6 +1048,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(const ExpandArgs A
     int *stage = chain_atom + IPW * lpad;
     int fill = 0, qfill = 0;
 
+    if (A.ctr->tail_level != 0 && A.ctr->tail_level <= (u64)l) return;   // finished depth first (k_expand_tail)
     u64 n_in = *A.in_count;
     if (l > 0 && (long long)n_in > A.in_cap) n_in = (u64)A.in_cap;
     const long long total_warps = (long long)gridDim.x * kExpandWarps;

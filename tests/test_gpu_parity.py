@@ -450,6 +450,38 @@ def test_depth_first_sweep_equals_level_sweep(workload, scale, monkeypatch):
             c.close()
 
 
+@pytest.mark.parametrize("workload,scale", [("cfg3", 0.06), ("cfg3dense", 0.04), ("cfg5", 0.012)])
+def test_tail_finish_equals_level_sweep(workload, scale, monkeypatch):
+    """The level sweep may hand a SMALL frontier to a depth-first finish (JB_TAIL_ITEMS, expand_dfs.cuh: TAIL): same hit
+    table and the same work counters whether the hand-over never happens (0), happens at a late level (a few thousand
+    partial matches) or at the first level it may (any frontier qualifies); DFS chunks switched off so that the level
+    kernels run."""
+    from pyjess_b200 import _capi, synth
+    from pyjess_b200._tables import query_params
+    tpl, mols, thr, kw = synth.workload(workload, scale=scale)
+    monkeypatch.setenv("JB_DFS_PAIRS", "0")
+    ctxs = {}
+    for name, items in (("levels", "0"), ("late", "3000"), ("always", "1000000000")):
+        monkeypatch.setenv("JB_TAIL_ITEMS", items)
+        ctxs[name] = _capi.Context(0)
+    try:
+        for ignore, reorder in ((kw.get("ignore_chain"), 2), ("residues", 1), ("atoms", 0)):
+            params = query_params(*thr, reorder=reorder, all_tuples=True, **dict(kw, ignore_chain=ignore))
+            got = {name: run_engine(c, tpl, mols, params) for name, c in ctxs.items()}
+            ta, sa = got["levels"]
+            assert ta.count > 0
+            for name in ("late", "always"):
+                tb, sb = got[name]
+                assert ta.count == tb.count
+                for a, b in zip(ta.arrays(), tb.arrays()):
+                    assert np.array_equal(a, b, equal_nan=a.dtype.kind == "f")
+                for key in ("live_pairs", "candidate_atoms", "candidate_tests", "frontier_items", "frontier_ints", "tuples", "hits"):
+                    assert sa[key] == sb[key], (name, key)
+    finally:
+        for c in ctxs.values():
+            c.close()
+
+
 @pytest.mark.parametrize("workload,scale,kwargs", [
     ("cfg3dense", 0.5, {}),                       # 50 templates x 500 structures, dense-hit thresholds: 2.2 M hits
     ("cfg4shard", 0.2, {}),                       # 200 templates x 1,250 structures of 300-1,500 residues
