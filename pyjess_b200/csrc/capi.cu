@@ -131,6 +131,7 @@ struct jb_context {
     int legacy = 0;               // JB_LEGACY: run-time-level k_expand at every level (A/B comparisons)
     int sweep = 1;                // JB_SWEEP: 1 cell-grid sweep (expand_grid.cuh), 0 x-range stream (expand_lv.cuh)
     long long dfs_pairs = 4096;   // JB_DFS_PAIRS: chunks of at most that many pairs take the one-launch depth-first sweep
+    int grid_levels = 24;         // JB_GRID_LEVELS: levels 1 .. this take the cell-grid kernel (kMaxGridLv), deeper ones k_expand<G>
     long long tail_items = 0;     // JB_TAIL_ITEMS: a frontier of at most that many partial matches is finished depth first (k_expand_tail); 0 = off
     cudaEvent_t lev[kMaxN + 1] = {};
     // workspace (grow only)
@@ -287,6 +288,7 @@ extern "C" int jb_context_create(int device, void *stream, int64_t workspace_byt
     if (const char *g = getenv("JB_SWEEP")) c->sweep = atoi(g);
     if (const char *g = getenv("JB_DFS_PAIRS")) c->dfs_pairs = atoll(g);
     if (const char *g = getenv("JB_TAIL_ITEMS")) c->tail_items = atoll(g);
+    if (const char *g = getenv("JB_GRID_LEVELS")) c->grid_levels = std::max(1, std::min(24, atoi(g)));
     if (const char *g = getenv("JB_PIPELINE")) c->pipeline_slices = atoi(g);
     if (c->debug) for (int i = 0; i <= kMaxN; i++) CU(cudaEventCreate(&c->lev[i]));
     CU(cudaMallocHost(&c->host_ctr, sizeof(Counters)));
@@ -839,6 +841,12 @@ static cudaError_t dispatch_expand_grid(int level, int g, int sm_count, cudaStre
         JB_GRID_CASE(1) JB_GRID_CASE(2) JB_GRID_CASE(3) JB_GRID_CASE(4)
         JB_GRID_CASE(5) JB_GRID_CASE(6) JB_GRID_CASE(7) JB_GRID_CASE(8)
         JB_GRID_CASE(9) JB_GRID_CASE(10) JB_GRID_CASE(11) JB_GRID_CASE(12)
+        // levels 13 .. kMaxGridLv (templates of up to 25 atoms, BASELINE config 5 holds 24): four lanes per partial match
+        // -- the staging of 13-24 placed atoms for 16 or 32 partial matches per warp does not fit two CTAs per SM
+#define JB_GRID_DEEP(LL) case LL: return launch_expand_grid<LL, 4>(sm_count, st, a, b, stats);
+        JB_GRID_DEEP(13) JB_GRID_DEEP(14) JB_GRID_DEEP(15) JB_GRID_DEEP(16) JB_GRID_DEEP(17) JB_GRID_DEEP(18)
+        JB_GRID_DEEP(19) JB_GRID_DEEP(20) JB_GRID_DEEP(21) JB_GRID_DEEP(22) JB_GRID_DEEP(23) JB_GRID_DEEP(24)
+#undef JB_GRID_DEEP
     default: return cudaErrorInvalidValue;
     }
 #undef JB_GRID_CASE
@@ -1209,7 +1217,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
                 CU(cudaGetLastError());
                 S.launches++;
             }
-            if (l >= 1 && l <= kMaxLv && !c->legacy) {
+            if (l >= 1 && l <= (c->sweep ? c->grid_levels : kMaxLv) && !c->legacy) {
                 if (c->sweep) CU(dispatch_expand_grid(l, g, c->sm_count, st, A, GA, c->debug != 0));
                 else CU(dispatch_expand_lv(l, g, c->sm_count, st, A, c->debug != 0));
                 continue;
@@ -1239,7 +1247,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
         HB.mol = c->h_mol.as<int>(); HB.tpl = c->h_tpl.as<int>(); HB.atoms = c->h_atoms.as<int>();
         HB.rmsd = c->h_rmsd.as<double>(); HB.rot = c->h_rot.as<double>(); HB.c0 = c->h_c0.as<double>();
         HB.c1 = c->h_c1.as<double>(); HB.cap = c->hit_cap; HB.stride = c->hit_stride;
-        k_superpose<<<c->sm_count * 8, 128, 0, st>>>(c->tuples.as<int>(), &dc->tuples, tuple_cap, tuple_stride,
+        k_superpose<<<c->sm_count * 8, 128, 0, st>>>(c->tuples.as<int>(), &dc->tuple_slots, tuple_cap, tuple_stride,
                                                     c->recs.as<PairRec>(), TT, MT, slice_base + r.m0, q->rmsd_threshold, q->all_tuples, HB,
                                                     dc);
         CU(cudaGetLastError());
@@ -1276,7 +1284,7 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
             // (levels from tail_level on were finished depth first: their counters are work counters, no frontier was written)
             const int fr_levels = hc.tail_level ? std::min<int>(t->nmax, (int)hc.tail_level) : t->nmax;
             for (int l = 0; l < fr_levels; l++) used(c->fr[l & 1], (size_t)hc.level[l + 1] * (l + 2) * sizeof(int));
-            used(c->tuples, (size_t)hc.tuples * tuple_stride * sizeof(int));
+            used(c->tuples, (size_t)hc.tuple_slots * tuple_stride * sizeof(int));
             const size_t nhits = (size_t)std::min<u64>(hc.hits, (u64)c->hit_cap);   // cumulative over the run
             DevBuf *hb[] = { &c->h_mol, &c->h_tpl, &c->h_atoms, &c->h_rmsd, &c->h_rot, &c->h_c0, &c->h_c1, &c->f_mol, &c->f_tpl,
                              &c->f_atoms, &c->f_rmsd, &c->f_rot, &c->f_c0, &c->f_c1, &c->h_pair, &c->h_keys };
@@ -1309,8 +1317,8 @@ static int query_run_impl(jb_context *c, const jb_templates *t, const jb_molecul
                         return fail(JB_ERR_CAPACITY, "structure %d needs a %zu MiB frontier; raise workspace_bytes", r.m0, want >> 20);
                     else { CU(c->fr[b].ensure(want, st)); retry = true; }
                 }
-            if ((long long)hc.tuples > tuple_cap) {
-                CU(c->tuples.ensure((size_t)(hc.tuples + hc.tuples / 2) * tuple_stride * sizeof(int), st));
+            if ((long long)hc.tuple_slots > tuple_cap) {     // (records reserved: the tuples plus the holes of the last chunks)
+                CU(c->tuples.ensure((size_t)(hc.tuple_slots + hc.tuple_slots / 2) * tuple_stride * sizeof(int), st));
                 retry = true;
             }
             if ((long long)hc.hits > c->hit_cap) {

@@ -141,7 +141,8 @@ __global__ void __launch_bounds__(kDfsThreads) k_expand_dfs_t(const ExpandArgs A
         auto emit = [&]() {
             u64 slot = 0;
             if (lane == 0) {
-                slot = atomicAdd(&A.ctr->tuples, 1ull);
+                slot = atomicAdd(&A.ctr->tuple_slots, 1ull);
+                atomicAdd(&A.ctr->tuples, 1ull);
                 atomicAdd(&A.ctr->tuple_ints, (u64)n);
             }
             slot = __shfl_sync(FULL, slot, 0);

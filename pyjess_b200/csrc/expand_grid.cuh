@@ -56,8 +56,14 @@ template <int L, int G> struct alignas(16) GridWarp {   // per-warp shared memor
     int2 meta[IPW];                                     // pair index, "this level completes the template"
                                       // records in the candidate list
     int chain_atom[L][IPW];
-    int stage[kStageItems * (L + 2)];                   // accepted extensions awaiting the flush
+    // deep levels (24-atom templates): half the staging, so that two CTAs still share an SM
+    static constexpr int kStage = L > 12 ? kStageItems / 2 : kStageItems;
+    int stage[kStage * (L + 2)];                        // accepted extensions awaiting the flush
     unsigned short queue[kGridQueue];                   // box survivors of the current window: (owner lane << 7) | position in its bin
+    long long t_next;                                   // the warp's chunk of the tuple list: next free record, records left,
+    int t_left;                                         // tuples written so far (flushed into the counters at the end),
+    unsigned n_tup;                                     // size of the next chunk (8 doubling to kTupleChunk: a warp that
+    int t_chunk, t_pad[3];                              // completes a handful of tuples leaves a handful of holes)
 };
 
 template <int L, int G> constexpr size_t expand_grid_smem() { return sizeof(GridWarp<L, G>) * kExpandWarps; }
@@ -80,6 +86,8 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_grid(const ExpandA
     const int grp = lane / G, gl = lane % G;
     const unsigned lt = (1u << lane) - 1;
     int fill = 0;
+    if (lane == 0) { W.t_next = 0; W.t_left = 0; W.n_tup = 0u; W.t_chunk = 8; }
+    __syncwarp();
 
     if (!ROOT && A.ctr->tail_level != 0 && A.ctr->tail_level <= (u64)L) return;   // finished depth first (k_expand_tail)
     u64 n_in = *A.in_count;
@@ -136,15 +144,25 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_grid(const ExpandA
         if (okm == 0) return;
         const unsigned cm = __ballot_sync(FULL, ok && mt.y);
         const unsigned nm = okm & ~cm;
-        if (cm) {   // finished tuples go straight to the tuple list (one atomic per warp)
-            u64 tb = 0;
-            if (lane == 0) {
-                tb = atomicAdd(&A.ctr->tuples, (u64)__popc(cm));
-                atomicAdd(&A.ctr->tuple_ints, (u64)__popc(cm) * (u64)(L + 1));
+        if (cm) {
+            // Finished tuples go straight to the tuple list.  Its records are reserved kTupleChunk at a time per warp: one
+            // atomic per round of 32 survivors (two, with the statistics) on ONE address serialised the completing levels
+            // of dense-hit workloads -- 8 M tuples at level 8 of cfg3dense cost 2.2 of its 4.8 ms (gpurun_out/r3n).  A
+            // round that does not fit the rest of the chunk fills it and continues in a new one; only the last chunk of a
+            // warp is left partly unused, its records marked as holes at the end of the kernel.
+            const int k = __popc(cm);
+            const long long t_next = W.t_next;
+            const int t_left = W.t_left;
+            long long fresh = 0;
+            const int want = max(W.t_chunk, k - t_left);     // (only used when the round does not fit)
+            if (k > t_left) {
+                u64 v = 0;
+                if (lane == 0) v = atomicAdd(&A.ctr->tuple_slots, (u64)want);
+                fresh = (long long)__shfl_sync(FULL, v, 0);
             }
-            tb = __shfl_sync(FULL, tb, 0);
             if (ok && mt.y) {
-                const long long slot = (long long)tb + __popc(cm & lt);
+                const int r = __popc(cm & lt);
+                const long long slot = r < t_left ? t_next + r : fresh + (r - t_left);
                 if (slot < A.tuple_cap) {
                     int *dst = A.tuples + slot * A.tuple_stride;
                     dst[0] = mt.x;
@@ -153,6 +171,16 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_grid(const ExpandA
                     dst[1 + L] = a;
                 }
             }
+            __syncwarp();
+            if (lane == 0) {
+                if (k > t_left) {
+                    W.t_next = fresh + (k - t_left); W.t_left = want - (k - t_left);
+                    W.t_chunk = min(kTupleChunk, 2 * W.t_chunk);
+                }
+                else { W.t_next = t_next + k; W.t_left = t_left - k; }
+                W.n_tup += (unsigned)k;
+            }
+            __syncwarp();
         }
         if (nm) {
             if (ok && !mt.y) {
@@ -163,7 +191,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_grid(const ExpandA
                 dst[1 + L] = a;
             }
             fill += __popc(nm);
-            if (fill + 32 > kStageItems) {   // flush
+            if (fill + 32 > GridWarp<L, G>::kStage) {   // flush
                 __syncwarp();
                 u64 ob = 0;
                 if (lane == 0) ob = atomicAdd(A.out_count, (u64)fill);
@@ -430,6 +458,16 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_grid(const ExpandA
             const int fit = (int)min((long long)fill, A.out_cap - (long long)ob);
             int *dst = A.out + (long long)ob * out_stride;
             for (int i = lane; i < fit * out_stride; i += 32) dst[i] = W.stage[i];
+        }
+    }
+    {   // the unused rest of the warp's last chunk of the tuple list: holes (k_superpose skips a negative pair)
+        const long long t_next = W.t_next;
+        const int t_left = W.t_left;
+        for (int i = lane; i < t_left; i += 32)
+            if (t_next + i < A.tuple_cap) A.tuples[(t_next + i) * A.tuple_stride] = -1;
+        if (lane == 0 && W.n_tup) {
+            atomicAdd(&A.ctr->tuples, (u64)W.n_tup);
+            atomicAdd(&A.ctr->tuple_ints, (u64)W.n_tup * (u64)(L + 1));
         }
     }
 #pragma unroll

@@ -131,7 +131,8 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand_lv(const ExpandArg
         if (cm) {   // finished tuples go straight to the tuple list (one atomic per warp)
             u64 tb = 0;
             if (lane == 0) {
-                tb = atomicAdd(&A.ctr->tuples, (u64)__popc(cm));
+                tb = atomicAdd(&A.ctr->tuple_slots, (u64)__popc(cm));
+                atomicAdd(&A.ctr->tuples, (u64)__popc(cm));
                 atomicAdd(&A.ctr->tuple_ints, (u64)__popc(cm) * (u64)(L + 1));
             }
             tb = __shfl_sync(FULL, tb, 0);

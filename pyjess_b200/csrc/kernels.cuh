@@ -41,6 +41,7 @@ typedef unsigned long long u64;
 
 constexpr int kMaxN = 32;            // JB_MAX_TEMPLATE_ATOMS
 constexpr int kStageItems = 64;      // per-warp staging capacity (items)
+constexpr int kTupleChunk = 64;      // records of the tuple list a warp reserves with one atomic (expand_grid.cuh)
 constexpr int kExpandThreads = 256;
 constexpr int kExpandWarps = kExpandThreads / 32;
 
@@ -185,6 +186,8 @@ struct Counters {              // device counters of one chunk attempt
     u64 scan_tests;            // FP32 box tests actually executed (after x-range narrowing)
     u64 box_pass;              // ... that survived and took the exact FP64 predicate
     u64 tuples;                // full tuples produced
+    u64 tuple_slots;           // records reserved in the tuple list: the level kernels reserve kTupleChunk at a time per warp
+                               // and mark the records a chunk leaves unused as holes (pair = -1); >= tuples
     u64 tuple_ints;            // sum of their sizes
     u64 hits;                  // hits written (absolute, across chunks)
     u64 nan_dropped;
@@ -1091,7 +1094,8 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(const ExpandArgs A
         if (cm) {   // finished tuples go straight to the tuple list (one atomic per warp)
             u64 tb = 0;
             if (lane == 0) {
-                tb = atomicAdd(&A.ctr->tuples, (u64)__popc(cm));
+                tb = atomicAdd(&A.ctr->tuple_slots, (u64)__popc(cm));
+                atomicAdd(&A.ctr->tuples, (u64)__popc(cm));
                 atomicAdd(&A.ctr->tuple_ints, (u64)__popc(cm) * (u64)(l + 1));
             }
             tb = __shfl_sync(FULL, tb, 0);
@@ -1313,7 +1317,7 @@ __global__ void __launch_bounds__(128) k_superpose(const int *tuples, const u64 
     const PairRec *rec = nullptr;
     int n = 0;
     unsigned char inv[kMaxN];   // template atom -> scan level
-    if (i < (long long)n_t) {
+    if (i < (long long)n_t && tuples[i * tuple_stride] >= 0) {      // (a negative pair: a record its chunk left unused)
         tp = tuples + i * tuple_stride;
         rec = recs + tp[0];
         n = rec->n;
