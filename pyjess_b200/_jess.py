@@ -509,8 +509,10 @@ class Query:
         self._run = run
         self._index = index
         self._pos = 0
-        self.ignore_chain = ignore_chain
-        self.max_candidates = max_candidates
+        # (validated once by `query_many`, which also told the run about `max_candidates`: the property setters
+        #  below serve later assignments -- a batch of 1,000 structures creates 1,000 of these objects)
+        self._ignore_chain = ignore_chain
+        self._max_candidates = max_candidates
         self._jess = jess
         self._molecule = molecule
         self._rmsd_threshold = float(rmsd_threshold)
